@@ -1,0 +1,495 @@
+// abi.cu -- the C ABI of libsimilarity_transform.so (include/similarity_transform.h).
+//
+// Part 1 re-exports the two symbols of reference wrapper/similarity_transform.cpp:3-37 on top
+// of the CUDA solver; Part 2 is the additive st_* surface.  Nothing throws across this file.
+#include "similarity_transform.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+
+#include <cuda_runtime.h>
+
+using st::Context;
+using st::Shard;
+
+namespace {
+
+template<typename F>
+int
+guarded(F&& f) noexcept
+{
+  try {
+    return f();
+  } catch (const std::invalid_argument& e) {
+    st::set_last_error(e.what());
+    return ST_ERR_ARG;
+  } catch (const std::bad_alloc&) {
+    st::set_last_error("host allocation failed");
+    return ST_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    st::set_last_error(e.what());
+    return ST_ERR_CUDA;
+  } catch (...) {
+    st::set_last_error("unknown failure");
+    return ST_ERR_CUDA;
+  }
+}
+
+#define ABI_CUDA(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s failed: %s", #call, cudaGetErrorString(e_));                 \
+      throw std::runtime_error(buf_);                                                              \
+    }                                                                                              \
+  } while (0)
+
+Context*
+as_ctx(void* p)
+{
+  if (!p)
+    throw std::invalid_argument("null context");
+  return static_cast<Context*>(p);
+}
+
+Shard*
+as_shard(void* p)
+{
+  if (!p)
+    throw std::invalid_argument("null shard");
+  return static_cast<Shard*>(p);
+}
+
+constexpr size_t kFlagBytes = 128; // ST_MAX_WORLD x 8-byte flags, padded to one line
+
+} // namespace
+
+extern "C" {
+
+// =============================================================================================
+// Part 1 -- drop-in boundary
+// =============================================================================================
+
+void
+make_queue(void** wq)
+{
+  if (!wq)
+    return;
+  *wq = nullptr;
+  guarded([&] {
+    *wq = new Context(0);
+    return ST_OK;
+  });
+}
+
+int64_t
+max_eigen_value(void* wq, float* mat, float* eigen_val, float* eigen_vec, st_uint dim,
+                st_uint* iter_cnt)
+{
+  int64_t ms = -1;
+  const int rc = guarded([&] {
+    if (!mat || !eigen_val || !eigen_vec || !iter_cnt || dim == 0)
+      throw std::invalid_argument("max_eigen_value: null pointer or dim == 0");
+    ms = similarity_transform(*as_ctx(wq), mat, eigen_val, eigen_vec, dim, dim >> 1, iter_cnt);
+    return ms < 0 ? (int)ms : ST_OK;
+  });
+  return rc == ST_OK ? ms : (int64_t)rc;
+}
+
+// =============================================================================================
+// Part 2 -- extensions
+// =============================================================================================
+
+const char*
+st_last_error(void)
+{
+  return st::last_error();
+}
+
+int
+st_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+void
+st_default_options(st_options* opt)
+{
+  if (!opt)
+    return;
+  memset(opt, 0, sizeof *opt);
+  opt->eps = ST_EPS;
+  opt->max_iter = ST_MAX_ITR;
+  opt->form = ST_FORM_READONLY;
+  opt->sweep = 0;
+}
+
+int
+st_create(int device, void** ctx)
+{
+  if (!ctx)
+    return ST_ERR_ARG;
+  *ctx = nullptr;
+  return guarded([&] {
+    *ctx = new Context(device);
+    return ST_OK;
+  });
+}
+
+void
+st_destroy(void* ctx)
+{
+  guarded([&] {
+    delete static_cast<Context*>(ctx);
+    return ST_OK;
+  });
+}
+
+int
+st_device_info(void* ctx, int* sm_count, size_t* l2_bytes, size_t* hbm_bytes, char* name,
+               size_t name_len)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    if (sm_count)
+      *sm_count = c->sm_count();
+    if (l2_bytes)
+      *l2_bytes = c->l2_bytes();
+    if (hbm_bytes)
+      *hbm_bytes = c->hbm_bytes();
+    if (name && name_len) {
+      strncpy(name, c->name().c_str(), name_len - 1);
+      name[name_len - 1] = 0;
+    }
+    return ST_OK;
+  });
+}
+
+int
+st_malloc(void* ctx, size_t bytes, void** dptr)
+{
+  return guarded([&] {
+    if (!dptr)
+      throw std::invalid_argument("st_malloc: null out pointer");
+    as_ctx(ctx)->activate();
+    ABI_CUDA(cudaMalloc(dptr, bytes));
+    return ST_OK;
+  });
+}
+
+int
+st_free(void* ctx, void* dptr)
+{
+  return guarded([&] {
+    as_ctx(ctx)->activate();
+    ABI_CUDA(cudaFree(dptr));
+    return ST_OK;
+  });
+}
+
+int
+st_memcpy_h2d(void* ctx, void* dptr, const void* hptr, size_t bytes)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    c->activate();
+    ABI_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream()));
+    ABI_CUDA(cudaStreamSynchronize(c->stream()));
+    return ST_OK;
+  });
+}
+
+int
+st_memcpy_d2h(void* ctx, void* hptr, const void* dptr, size_t bytes)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    c->activate();
+    ABI_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream()));
+    ABI_CUDA(cudaStreamSynchronize(c->stream()));
+    return ST_OK;
+  });
+}
+
+int
+st_synchronize(void* ctx)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    c->activate();
+    ABI_CUDA(cudaStreamSynchronize(c->stream()));
+    return ST_OK;
+  });
+}
+
+int
+st_generate_hilbert(void* ctx, float* d_rows, uint32_t dim, uint32_t row0, uint32_t rows)
+{
+  return guarded([&] {
+    if (!d_rows || dim == 0 || rows == 0 || (uint64_t)row0 + rows > dim)
+      throw std::invalid_argument("st_generate_hilbert: bad row range");
+    return generate_hilbert_matrix(*as_ctx(ctx), d_rows, dim, row0, rows);
+  });
+}
+
+int
+st_generate_uniform(void* ctx, float* d_rows, uint32_t dim, uint32_t row0, uint32_t rows,
+                    uint64_t seed)
+{
+  return guarded([&] {
+    if (!d_rows || dim == 0 || rows == 0 || (uint64_t)row0 + rows > dim)
+      throw std::invalid_argument("st_generate_uniform: bad row range");
+    return generate_uniform_matrix(*as_ctx(ctx), d_rows, dim, seed, row0, rows);
+  });
+}
+
+int
+st_solve_device(void* ctx, const float* d_mat, uint32_t dim, const st_options* opt,
+                float* d_eigen_vec, st_result* res)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve(d_mat, dim, o, nullptr, d_eigen_vec, res);
+  });
+}
+
+int
+st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt,
+              float* h_eigen_val, float* h_eigen_vec, st_result* res)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve_host(h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
+  });
+}
+
+int
+st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    const auto& ts = c->round_timestamps();
+    const uint32_t n = (uint32_t)std::min<size_t>(ts.size(), capacity);
+    if (out)
+      memcpy(out, ts.data(), sizeof(uint64_t) * n);
+    if (count)
+      *count = (uint32_t)ts.size();
+    return ST_OK;
+  });
+}
+
+// ---- per-kernel entry points ------------------------------------------------------------------
+int
+st_sum_across_rows(void* ctx, const float* d_mat, float* d_vec, uint32_t dim)
+{
+  return guarded([&] { return sum_across_rows(*as_ctx(ctx), d_mat, d_vec, dim, 0); });
+}
+int
+st_row_pass_readonly(void* ctx, const float* d_rows, const float* d_e, float* d_vec, uint32_t dim,
+                     uint32_t row0, uint32_t rows)
+{
+  return guarded([&] {
+    if (!d_rows || !d_e || !d_vec || rows == 0 || (uint64_t)row0 + rows > dim)
+      throw std::invalid_argument("st_row_pass_readonly: bad argument");
+    return row_pass_readonly(*as_ctx(ctx), d_rows, d_e, d_vec, dim, row0, rows);
+  });
+}
+int
+st_find_max(void* ctx, const float* d_vec, float* d_max, uint32_t dim)
+{
+  return guarded([&] { return find_max(*as_ctx(ctx), d_vec, d_max, dim, 0); });
+}
+int
+st_compute_eigen_vector(void* ctx, const float* d_vec, const float* d_max, float* d_eigen_vec,
+                        uint32_t dim)
+{
+  return guarded([&] { return compute_eigen_vector(*as_ctx(ctx), d_vec, d_max, d_eigen_vec, dim, 0); });
+}
+int
+st_initialise_eigen_vector(void* ctx, float* d_eigen_vec, uint32_t dim)
+{
+  return guarded([&] { return initialise_eigen_vector(*as_ctx(ctx), d_eigen_vec, dim); });
+}
+int
+st_compute_next_matrix(void* ctx, float* d_mat, const float* d_vec, uint32_t dim)
+{
+  return guarded([&] { return compute_next_matrix(*as_ctx(ctx), d_mat, d_vec, dim, 0); });
+}
+int
+st_stop(void* ctx, const float* d_vec, uint32_t* d_ret, uint32_t dim, float eps)
+{
+  return guarded([&] { return stop(*as_ctx(ctx), d_vec, d_ret, dim, 0, eps); });
+}
+
+// ---- row-block sharding -------------------------------------------------------------------------
+int
+st_shard_create(void* ctx, uint32_t dim, uint32_t rank, uint32_t world, void** shard)
+{
+  if (!shard)
+    return ST_ERR_ARG;
+  *shard = nullptr;
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    if (dim == 0 || world == 0 || world > ST_MAX_WORLD || rank >= world || world > dim)
+      throw std::invalid_argument("st_shard_create: bad rank/world/dim");
+    c->activate();
+    Shard* s = new Shard();
+    s->ctx = c;
+    s->dim = dim;
+    s->rank = rank;
+    s->world = world;
+    s->row0 = (uint32_t)((uint64_t)dim * rank / world);
+    s->rows = (uint32_t)((uint64_t)dim * (rank + 1) / world) - s->row0;
+    const size_t vec_bytes = (((size_t)dim * sizeof(float)) + 127) & ~(size_t)127;
+    s->s_offset[0] = kFlagBytes;
+    s->s_offset[1] = kFlagBytes + vec_bytes;
+    s->block_bytes = kFlagBytes + 2 * vec_bytes;
+    cudaError_t e = cudaMalloc(&s->block, s->block_bytes);
+    if (e != cudaSuccess) {
+      delete s;
+      throw std::runtime_error(std::string("cudaMalloc(exchange block): ") + cudaGetErrorString(e));
+    }
+    ABI_CUDA(cudaMemset(s->block, 0, s->block_bytes));
+    s->peer_block[rank] = s->block;
+    s->linked = (world == 1);
+    *shard = s;
+    return ST_OK;
+  });
+}
+
+int
+st_shard_export(void* shard, void* handle_out)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    if (!handle_out)
+      throw std::invalid_argument("st_shard_export: null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == ST_IPC_HANDLE_BYTES, "IPC handle size");
+    s->ctx->activate();
+    cudaIpcMemHandle_t h;
+    ABI_CUDA(cudaIpcGetMemHandle(&h, s->block));
+    memcpy(handle_out, &h, sizeof h);
+    return ST_OK;
+  });
+}
+
+int
+st_shard_import(void* shard, const void* handles)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    if (!handles)
+      throw std::invalid_argument("st_shard_import: null handle table");
+    s->ctx->activate();
+    const char* tab = static_cast<const char*>(handles);
+    for (uint32_t g = 0; g < s->world; g++) {
+      if (g == s->rank)
+        continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, tab + (size_t)g * ST_IPC_HANDLE_BYTES, sizeof h);
+      void* p = nullptr;
+      ABI_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      s->peer_block[g] = p;
+      s->peer_is_ipc[g] = true;
+    }
+    s->linked = true;
+    return ST_OK;
+  });
+}
+
+int
+st_shard_link_local(void** shards, uint32_t world)
+{
+  return guarded([&] {
+    if (!shards || world == 0 || world > ST_MAX_WORLD)
+      throw std::invalid_argument("st_shard_link_local: bad world");
+    for (uint32_t a = 0; a < world; a++) {
+      Shard* sa = as_shard(shards[a]);
+      if (sa->rank != a || sa->world != world)
+        throw std::invalid_argument("st_shard_link_local: shards must be passed in rank order");
+      sa->ctx->activate();
+      for (uint32_t b = 0; b < world; b++) {
+        Shard* sb = as_shard(shards[b]);
+        if (a != b && sa->ctx->device() != sb->ctx->device()) {
+          int can = 0;
+          ABI_CUDA(cudaDeviceCanAccessPeer(&can, sa->ctx->device(), sb->ctx->device()));
+          if (!can)
+            throw std::runtime_error("st_shard_link_local: no peer access between the devices");
+          cudaError_t e = cudaDeviceEnablePeerAccess(sb->ctx->device(), 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            throw std::runtime_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+          (void)cudaGetLastError();
+        }
+        sa->peer_block[b] = sb->block;
+      }
+      sa->linked = true;
+    }
+    return ST_OK;
+  });
+}
+
+int
+st_shard_rows(void* shard, uint32_t* row0, uint32_t* rows)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    if (row0)
+      *row0 = s->row0;
+    if (rows)
+      *rows = s->rows;
+    return ST_OK;
+  });
+}
+
+int
+st_shard_solve(void* shard, const float* d_rows, const st_options* opt, float* d_eigen_vec,
+               st_result* res)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(s->ctx->mutex());
+    return s->ctx->solve(d_rows, s->dim, o, s, d_eigen_vec, res);
+  });
+}
+
+void
+st_shard_destroy(void* shard)
+{
+  guarded([&] {
+    Shard* s = static_cast<Shard*>(shard);
+    if (!s)
+      return ST_OK;
+    s->ctx->activate();
+    for (uint32_t g = 0; g < s->world; g++)
+      if (s->peer_is_ipc[g] && s->peer_block[g])
+        cudaIpcCloseMemHandle(s->peer_block[g]);
+    cudaFree(s->block);
+    delete s;
+    return ST_OK;
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,694 @@
+// kernels.cuh -- sm_100a device code for the similarity_transform() round loop.
+//
+// One persistent, cooperatively launched kernel (round_loop_kernel) runs the WHOLE loop of
+// reference similarity_transform.cpp:39-53 on the device: per round it makes a single
+// 128-bit-vectorised pass over this GPU's rows of the matrix, reduces each row inside one
+// warp (shuffle tree, no atomics, deterministic), publishes the row sums (to peer GPUs too
+// when the matrix is row-block sharded), crosses ONE grid-wide barrier, and then every CTA
+// redundantly reduces the N-length row-sum vector to the max, the circular stop flag and the
+// next eigenvector -- the work of the reference's five kernels + three fills + blocking
+// host read per round (:40-52).
+//
+// The small standalone kernels at the bottom are the per-kernel entry points mirroring the
+// reference's L1 functions (similarity_transform.cpp:77-460) and the input generators
+// (utils.cpp:136-154, :124-134).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+constexpr int kMaxWorld = 8;      // ST_MAX_WORLD
+constexpr int kChunkCols = 8192;  // columns of the scale vector staged in shared memory at a time
+constexpr int kUnroll = 8;        // independent 128-bit loads in flight per lane
+
+enum : int
+{
+  kFormReadOnly = 0, // s = (A.e)/e
+  kFormInPlace = 1   // W <- D^-1 W D, s = rowsum(W)
+};
+
+// Barrier words live on their own 128-byte lines.
+struct alignas(128) BarrierState
+{
+  unsigned int count; // monotonically increasing arrival counter
+  unsigned int pad0[31];
+  unsigned int gen; // number of completed barriers
+  unsigned int pad1[31];
+  unsigned int error; // set by any CTA whose wait timed out
+  unsigned int pad2[31];
+};
+
+struct RoundParams
+{
+  const float* A; // this GPU's rows of the input: rows x N, row-major (never written)
+  float* W;       // in-place form only: working copy, rows x N
+  uint32_t N;     // matrix dimension
+  uint32_t row0;  // first global row owned by this GPU
+  uint32_t rows;  // rows owned by this GPU
+  float* S[2];    // full-length row-sum vectors, double-buffered by round parity (local)
+  float* E[2];    // full-length eigenvector, double-buffered by round parity (local)
+  float eps;
+  uint32_t max_iter;
+  int sweep;           // 1: alternate the row order every round (L2 reuse of the pass tail)
+  uint32_t chunk_cols; // columns staged per chunk (<= kChunkCols)
+  BarrierState* bar;
+  unsigned long long timeout_ns;
+  // row-block sharding (world == 1: unused)
+  uint32_t rank, world;
+  float* peer_S[2][kMaxWorld];            // S buffers of every rank (own entry == S[b])
+  unsigned long long* peer_flags[kMaxWorld]; // flag array of every rank; slot [src rank]
+  unsigned long long* flags;              // this rank's flag array (written by the peers)
+  unsigned long long epoch;               // solve counter << 32; flags are never reset
+  // results
+  float* out_eigen_vec;  // N floats (device)
+  float* out_eigen_val;  // 1 float  (device)
+  uint32_t* out_iter;    // [0] iter_count, [1] passes
+  unsigned long long* round_ts; // max_iter + 1 globaltimer stamps
+};
+
+// ---------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long
+globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned int
+ld_acquire_gpu(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void
+st_release_gpu(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long
+ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void
+st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Streaming 128-bit load of matrix data that is never written while the kernel runs:
+// read-only path, no L1 allocation (each byte is used exactly once per round).
+__device__ __forceinline__ float4
+ld_stream(const float4* p)
+{
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float
+ld_stream(const float* p)
+{
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// L2-coherent loads/stores for data other CTAs (or other GPUs) write during the kernel.
+__device__ __forceinline__ float
+ld_cg(const float* p)
+{
+  return __ldcg(p);
+}
+__device__ __forceinline__ float4
+ld_cg(const float4* p)
+{
+  return __ldcg(p);
+}
+
+__device__ __forceinline__ float
+warp_sum(float v)
+{
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// one row segment, one warp
+// ---------------------------------------------------------------------------------------
+template<int VEC>
+struct Vec;
+template<>
+struct Vec<4>
+{
+  using type = float4;
+};
+template<>
+struct Vec<1>
+{
+  using type = float;
+};
+
+__device__ __forceinline__ float
+dot_acc(float4 a, float4 e, float acc)
+{
+  acc = fmaf(a.x, e.x, acc);
+  acc = fmaf(a.y, e.y, acc);
+  acc = fmaf(a.z, e.z, acc);
+  acc = fmaf(a.w, e.w, acc);
+  return acc;
+}
+__device__ __forceinline__ float
+dot_acc(float a, float e, float acc)
+{
+  return fmaf(a, e, acc);
+}
+
+// Read-only form: sum over one row segment of A[r][c] * e[c]; e staged in shared memory.
+// Fixed evaluation order (depends on the segment length only): lane l owns vectors
+// l, l+32, ...; vector j of a batch goes to accumulator j; accumulators are folded pairwise,
+// then the 32 lanes by an xor-shuffle tree.  All lanes return the sum.
+template<int VEC>
+__device__ __forceinline__ float
+row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, int lane)
+{
+  using V = typename Vec<VEC>::type;
+  const V* __restrict__ a = reinterpret_cast<const V*>(row);
+  const V* es = reinterpret_cast<const V*>(e_s);
+  const uint32_t nv = len / VEC;
+  float acc[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++)
+    acc[u] = 0.f;
+  uint32_t i = (uint32_t)lane;
+  for (; i + 32u * (kUnroll - 1) < nv; i += 32u * kUnroll) {
+    V v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+      v[u] = ld_stream(a + i + 32u * u);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+      acc[u] = dot_acc(v[u], es[i + 32u * u], acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++) {
+    const uint32_t j = i + 32u * u;
+    if (j < nv)
+      acc[u] = dot_acc(ld_stream(a + j), es[j], acc[u]);
+  }
+#pragma unroll
+  for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+    for (int u = 0; u < s; u++)
+      acc[u] += acc[u + s];
+  return warp_sum(acc[0]);
+}
+
+__device__ __forceinline__ float4
+rescale(float4 w, float inv_r, float4 sc)
+{
+  // W[r][c] *= (1.f / s[r]) * s[c]        reference similarity_transform.cpp:324-325
+  w.x *= inv_r * sc.x;
+  w.y *= inv_r * sc.y;
+  w.z *= inv_r * sc.z;
+  w.w *= inv_r * sc.w;
+  return w;
+}
+__device__ __forceinline__ float
+rescale(float w, float inv_r, float sc)
+{
+  return w * (inv_r * sc);
+}
+__device__ __forceinline__ float
+sum_acc(float4 w, float acc)
+{
+  acc += w.x;
+  acc += w.y;
+  acc += w.z;
+  acc += w.w;
+  return acc;
+}
+__device__ __forceinline__ float
+sum_acc(float w, float acc)
+{
+  return acc + w;
+}
+
+// In-place form: (first pass) copy A -> W and sum it, (later passes) rescale W in place by
+// (1/s_prev[r]) * s_prev[c] and sum the new values.  Same lane/accumulator order as above.
+template<int VEC, bool FIRST>
+__device__ __forceinline__ float
+row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, float inv_r,
+                 uint32_t len, int lane)
+{
+  using V = typename Vec<VEC>::type;
+  const V* a = reinterpret_cast<const V*>(src);
+  V* w = reinterpret_cast<V*>(dst);
+  const V* ss = reinterpret_cast<const V*>(sc_s);
+  const uint32_t nv = len / VEC;
+  float acc[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++)
+    acc[u] = 0.f;
+  uint32_t i = (uint32_t)lane;
+  for (; i + 32u * (kUnroll - 1) < nv; i += 32u * kUnroll) {
+    V v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+      v[u] = FIRST ? ld_stream(a + i + 32u * u) : ld_cg(a + i + 32u * u);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      if (!FIRST)
+        v[u] = rescale(v[u], inv_r, ss[i + 32u * u]);
+      __stcg(w + i + 32u * u, v[u]);
+      acc[u] = sum_acc(v[u], acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++) {
+    const uint32_t j = i + 32u * u;
+    if (j < nv) {
+      V v = FIRST ? ld_stream(a + j) : ld_cg(a + j);
+      if (!FIRST)
+        v = rescale(v, inv_r, ss[j]);
+      __stcg(w + j, v);
+      acc[u] = sum_acc(v, acc[u]);
+    }
+  }
+#pragma unroll
+  for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+    for (int u = 0; u < s; u++)
+      acc[u] += acc[u + s];
+  return warp_sum(acc[0]);
+}
+
+// ---------------------------------------------------------------------------------------
+// grid-wide (and, when sharded, cross-GPU) barrier at the end of round k
+// ---------------------------------------------------------------------------------------
+// Every CTA has written its row sums (locally and into every peer's S buffer).  The last CTA
+// to arrive signals the peers with one 64-bit release store each and waits for theirs, then
+// releases the local CTAs.  All waits are bounded by timeout_ns so that a missing rank turns
+// into an error code instead of a hung GPU.  Returns false on timeout.
+__device__ __forceinline__ bool
+round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int fail = 0;
+    if (p.world > 1)
+      __threadfence_system();
+    else
+      __threadfence();
+    const unsigned int target = (k + 1u) * gridDim.x;
+    const unsigned int prev = atomicAdd(&p.bar->count, 1u);
+    const unsigned long long t0 = globaltimer_ns();
+    if (prev + 1u == target) {
+      if (p.world > 1) {
+        __threadfence_system();
+        const unsigned long long want = p.epoch + (unsigned long long)(k + 1u);
+        for (uint32_t g = 0; g < p.world; g++)
+          if (g != p.rank)
+            st_release_sys(p.peer_flags[g] + p.rank, want);
+        for (uint32_t g = 0; g < p.world && !fail; g++) {
+          if (g == p.rank)
+            continue;
+          unsigned int spins = 0;
+          while (ld_acquire_sys(p.flags + g) < want) {
+            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > p.timeout_ns) {
+              fail = 1;
+              break;
+            }
+          }
+        }
+        if (fail)
+          atomicExch(&p.bar->error, 1u);
+      }
+      st_release_gpu(&p.bar->gen, k + 1u);
+    } else {
+      unsigned int spins = 0;
+      while (ld_acquire_gpu(&p.bar->gen) < k + 1u) {
+        if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > 2ull * p.timeout_ns) {
+          atomicExch(&p.bar->error, 1u);
+          fail = 1;
+          break;
+        }
+      }
+    }
+    if (!fail && ld_acquire_gpu(&p.bar->error) != 0u)
+      fail = 1;
+    __threadfence();
+    *s_abort = fail;
+  }
+  __syncthreads();
+  return *s_abort == 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// the round loop
+// ---------------------------------------------------------------------------------------
+template<int VEC, int FORM, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParams p)
+{
+  extern __shared__ __align__(16) float smem[];
+  float* scale_s = smem;               // chunk_cols floats: e (read-only) or s_prev (in-place)
+  float* part_s = smem + p.chunk_cols; // one partial row sum per owned row
+  __shared__ float red_max[32];
+  __shared__ int red_ok[32];
+  __shared__ float bc_max;
+  __shared__ int bc_ok;
+  __shared__ int s_abort;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  constexpr int kWarps = THREADS / 32;
+  const uint32_t N = p.N;
+
+  // rows of this GPU's block owned by this CTA, and the slice of the N-vector it maintains
+  const uint32_t rb = (uint32_t)((uint64_t)p.rows * blockIdx.x / gridDim.x);
+  const uint32_t re = (uint32_t)((uint64_t)p.rows * (blockIdx.x + 1) / gridDim.x);
+  const uint32_t nrows = re - rb;
+  const uint32_t cb = (uint32_t)((uint64_t)N * blockIdx.x / gridDim.x);
+  const uint32_t ce = (uint32_t)((uint64_t)N * (blockIdx.x + 1) / gridDim.x);
+
+  if (blockIdx.x == 0 && tid == 0)
+    p.round_ts[0] = globaltimer_ns();
+
+  float m_prev = 1.f;
+  for (uint32_t k = 0;; ++k) {
+    const float* Sprev = p.S[(k + 1) & 1];
+    const float* Eprev = p.E[(k + 1) & 1];
+    float* Scur = p.S[k & 1];
+    float* Ecur = p.E[k & 1];
+    const bool first = (k == 0);
+
+    // e_k = e_{k-1} * (s_{k-1} / m_{k-1})          reference :42-43 -> :260; e_0 = 1 (:34 -> :280)
+    for (uint32_t c = cb + tid; c < ce; c += THREADS)
+      Ecur[c] = first ? 1.f : ld_cg(Eprev + c) * (ld_cg(Sprev + c) / m_prev);
+    for (uint32_t r = tid; r < nrows; r += THREADS)
+      part_s[r] = 0.f;
+
+    // ---- the pass over the matrix ----                                   reference :40 (+ :52)
+    const bool backward = p.sweep && (k & 1);
+    for (uint32_t c0 = 0; c0 < N; c0 += p.chunk_cols) {
+      const uint32_t clen = min(p.chunk_cols, N - c0);
+      __syncthreads();
+      for (uint32_t c = tid; c < clen; c += THREADS) {
+        float v = 1.f;
+        if (!first) {
+          const float sp = ld_cg(Sprev + c0 + c);
+          v = (FORM == kFormReadOnly) ? ld_cg(Eprev + c0 + c) * (sp / m_prev) : sp;
+        }
+        scale_s[c] = v;
+      }
+      __syncthreads();
+      for (uint32_t i = warp; i < nrows; i += kWarps) {
+        const uint32_t rl = backward ? (nrows - 1u - i) : i;
+        const size_t off = (size_t)(rb + rl) * N + c0;
+        float t;
+        if (FORM == kFormReadOnly) {
+          t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
+        } else if (first) {
+          t = row_pass_inplace<VEC, true>(p.A + off, p.W + off, scale_s, 1.f, clen, lane);
+        } else {
+          const float inv_r = 1.f / ld_cg(Sprev + p.row0 + rb + rl);
+          t = row_pass_inplace<VEC, false>(p.W + off, p.W + off, scale_s, inv_r, clen, lane);
+        }
+        if (lane == 0)
+          part_s[rl] += t;
+      }
+    }
+    __syncthreads();
+
+    // ---- publish this CTA's row sums (to every rank when sharded) ----
+    for (uint32_t r = tid; r < nrows; r += THREADS) {
+      const uint32_t gr = p.row0 + rb + r;
+      float s = part_s[r];
+      if (FORM == kFormReadOnly && !first)
+        s = s / (ld_cg(Eprev + gr) * (ld_cg(Sprev + gr) / m_prev));
+      if (p.world > 1) {
+        for (uint32_t g = 0; g < p.world; g++)
+          __stcg(p.peer_S[k & 1][g] + gr, s);
+      } else {
+        __stcg(Scur + gr, s);
+      }
+    }
+
+    if (!round_barrier(p, k, &s_abort))
+      return;
+
+    // ---- every CTA: max, circular stop test over the full vector ----   reference :41, :44
+    float mx = 0.f; // reference zero-fills the max cell (:169)
+    int ok = 1;
+    for (uint32_t c = tid; c < N; c += THREADS) {
+      const float self = ld_cg(Scur + c);
+      const float next = ld_cg(Scur + (c + 1u == N ? 0u : c + 1u));
+      mx = fmaxf(mx, self);
+      ok &= (fabsf(self - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if (lane == 0) {
+      red_max[warp] = mx;
+      red_ok[warp] = ok;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      mx = lane < kWarps ? red_max[lane] : 0.f;
+      ok = lane < kWarps ? red_ok[lane] : 1;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+      }
+      if (lane == 0) {
+        bc_max = mx;
+        bc_ok = ok;
+      }
+    }
+    __syncthreads();
+    const float m_k = bc_max;
+    const bool converged = bc_ok != 0;
+
+    if (blockIdx.x == 0 && tid == 0)
+      p.round_ts[k + 1] = globaltimer_ns();
+
+    if (converged || k + 1u == p.max_iter) {
+      // the eigenvector update of this round still happens before the break (:42-50)
+      for (uint32_t c = cb + tid; c < ce; c += THREADS)
+        p.out_eigen_vec[c] = ld_cg(Ecur + c) * (ld_cg(Scur + c) / m_k);
+      if (blockIdx.x == 0 && tid == 0) {
+        *p.out_eigen_val = ld_cg(Scur);                  // :60-65
+        p.out_iter[0] = converged ? k : p.max_iter;      // :54
+        p.out_iter[1] = k + 1u;
+      }
+      return;
+    }
+    m_prev = m_k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-kernel entry points (reference L1 functions) -- small, not on the fused path
+// ---------------------------------------------------------------------------------------
+
+// sum_across_rows()  reference similarity_transform.cpp:77-152: one warp per row, same
+// evaluation order as the fused kernel.  With e == nullptr it is the plain row sum
+// (vec[r] = sum_c mat[r][c]); with e it is one read-only round's row pass for rows
+// [row0, row0+rows): vec[row0+r] = (sum_c mat[r][c] * e[c]) / e[row0+r]  -- the unfused
+// building block of the collective (NCCL) variant of the sharded loop.
+template<int VEC>
+__global__ void __launch_bounds__(256) sum_across_rows_kernel(const float* __restrict__ mat,
+                                                              const float* __restrict__ e,
+                                                              float* __restrict__ vec, uint32_t dim,
+                                                              uint32_t row0, uint32_t rows)
+{
+  extern __shared__ __align__(16) float scale_s[];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t chunk = min((uint32_t)kChunkCols, dim);
+  const bool single = chunk == dim;
+  for (uint32_t c0 = 0; c0 < dim; c0 += chunk) {
+    const uint32_t clen = min(chunk, dim - c0);
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < clen; c += blockDim.x)
+      scale_s[c] = e ? e[c0 + c] : 1.f;
+    __syncthreads();
+    for (uint32_t r = gw; r < rows; r += warps) {
+      const float t = row_dot_readonly<VEC>(mat + (size_t)r * dim + c0, scale_s, clen, lane);
+      if (lane == 0) {
+        const float acc = (c0 == 0 ? 0.f : vec[row0 + r]) + t;
+        const bool last = single || c0 + clen == dim;
+        vec[row0 + r] = (last && e) ? acc / e[row0 + r] : acc;
+      }
+    }
+  }
+}
+
+// find_max()  reference :154-227 -- single CTA, m = max(0, max_r s[r]).
+__global__ void __launch_bounds__(1024) find_max_kernel(const float* __restrict__ vec,
+                                                        float* __restrict__ out, uint32_t dim)
+{
+  __shared__ float red[32];
+  float mx = 0.f;
+  for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x)
+    mx = fmaxf(mx, vec[c]);
+  for (int o = 16; o >= 1; o >>= 1)
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o >= 1; o >>= 1)
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0)
+      *out = mx;
+  }
+}
+
+// compute_eigen_vector()  reference :229-265: e[r] *= s[r] / m
+__global__ void
+compute_eigen_vector_kernel(const float* __restrict__ vec, const float* __restrict__ mx,
+                            float* __restrict__ eigen_vec, uint32_t dim)
+{
+  const float m = *mx;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += gridDim.x * blockDim.x)
+    eigen_vec[r] *= (vec[r] / m);
+}
+
+// initialise_eigen_vector()  reference :267-284
+__global__ void
+fill_kernel(float* __restrict__ v, float value, uint32_t dim)
+{
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += gridDim.x * blockDim.x)
+    v[r] = value;
+}
+
+// stop()  reference :332-460 -- single CTA; ret = 1 iff every circular adjacent pair differs by < eps
+__global__ void __launch_bounds__(1024) stop_kernel(const float* __restrict__ vec,
+                                                    uint32_t* __restrict__ ret, uint32_t dim, float eps)
+{
+  int ok = 1;
+  for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) {
+    const float self = vec[c];
+    const float next = vec[c + 1u == dim ? 0u : c + 1u];
+    ok &= (fabsf(self - next) < eps) ? 1 : 0;
+  }
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0)
+    *ret = ok ? 1u : 0u;
+}
+
+// compute_next_matrix()  reference :286-330: W[r][c] *= (1.f / s[r]) * s[c]
+template<int VEC>
+__global__ void __launch_bounds__(256) compute_next_matrix_kernel(float* __restrict__ mat,
+                                                                  const float* __restrict__ vec,
+                                                                  uint32_t dim)
+{
+  using V = typename Vec<VEC>::type;
+  const uint32_t nv = dim / VEC;
+  for (uint32_t r = blockIdx.y; r < dim; r += gridDim.y) {
+    const float inv_r = 1.f / vec[r];
+    V* row = reinterpret_cast<V*>(mat + (size_t)r * dim);
+    const V* sc = reinterpret_cast<const V*>(vec);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nv; j += gridDim.x * blockDim.x)
+      row[j] = rescale(row[j], inv_r, sc[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// input generation
+// ---------------------------------------------------------------------------------------
+
+// generate_hilbert_matrix()  reference utils.cpp:136-154: A[r][c] = 1.f / (float)(r + c + 1)
+// (IEEE-rounded division; r + c + 1 < 2^24 up to N = 2^23 so the cast is exact.)
+__global__ void __launch_bounds__(256) hilbert_kernel(float* __restrict__ out, uint32_t dim,
+                                                      uint32_t row0, uint32_t rows)
+{
+  for (uint32_t i = blockIdx.y; i < rows; i += gridDim.y) {
+    float* row = out + (size_t)i * dim;
+    const uint32_t base = row0 + i + 1u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x)
+      row[c] = __fdiv_rn(1.f, (float)(base + c));
+  }
+}
+
+// Philox-4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): counter (ctr, 0), key = seed.
+__device__ __forceinline__ uint4
+philox4x32_10(unsigned long long ctr, unsigned long long key)
+{
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float
+u01_open_closed(uint32_t x)
+{
+  return (float)((x >> 8) + 1u) * 5.9604644775390625e-08f; // (0, 1]
+}
+
+// Seeded uniform (0,1] fill; element idx = r*dim + c takes word idx%4 of Philox block idx/4,
+// so the values do not depend on how the rows are sharded.
+__global__ void __launch_bounds__(256) uniform_kernel(float* __restrict__ out, uint32_t dim,
+                                                      uint32_t row0, uint32_t rows,
+                                                      unsigned long long seed)
+{
+  const unsigned long long first = (unsigned long long)row0 * dim;
+  const unsigned long long last = first + (unsigned long long)rows * dim; // exclusive
+  const unsigned long long blk0 = first >> 2;
+  const unsigned long long nblk = ((last + 3ull) >> 2) - blk0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk;
+       b += stride) {
+    const unsigned long long blk = blk0 + b;
+    const uint4 w = philox4x32_10(blk, seed);
+    const unsigned long long base = blk << 2;
+    const float v[4] = { u01_open_closed(w.x), u01_open_closed(w.y), u01_open_closed(w.z),
+                         u01_open_closed(w.w) };
+    if (base >= first && base + 3ull < last && (((base - first) & 3ull) == 0ull)) {
+      *reinterpret_cast<float4*>(out + (base - first)) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned long long idx = base + j;
+        if (idx >= first && idx < last)
+          out[idx - first] = v[j];
+      }
+    }
+  }
+}
+
+} // namespace st

@@ -1,0 +1,471 @@
+// solver.cu -- host side of the B200 similarity_transform(): context, scratch, launches.
+//
+// Replaces the host loop of reference similarity_transform.cpp:5-75 (8 queue submissions and
+// one blocking host read per round) by ONE cooperative launch of st::round_loop_kernel; the
+// host only stages buffers, launches, and reads back (lambda, iter_count, timestamps).
+#include "similarity_transform.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace st {
+
+// ---- error plumbing -----------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void
+set_last_error(const std::string& msg)
+{
+  g_last_error = msg;
+}
+const char*
+last_error()
+{
+  return g_last_error.c_str();
+}
+
+struct CudaError : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+#define ST_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),          \
+               __FILE__, __LINE__);                                                                \
+      throw ::st::CudaError(buf_);                                                                 \
+    }                                                                                              \
+  } while (0)
+
+// ---- Context --------------------------------------------------------------------------------
+Context::Context(int device)
+  : device_(device)
+{
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+    throw CudaError("no usable CUDA device");
+  ST_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop{};
+  ST_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10)
+    throw CudaError(std::string("device is not sm_100-class: ") + prop.name);
+  int coop = 0;
+  ST_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+  if (!coop)
+    throw CudaError("device does not support cooperative launch");
+  sm_count_ = prop.multiProcessorCount;
+  l2_bytes_ = (size_t)prop.l2CacheSize;
+  hbm_bytes_ = prop.totalGlobalMem;
+  name_ = prop.name;
+  ST_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  ST_CUDA(cudaEventCreate(&ev0_));
+  ST_CUDA(cudaEventCreate(&ev1_));
+  ST_CUDA(cudaMalloc(&d_bar_, sizeof(BarrierState)));
+  ST_CUDA(cudaMalloc(&d_scalars_, 64));
+  ST_CUDA(cudaHostAlloc(&h_pinned_, 64, cudaHostAllocDefault));
+}
+
+Context::~Context()
+{
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  cudaFree(d_vec_);
+  cudaFree(d_ts_);
+  cudaFree(d_bar_);
+  cudaFree(d_scalars_);
+  cudaFree(d_mat_);
+  cudaFree(d_work_);
+  cudaFreeHost(h_pinned_);
+  cudaEventDestroy(ev0_);
+  cudaEventDestroy(ev1_);
+  cudaStreamDestroy(stream_);
+}
+
+void
+Context::activate() const
+{
+  ST_CUDA(cudaSetDevice(device_));
+}
+
+void
+Context::reserve_vectors(uint32_t dim, uint32_t max_iter)
+{
+  const uint32_t need = (dim + 31u) & ~31u;
+  if (need > vec_cap_) {
+    cudaFree(d_vec_);
+    d_vec_ = nullptr;
+    vec_cap_ = 0;
+    ST_CUDA(cudaMalloc(&d_vec_, sizeof(float) * 5 * (size_t)need));
+    vec_cap_ = need;
+  }
+  if (max_iter + 2 > ts_cap_) {
+    cudaFree(d_ts_);
+    d_ts_ = nullptr;
+    ts_cap_ = 0;
+    ST_CUDA(cudaMalloc(&d_ts_, sizeof(unsigned long long) * (size_t)(max_iter + 2)));
+    ts_cap_ = max_iter + 2;
+  }
+}
+
+void
+Context::reserve_matrix(size_t elems)
+{
+  if (elems > mat_cap_) {
+    cudaFree(d_mat_);
+    d_mat_ = nullptr;
+    mat_cap_ = 0;
+    ST_CUDA(cudaMalloc(&d_mat_, sizeof(float) * elems));
+    mat_cap_ = elems;
+  }
+}
+
+void
+Context::reserve_work(size_t elems)
+{
+  if (elems > work_cap_) {
+    cudaFree(d_work_);
+    d_work_ = nullptr;
+    work_cap_ = 0;
+    ST_CUDA(cudaMalloc(&d_work_, sizeof(float) * elems));
+    work_cap_ = elems;
+  }
+}
+
+// ---- launch of the round loop ------------------------------------------------------------
+template<int VEC, int FORM, int THREADS>
+static void
+launch_round_loop(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_kernel<VEC, FORM, THREADS>;
+  if (smem > 48 * 1024)
+    ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
+                                      stream));
+}
+
+template<int VEC, int FORM>
+static void
+launch_by_threads(int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  switch (threads) {
+    case 256:
+      return launch_round_loop<VEC, FORM, 256>(p, grid, smem, stream);
+    case 1024:
+      return launch_round_loop<VEC, FORM, 1024>(p, grid, smem, stream);
+    default:
+      return launch_round_loop<VEC, FORM, 512>(p, grid, smem, stream);
+  }
+}
+
+static bool
+aligned16(const void* p)
+{
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+int
+Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
+               float* d_eigen_vec, st_result* res)
+{
+  if (!d_rows || dim == 0 || opt.max_iter == 0 || !(opt.eps >= 0.f))
+    throw std::invalid_argument("solve: bad argument");
+  if (shard && (shard->dim != dim || !shard->linked))
+    throw std::invalid_argument("solve: shard not linked or dimension mismatch");
+  const auto host_t0 = std::chrono::steady_clock::now();
+  activate();
+  reserve_vectors(dim, opt.max_iter);
+
+  const uint32_t row0 = shard ? shard->row0 : 0u;
+  const uint32_t rows = shard ? shard->rows : dim;
+  const int form = opt.form == ST_FORM_INPLACE ? kFormInPlace : kFormReadOnly;
+
+  RoundParams p{};
+  p.A = d_rows;
+  p.W = nullptr;
+  if (form == kFormInPlace) {
+    reserve_work((size_t)rows * dim);
+    p.W = d_work_;
+  }
+  p.N = dim;
+  p.row0 = row0;
+  p.rows = rows;
+  float* v = d_vec_;
+  const size_t cap = vec_cap_;
+  p.S[0] = v;
+  p.S[1] = v + cap;
+  p.E[0] = v + 2 * cap;
+  p.E[1] = v + 3 * cap;
+  float* d_out_vec = d_eigen_vec ? d_eigen_vec : v + 4 * cap;
+  p.eps = opt.eps;
+  p.max_iter = opt.max_iter;
+  p.sweep = opt.sweep;
+  p.chunk_cols = std::min<uint32_t>((uint32_t)kChunkCols, dim);
+  p.bar = d_bar_;
+  p.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+  p.rank = shard ? shard->rank : 0u;
+  p.world = shard ? shard->world : 1u;
+  if (shard) {
+    for (uint32_t g = 0; g < shard->world; g++) {
+      char* base = static_cast<char*>(shard->peer_block[g]);
+      p.peer_S[0][g] = reinterpret_cast<float*>(base + shard->s_offset[0]);
+      p.peer_S[1][g] = reinterpret_cast<float*>(base + shard->s_offset[1]);
+      p.peer_flags[g] = reinterpret_cast<unsigned long long*>(base);
+    }
+    p.S[0] = p.peer_S[0][shard->rank];
+    p.S[1] = p.peer_S[1][shard->rank];
+    p.flags = p.peer_flags[shard->rank];
+    shard->solves += 1;
+    p.epoch = shard->solves << 32;
+  }
+  p.out_eigen_vec = d_out_vec;
+  p.out_eigen_val = d_scalars_;
+  p.out_iter = reinterpret_cast<uint32_t*>(d_scalars_ + 1);
+  p.round_ts = d_ts_;
+
+  // launch shape: one persistent CTA per SM, fewer when there are fewer rows than warps
+  int threads = opt.threads == 256 || opt.threads == 1024 ? opt.threads : 512;
+  int grid = opt.ctas > 0 ? opt.ctas : sm_count_;
+  const int warps = threads / 32;
+  const int useful = (int)std::max<uint32_t>(1u, (rows + (uint32_t)warps - 1u) / (uint32_t)warps);
+  grid = std::max(1, std::min(grid, std::min(useful, sm_count_)));
+  const uint32_t rows_cap = (rows + (uint32_t)grid - 1u) / (uint32_t)grid + 1u;
+  const size_t smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
+  const bool vec4 = (dim % 4u == 0u) && aligned16(d_rows) && (!p.W || aligned16(p.W));
+
+  ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
+  ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
+  ST_CUDA(cudaEventRecord(ev0_, stream_));
+  if (vec4) {
+    if (form == kFormInPlace)
+      launch_by_threads<4, kFormInPlace>(threads, p, grid, smem, stream_);
+    else
+      launch_by_threads<4, kFormReadOnly>(threads, p, grid, smem, stream_);
+  } else {
+    if (form == kFormInPlace)
+      launch_by_threads<1, kFormInPlace>(threads, p, grid, smem, stream_);
+    else
+      launch_by_threads<1, kFormReadOnly>(threads, p, grid, smem, stream_);
+  }
+  ST_CUDA(cudaEventRecord(ev1_, stream_));
+
+  // read back: lambda, iter_count, passes, barrier error word
+  float* hp = static_cast<float*>(h_pinned_);
+  ST_CUDA(cudaMemcpyAsync(hp, d_scalars_, 16, cudaMemcpyDeviceToHost, stream_));
+  ST_CUDA(cudaMemcpyAsync(hp + 4, &d_bar_->error, 4, cudaMemcpyDeviceToHost, stream_));
+  ST_CUDA(cudaStreamSynchronize(stream_));
+  float loop_ms = 0.f;
+  ST_CUDA(cudaEventElapsedTime(&loop_ms, ev0_, ev1_));
+
+  uint32_t words[5];
+  memcpy(words, hp, sizeof words);
+  if (words[4] != 0u) {
+    set_last_error("round barrier timed out (a peer rank did not arrive)");
+    if (res)
+      res->status = ST_ERR_TIMEOUT;
+    return ST_ERR_TIMEOUT;
+  }
+  const uint32_t passes = words[2];
+  last_ts_.assign((size_t)passes + 1, 0);
+  ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)passes + 1),
+                     cudaMemcpyDeviceToHost));
+
+  if (res) {
+    memset(res, 0, sizeof *res);
+    memcpy(&res->eigen_val, &words[0], 4);
+    res->iter_count = words[1];
+    res->passes = passes;
+    res->launches = 1;
+    res->loop_ms = loop_ms;
+    res->grid = (uint32_t)grid;
+    const uint64_t per_pass = (uint64_t)rows * dim * sizeof(float);
+    res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;
+    std::vector<float> dt;
+    for (uint32_t k = 0; k < passes; k++)
+      dt.push_back((float)(last_ts_[k + 1] - last_ts_[k]) * 1e-3f);
+    if (!dt.empty()) {
+      std::sort(dt.begin(), dt.end());
+      res->round_us_min = dt.front();
+      res->round_us_median = dt[dt.size() / 2];
+    }
+    res->status = ST_OK;
+    const auto host_t1 = std::chrono::steady_clock::now();
+    res->total_ms = std::chrono::duration<float, std::milli>(host_t1 - host_t0).count();
+  }
+  return ST_OK;
+}
+
+int
+Context::solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
+                    float* h_eigen_vec, st_result* res)
+{
+  if (!h_mat || dim == 0)
+    throw std::invalid_argument("solve_host: bad argument");
+  const auto host_t0 = std::chrono::steady_clock::now();
+  activate();
+  const size_t elems = (size_t)dim * dim;
+  reserve_matrix(elems);
+  reserve_vectors(dim, opt.max_iter);
+  // the caller's matrix is never modified (reference similarity_transform.cpp:14,19 copies it)
+  ST_CUDA(cudaMemcpyAsync(d_mat_, h_mat, sizeof(float) * elems, cudaMemcpyHostToDevice, stream_));
+  st_result local{};
+  const int rc = solve(d_mat_, dim, opt, nullptr, nullptr, &local);
+  if (rc == ST_OK) {
+    if (h_eigen_vec)
+      ST_CUDA(cudaMemcpy(h_eigen_vec, d_vec_ + 4 * (size_t)vec_cap_, sizeof(float) * dim,
+                         cudaMemcpyDeviceToHost));
+    if (h_eigen_val)
+      *h_eigen_val = local.eigen_val;
+  }
+  const auto host_t1 = std::chrono::steady_clock::now();
+  local.total_ms = std::chrono::duration<float, std::milli>(host_t1 - host_t0).count();
+  if (res)
+    *res = local;
+  return rc;
+}
+
+} // namespace st
+
+// =============================================================================================
+// reference-named C++ entry points
+// =============================================================================================
+using namespace st;
+
+int64_t
+similarity_transform(st::Context& q, const float* mat, float* const eigen_val,
+                     float* const eigen_vec, const uint dim, const uint /*wg_size*/,
+                     uint* const iter_count)
+{
+  std::lock_guard<std::mutex> lock(q.mutex());
+  st_options opt;
+  st_default_options(&opt);
+  st_result res{};
+  const int rc = q.solve_host(mat, dim, opt, eigen_val, eigen_vec, &res);
+  if (rc != ST_OK)
+    return rc;
+  if (iter_count)
+    *iter_count = res.iter_count; // exactly 4 bytes
+  return (int64_t)res.loop_ms;    // whole milliseconds of the loop, like reference :56-58
+}
+
+static int
+blocks_for(uint32_t n, int threads, int cap)
+{
+  return (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)cap));
+}
+
+static int
+launch_row_pass(st::Context& q, const float* d_rows, const float* d_e, float* d_vec, uint32_t dim,
+                uint32_t row0, uint32_t rows)
+{
+  q.activate();
+  const bool vec4 = (dim % 4u == 0u) && aligned16(d_rows);
+  const uint32_t chunk = std::min<uint32_t>((uint32_t)kChunkCols, dim);
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((rows + 7u) / 8u, 8u * q.sm_count()));
+  if (vec4)
+    sum_across_rows_kernel<4><<<grid, 256, chunk * sizeof(float), q.stream()>>>(d_rows, d_e, d_vec, dim, row0, rows);
+  else
+    sum_across_rows_kernel<1><<<grid, 256, chunk * sizeof(float), q.stream()>>>(d_rows, d_e, d_vec, dim, row0, rows);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+sum_across_rows(st::Context& q, const float* d_mat, float* d_vec, const uint dim, const uint)
+{
+  return launch_row_pass(q, d_mat, nullptr, d_vec, dim, 0, dim);
+}
+
+int
+row_pass_readonly(st::Context& q, const float* d_rows, const float* d_e, float* d_vec, const uint dim,
+                  const uint row0, const uint rows)
+{
+  return launch_row_pass(q, d_rows, d_e, d_vec, dim, row0, rows);
+}
+
+int
+find_max(st::Context& q, const float* d_vec, float* d_max, const uint dim, const uint)
+{
+  q.activate();
+  find_max_kernel<<<1, 1024, 0, q.stream()>>>(d_vec, d_max, dim);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+compute_eigen_vector(st::Context& q, const float* d_vec, const float* d_max, float* d_eigen_vec,
+                     const uint dim, const uint)
+{
+  q.activate();
+  compute_eigen_vector_kernel<<<blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream()>>>(
+    d_vec, d_max, d_eigen_vec, dim);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+initialise_eigen_vector(st::Context& q, float* d_eigen_vec, const uint dim)
+{
+  q.activate();
+  fill_kernel<<<blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream()>>>(d_eigen_vec, 1.f, dim);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+compute_next_matrix(st::Context& q, float* d_mat, const float* d_vec, const uint dim, const uint)
+{
+  q.activate();
+  const bool vec4 = (dim % 4u == 0u) && aligned16(d_mat) && aligned16(d_vec);
+  const dim3 grid(blocks_for(vec4 ? dim / 4 : dim, 256, 64),
+                  (unsigned)std::min<uint32_t>(dim, 16384u));
+  if (vec4)
+    compute_next_matrix_kernel<4><<<grid, 256, 0, q.stream()>>>(d_mat, d_vec, dim);
+  else
+    compute_next_matrix_kernel<1><<<grid, 256, 0, q.stream()>>>(d_mat, d_vec, dim);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+stop(st::Context& q, const float* d_vec, uint* d_ret, const uint dim, const uint, float eps)
+{
+  q.activate();
+  stop_kernel<<<1, 1024, 0, q.stream()>>>(d_vec, d_ret, dim, eps);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+generate_hilbert_matrix(st::Context& q, float* d_rows, const uint dim, const uint row0, const uint rows_)
+{
+  q.activate();
+  const uint rows = rows_ ? rows_ : dim - row0;
+  const dim3 grid(blocks_for(dim, 256, 32), (unsigned)std::min<uint32_t>(rows, 32768u));
+  hilbert_kernel<<<grid, 256, 0, q.stream()>>>(d_rows, dim, row0, rows);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+generate_uniform_matrix(st::Context& q, float* d_rows, const uint dim, uint64_t seed, const uint row0,
+                        const uint rows_)
+{
+  q.activate();
+  const uint rows = rows_ ? rows_ : dim - row0;
+  const size_t blocks4 = ((size_t)rows * dim + 3) / 4 + 1;
+  const int grid = (int)std::min<size_t>((blocks4 + 255) / 256, (size_t)q.sm_count() * 16);
+  uniform_kernel<<<std::max(1, grid), 256, 0, q.stream()>>>(d_rows, dim, row0, rows, seed);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}

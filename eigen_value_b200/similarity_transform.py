@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's Python interface, on top of the CUDA C ABI.
+
+`EigenValue` has the reference's name, constructor and `similarity_transform(mat)` method
+with the same argument checks and the same 4-tuple result
+(reference wrapper/python/similarity_transform.py:18-78).  `Solver` is the additive
+surface: device-resident matrices, on-device Hilbert / uniform generation, solver options,
+per-kernel calls (reference include/similarity_transform.hpp:55-100) and per-round timing.
+
+No numerics happen in this file: every call goes through libsimilarity_transform.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import StOptions, StResult, check
+
+EPS = 1e-3       # reference include/similarity_transform.hpp:4
+MAX_ITR = 1000   # reference include/similarity_transform.hpp:5
+FORM_READONLY, FORM_INPLACE = 0, 1
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class EigenValue:
+    """Drop-in for the reference's `EigenValue` (similarity_transform.py:18-78)."""
+
+    def __init__(self) -> None:
+        # reference :29-40 -- load the shared object, make the queue, fail on a NULL handle
+        self.so_lib = _lib.load()
+        self.so_path = _lib.so_path()
+        self.sycl_q = ctypes.c_void_p()          # keeps the reference's attribute name
+        self.so_lib.make_queue(ctypes.byref(self.sycl_q))
+        if self.sycl_q.value is None:
+            err = self.so_lib.st_last_error()
+            raise Exception("failed to get default CUDA device queue: "
+                            + (err.decode() if err else "no GPU"))
+
+    def similarity_transform(self, mat: np.ndarray) -> Tuple[np.float32, np.ndarray, int, int]:
+        """(max eigen value, eigen vector, loop milliseconds, iteration count) of a positive
+        square float32 matrix; A v = lambda v holds to the reference's tolerance
+        (wrapper/python/test.py:15-16)."""
+        m, n = mat.shape
+        assert m == n, "must be square matrix of floating points !"          # reference :55
+        assert mat.dtype.num == 11, "dtype of input matrix must be float32 !"  # reference :56-57
+        assert mat.flags["C_CONTIGUOUS"], "matrix must be C-contiguous"       # ndpointer flag, :59-60
+
+        eigen_val = np.empty(1, dtype=np.float32)
+        eigen_vec = np.empty(n, dtype=np.float32)
+        iter_cnt = np.zeros(1, dtype=np.uint)    # 8-byte slot, C writes the low 4 bytes (:73)
+        ts = self.so_lib.max_eigen_value(self.sycl_q, _ptr(mat), _ptr(eigen_val), _ptr(eigen_vec),
+                                         n, _ptr(iter_cnt))
+        if ts < 0:
+            err = self.so_lib.st_last_error()
+            raise RuntimeError(f"max_eigen_value failed ({ts}): {err.decode() if err else ''}")
+        return eigen_val[0], eigen_vec, ts, int(iter_cnt[0])
+
+
+@dataclass
+class SolveInfo:
+    eigen_val: np.float32
+    iter_count: int
+    passes: int
+    launches: int
+    loop_ms: float
+    total_ms: float
+    round_us_median: float
+    round_us_min: float
+    bytes_per_round: int
+    grid: int
+
+    @classmethod
+    def from_c(cls, r: StResult) -> "SolveInfo":
+        return cls(np.float32(r.eigen_val), int(r.iter_count), int(r.passes), int(r.launches),
+                   float(r.loop_ms), float(r.total_ms), float(r.round_us_median),
+                   float(r.round_us_min), int(r.bytes_per_round), int(r.grid))
+
+
+class DeviceBuffer:
+    """A device allocation owned by a Solver (plain pointer + size; no torch types)."""
+
+    def __init__(self, solver: "Solver", nbytes: int):
+        self.solver = solver
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        check(solver.lib.st_malloc(solver.ctx, self.nbytes, ctypes.byref(p)), "st_malloc")
+        self.ptr = p
+
+    def free(self) -> None:
+        if self.ptr is not None and self.ptr.value:
+            self.solver.lib.st_free(self.solver.ctx, self.ptr)
+            self.ptr = None
+
+    def upload(self, a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        check(self.solver.lib.st_memcpy_h2d(self.solver.ctx, self.ptr, _ptr(a), a.nbytes), "st_memcpy_h2d")
+        return self
+
+    def download(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(self.solver.lib.st_memcpy_d2h(self.solver.ctx, _ptr(out), self.ptr, out.nbytes), "st_memcpy_d2h")
+        return out
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_options(lib, eps: float = EPS, max_iter: int = MAX_ITR, form: int = FORM_READONLY,
+                 sweep: int = 0, threads: int = 0, ctas: int = 0, kernel: int = 0) -> StOptions:
+    o = StOptions()
+    lib.st_default_options(ctypes.byref(o))
+    o.eps, o.max_iter, o.form, o.sweep = eps, max_iter, form, sweep
+    o.threads, o.ctas, o.kernel = threads, ctas, kernel
+    return o
+
+
+class Solver:
+    """One CUDA device: st_create / st_destroy plus everything that runs on it."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.ctx = ctypes.c_void_p()
+        check(self.lib.st_create(device, ctypes.byref(self.ctx)), "st_create")
+        self.device = device
+        sm = ctypes.c_int()
+        l2 = ctypes.c_size_t()
+        hbm = ctypes.c_size_t()
+        name = ctypes.create_string_buffer(128)
+        check(self.lib.st_device_info(self.ctx, ctypes.byref(sm), ctypes.byref(l2), ctypes.byref(hbm),
+                                      name, 128), "st_device_info")
+        self.sm_count, self.l2_bytes, self.hbm_bytes = sm.value, l2.value, hbm.value
+        self.name = name.value.decode()
+
+    def close(self) -> None:
+        if self.ctx is not None and self.ctx.value:
+            self.lib.st_destroy(self.ctx)
+            self.ctx = None
+
+    # ---- memory / inputs ------------------------------------------------------------------
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def upload(self, a: np.ndarray) -> DeviceBuffer:
+        a = np.ascontiguousarray(a)
+        return self.alloc(max(a.nbytes, 4)).upload(a)
+
+    def hilbert(self, dim: int, row0: int = 0, rows: Optional[int] = None) -> DeviceBuffer:
+        """reference utils.cpp:136-154, generated on the device."""
+        rows = dim - row0 if rows is None else rows
+        buf = self.alloc(4 * rows * dim)
+        check(self.lib.st_generate_hilbert(self.ctx, buf.ptr, dim, row0, rows), "st_generate_hilbert")
+        return buf
+
+    def uniform(self, dim: int, seed: int, row0: int = 0, rows: Optional[int] = None) -> DeviceBuffer:
+        """seeded uniform (0,1] fill (replaces reference utils.cpp:124-134)."""
+        rows = dim - row0 if rows is None else rows
+        buf = self.alloc(4 * rows * dim)
+        check(self.lib.st_generate_uniform(self.ctx, buf.ptr, dim, row0, rows, seed), "st_generate_uniform")
+        return buf
+
+    def synchronize(self) -> None:
+        check(self.lib.st_synchronize(self.ctx), "st_synchronize")
+
+    # ---- the round loop -------------------------------------------------------------------
+    def solve_device(self, d_mat: DeviceBuffer, dim: int, d_eigen_vec: Optional[DeviceBuffer] = None,
+                     **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
+        """similarity_transform() on a device-resident matrix.  Returns (info, eigen_vec);
+        eigen_vec is downloaded only when no device output buffer was supplied."""
+        o = make_options(self.lib, **opts)
+        res = StResult()
+        own = d_eigen_vec is None
+        vec = self.alloc(4 * dim) if own else d_eigen_vec
+        check(self.lib.st_solve_device(self.ctx, d_mat.ptr, dim, ctypes.byref(o), vec.ptr,
+                                       ctypes.byref(res)), "st_solve_device")
+        out = vec.download(np.float32, dim) if own else None
+        if own:
+            vec.free()
+        return SolveInfo.from_c(res), out
+
+    def solve_host(self, mat: np.ndarray, **opts) -> Tuple[SolveInfo, np.ndarray]:
+        """similarity_transform() on a host matrix (H2D copy, solve, D2H of the results)."""
+        assert mat.ndim == 2 and mat.shape[0] == mat.shape[1] and mat.dtype == np.float32
+        assert mat.flags["C_CONTIGUOUS"]
+        n = mat.shape[0]
+        o = make_options(self.lib, **opts)
+        res = StResult()
+        val = np.empty(1, dtype=np.float32)
+        vec = np.empty(n, dtype=np.float32)
+        check(self.lib.st_solve_host(self.ctx, _ptr(mat), n, ctypes.byref(o), _ptr(val), _ptr(vec),
+                                     ctypes.byref(res)), "st_solve_host")
+        return SolveInfo.from_c(res), vec
+
+    def round_timestamps(self) -> np.ndarray:
+        n = ctypes.c_uint32()
+        check(self.lib.st_round_timestamps(self.ctx, None, 0, ctypes.byref(n)), "st_round_timestamps")
+        out = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            check(self.lib.st_round_timestamps(self.ctx, _ptr(out), n.value, ctypes.byref(n)),
+                  "st_round_timestamps")
+        return out
+
+    # ---- per-kernel calls (reference L1 functions), numpy in / numpy out -------------------
+    def sum_across_rows(self, mat: np.ndarray) -> np.ndarray:
+        n = mat.shape[0]
+        d_mat, d_vec = self.upload(mat.astype(np.float32)), self.alloc(4 * n)
+        check(self.lib.st_sum_across_rows(self.ctx, d_mat.ptr, d_vec.ptr, n), "st_sum_across_rows")
+        self.synchronize()
+        return d_vec.download(np.float32, n)
+
+    def find_max(self, vec: np.ndarray) -> np.float32:
+        n = vec.shape[0]
+        d_vec, d_max = self.upload(vec.astype(np.float32)), self.alloc(4)
+        check(self.lib.st_find_max(self.ctx, d_vec.ptr, d_max.ptr, n), "st_find_max")
+        self.synchronize()
+        return d_max.download(np.float32, 1)[0]
+
+    def compute_eigen_vector(self, vec: np.ndarray, mx: float, eigen_vec: np.ndarray) -> np.ndarray:
+        n = vec.shape[0]
+        d_vec, d_max = self.upload(vec.astype(np.float32)), self.upload(np.array([mx], dtype=np.float32))
+        d_e = self.upload(eigen_vec.astype(np.float32))
+        check(self.lib.st_compute_eigen_vector(self.ctx, d_vec.ptr, d_max.ptr, d_e.ptr, n),
+              "st_compute_eigen_vector")
+        self.synchronize()
+        return d_e.download(np.float32, n)
+
+    def initialise_eigen_vector(self, n: int) -> np.ndarray:
+        d_e = self.alloc(4 * n)
+        check(self.lib.st_initialise_eigen_vector(self.ctx, d_e.ptr, n), "st_initialise_eigen_vector")
+        self.synchronize()
+        return d_e.download(np.float32, n)
+
+    def compute_next_matrix(self, mat: np.ndarray, vec: np.ndarray) -> np.ndarray:
+        n = mat.shape[0]
+        d_mat, d_vec = self.upload(mat.astype(np.float32)), self.upload(vec.astype(np.float32))
+        check(self.lib.st_compute_next_matrix(self.ctx, d_mat.ptr, d_vec.ptr, n), "st_compute_next_matrix")
+        self.synchronize()
+        return d_mat.download(np.float32, n * n).reshape(n, n)
+
+    def stop(self, vec: np.ndarray, eps: float = EPS) -> int:
+        n = vec.shape[0]
+        d_vec, d_ret = self.upload(vec.astype(np.float32)), self.alloc(4)
+        check(self.lib.st_stop(self.ctx, d_vec.ptr, d_ret.ptr, n, eps), "st_stop")
+        self.synchronize()
+        return int(d_ret.download(np.uint32, 1)[0])
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,183 @@
+/*
+ * similarity_transform.h -- C ABI of libsimilarity_transform.so (B200 / sm_100a build).
+ *
+ * Part 1 is the drop-in boundary: the two symbols the reference's
+ * wrapper/similarity_transform.cpp exports and its Python wrapper binds
+ * (wrapper/python/similarity_transform.py:19,35-37,66-76).  Same names, same argument
+ * meaning, same return value; plain pointers and sizes only.
+ *
+ * Part 2 is additive (st_*): device-resident inputs, on-device input generation,
+ * per-kernel entry points mirroring include/similarity_transform.hpp:55-100, and the
+ * row-block sharded multi-GPU solve.  None of it changes Part 1.
+ *
+ * Error convention (the reference has none: wrapper/similarity_transform.cpp never checks):
+ * no exception ever crosses this boundary; st_* return 0 on success and a negative code on
+ * failure, max_eigen_value returns a negative value on failure (the reference only ever
+ * returns >= 0), and st_last_error() describes the most recent failure on this thread.
+ */
+#ifndef SIMILARITY_TRANSFORM_H
+#define SIMILARITY_TRANSFORM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef ST_UINT_DEFINED
+#define ST_UINT_DEFINED
+typedef unsigned int st_uint; /* the reference spells it `uint` */
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1 -- drop-in boundary
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces make_queue()  (reference wrapper/similarity_transform.cpp:3-12).
+ * Writes an opaque heap-allocated solver handle bound to CUDA device 0 (the "default
+ * device") to *wq; leaves *wq == NULL when no usable GPU exists, which the reference's
+ * Python wrapper already treats as failure (similarity_transform.py:39-40).  Like the
+ * reference there is no matching destroy call in Part 1 (st_destroy exists in Part 2). */
+void make_queue(void** wq);
+
+/* Replaces max_eigen_value()  (reference wrapper/similarity_transform.cpp:14-37), which
+ * forwards to similarity_transform() (reference similarity_transform.cpp:5-75).
+ *   wq         handle from make_queue
+ *   mat        HOST pointer, dim x dim fp32 row-major, not modified
+ *   eigen_val  HOST float[1]   <- s[0] of the last row-sum vector      (:60-65)
+ *   eigen_vec  HOST float[dim] <- raw accumulated eigenvector           (:42-43)
+ *   dim        matrix dimension, any dim >= 1
+ *   iter_cnt   HOST, exactly 4 bytes written: the break index, or 1000 if the stop test
+ *              never held                                                (:54)
+ * Returns the round loop's duration in whole milliseconds (:36,:56-58), measured on the
+ * device; negative on error.  EPS = 1e-3f, MAX_ITR = 1000 (include/similarity_transform.hpp:4-5). */
+int64_t max_eigen_value(void* wq, float* mat, float* eigen_val, float* eigen_vec, st_uint dim,
+                        st_uint* iter_cnt);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2 -- additive extensions
+ * ---------------------------------------------------------------------------------------- */
+
+#define ST_EPS 1e-3f     /* include/similarity_transform.hpp:4 */
+#define ST_MAX_ITR 1000u /* include/similarity_transform.hpp:5 */
+
+enum
+{
+  ST_OK = 0,
+  ST_ERR_CUDA = -1,      /* a CUDA runtime call failed; see st_last_error() */
+  ST_ERR_ARG = -2,       /* bad argument */
+  ST_ERR_NO_DEVICE = -3, /* no usable GPU */
+  ST_ERR_TIMEOUT = -4,   /* a device-side barrier timed out (peer rank missing) */
+  ST_ERR_NOMEM = -5
+};
+
+enum
+{
+  ST_FORM_READONLY = 0, /* s = (A.e)/e, A read once per round, never written (default) */
+  ST_FORM_INPLACE = 1   /* literal W <- D^-1 W D on a working copy (reference :52)       */
+};
+
+typedef struct st_options
+{
+  float eps;         /* stop threshold, reference EPS                               */
+  uint32_t max_iter; /* round cap, reference MAX_ITR                                */
+  int32_t form;      /* ST_FORM_*                                                   */
+  int32_t sweep;     /* 0: rows always ascending; 1: alternate direction per round
+                        so the tail of one pass is the L2-resident head of the next */
+  int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
+  int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
+  int32_t kernel;    /* 0 = default round kernel; others are tuning variants        */
+  int32_t reserved;
+} st_options;
+
+typedef struct st_result
+{
+  float eigen_val;        /* s[0] of the last pass                                  */
+  uint32_t iter_count;    /* break index (reference iter_count)                     */
+  uint32_t passes;        /* row passes executed = min(iter_count + 1, max_iter)    */
+  uint32_t launches;      /* kernels launched by this call                          */
+  float loop_ms;          /* round loop, CUDA events on the solver stream           */
+  float total_ms;         /* whole call incl. host<->device copies (host clock)     */
+  float round_us_median;  /* per-round time from in-kernel globaltimer stamps       */
+  float round_us_min;
+  uint64_t bytes_per_round; /* algorithmic bytes one round moves on this GPU        */
+  int32_t status;
+  uint32_t grid;          /* CTAs the round kernel ran with                          */
+} st_result;
+
+const char* st_last_error(void);
+int st_device_count(void);
+void st_default_options(st_options* opt);
+
+/* Solver context bound to one CUDA device (what make_queue creates for device 0). */
+int st_create(int device, void** ctx);
+void st_destroy(void* ctx);
+int st_device_info(void* ctx, int* sm_count, size_t* l2_bytes, size_t* hbm_bytes, char* name,
+                   size_t name_len);
+
+/* Device memory owned by the context's device. */
+int st_malloc(void* ctx, size_t bytes, void** dptr);
+int st_free(void* ctx, void* dptr);
+int st_memcpy_h2d(void* ctx, void* dptr, const void* hptr, size_t bytes);
+int st_memcpy_d2h(void* ctx, void* hptr, const void* dptr, size_t bytes);
+int st_synchronize(void* ctx);
+
+/* Input generation on the device, rows [row0, row0+rows) of the dim x dim matrix written
+ * to d_rows (rows x dim, row-major).
+ * Hilbert: reference utils.cpp:136-154, A[r][c] = 1.f / (float)(r + c + 1).
+ * Uniform: replaces the reference's unseeded host fill utils.cpp:124-134 by a seeded
+ * Philox-4x32-10 uniform (0,1] fill that does not depend on the sharding. */
+int st_generate_hilbert(void* ctx, float* d_rows, uint32_t dim, uint32_t row0, uint32_t rows);
+int st_generate_uniform(void* ctx, float* d_rows, uint32_t dim, uint32_t row0, uint32_t rows,
+                        uint64_t seed);
+
+/* similarity_transform() on a matrix already resident in device memory; d_eigen_vec is a
+ * device float[dim].  Same semantics as max_eigen_value otherwise. */
+int st_solve_device(void* ctx, const float* d_mat, uint32_t dim, const st_options* opt,
+                    float* d_eigen_vec, st_result* res);
+/* Same with host buffers (what max_eigen_value calls with default options). */
+int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt,
+                  float* h_eigen_val, float* h_eigen_vec, st_result* res);
+/* Per-round device timestamps (ns, globaltimer) of the last solve on this context. */
+int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
+
+/* Per-kernel entry points on device buffers, one per reference L1 function
+ * (include/similarity_transform.hpp:55-100; similarity_transform.cpp:77-460). */
+int st_sum_across_rows(void* ctx, const float* d_mat, float* d_vec, uint32_t dim);      /* :77-152  */
+/* Unfused building block of the collective variant of the sharded loop: one read-only
+ * round's row pass on rows [row0,row0+rows): d_vec[row0+r] = (sum_c A[r][c] e[c]) / e[row0+r]. */
+int st_row_pass_readonly(void* ctx, const float* d_rows, const float* d_e, float* d_vec,
+                         uint32_t dim, uint32_t row0, uint32_t rows);
+int st_find_max(void* ctx, const float* d_vec, float* d_max, uint32_t dim);             /* :154-227 */
+int st_compute_eigen_vector(void* ctx, const float* d_vec, const float* d_max,
+                            float* d_eigen_vec, uint32_t dim);                          /* :229-265 */
+int st_initialise_eigen_vector(void* ctx, float* d_eigen_vec, uint32_t dim);            /* :267-284 */
+int st_compute_next_matrix(void* ctx, float* d_mat, const float* d_vec, uint32_t dim);  /* :286-330 */
+int st_stop(void* ctx, const float* d_vec, uint32_t* d_ret, uint32_t dim, float eps);   /* :332-460 */
+
+/* Row-block sharded solve: one context (one process) per GPU, rank g owns rows
+ * [dim*g/world, dim*(g+1)/world).  The per-round exchange of the row-sum slices is done by
+ * the round kernel itself with stores into peer memory and a flag barrier over NVLink.
+ *   st_shard_create  allocates this rank's exchange block
+ *   st_shard_export  writes its 64-byte CUDA IPC handle (ship it to the peers with any
+ *                    host-side transport, e.g. torch.distributed all_gather)
+ *   st_shard_import  opens the world x 64-byte handle table, in rank order
+ *   st_shard_solve   collective: every rank calls it with its own rows */
+#define ST_IPC_HANDLE_BYTES 64
+#define ST_MAX_WORLD 8
+int st_shard_create(void* ctx, uint32_t dim, uint32_t rank, uint32_t world, void** shard);
+int st_shard_export(void* shard, void* handle_out);
+int st_shard_import(void* shard, const void* handles);
+/* Same-process alternative to export/import (one host thread per GPU): links `world` shards
+ * created in this process, in rank order, through plain CUDA peer access. */
+int st_shard_link_local(void** shards, uint32_t world);
+int st_shard_rows(void* shard, uint32_t* row0, uint32_t* rows);
+int st_shard_solve(void* shard, const float* d_rows, const st_options* opt, float* d_eigen_vec,
+                   st_result* res);
+void st_shard_destroy(void* shard);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMILARITY_TRANSFORM_H */

@@ -1,0 +1,144 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (eigen_value_b200/) never imports it.
+
+The oracle restates reference similarity_transform.cpp:5-460 on the CPU; see the header of
+oracle.c for what pins it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+EPS = 1e-3        # reference include/similarity_transform.hpp:4
+MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
+
+FORM_INPLACE, FORM_READONLY = 0, 1
+SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c -> liboracle.so with the recipe in oracle/Makefile."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        L.oracle_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_sum_across_rows.argtypes = [_f32p, _f32p, ctypes.c_uint32, ctypes.c_int]
+        L.oracle_find_max.argtypes = [_f32p, ctypes.c_uint32]
+        L.oracle_find_max.restype = ctypes.c_float
+        L.oracle_compute_eigen_vector.argtypes = [_f32p, ctypes.c_float, _f32p, ctypes.c_uint32]
+        L.oracle_initialise_eigen_vector.argtypes = [_f32p, ctypes.c_uint32]
+        L.oracle_stop.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_float]
+        L.oracle_stop.restype = ctypes.c_uint32
+        L.oracle_compute_next_matrix.argtypes = [_f32p, _f32p, ctypes.c_uint32]
+        L.oracle_generate_hilbert.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+        L.oracle_generate_uniform.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_uint64]
+        L.oracle_philox_block.argtypes = [ctypes.c_uint64, ctypes.c_uint64,
+                                          np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
+        L.oracle_similarity_transform_ex.argtypes = [
+            _f32p, _f32p, _f32p, ctypes.c_uint32,
+            np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS"),
+            ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+            ctypes.POINTER(ctypes.c_double)]
+        L.oracle_similarity_transform_ex.restype = ctypes.c_int64
+        L.oracle_time_rounds.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        L.oracle_time_rounds.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def threads() -> int:
+    return int(lib().oracle_threads())
+
+
+def hilbert(dim: int, row0: int = 0, rows: int | None = None) -> np.ndarray:
+    rows = dim - row0 if rows is None else rows
+    out = np.empty((rows, dim), dtype=np.float32)
+    lib().oracle_generate_hilbert(out, dim, row0, rows)
+    return out
+
+
+def uniform(dim: int, seed: int, row0: int = 0, rows: int | None = None) -> np.ndarray:
+    rows = dim - row0 if rows is None else rows
+    out = np.empty((rows, dim), dtype=np.float32)
+    lib().oracle_generate_uniform(out, dim, row0, rows, seed)
+    return out
+
+
+def philox_block(ctr: int, key: int) -> np.ndarray:
+    out = np.empty(4, dtype=np.uint32)
+    lib().oracle_philox_block(ctr, key, out)
+    return out
+
+
+def sum_across_rows(mat: np.ndarray, sum_mode: int = SUM_LANES16) -> np.ndarray:
+    n = mat.shape[0]
+    out = np.empty(n, dtype=np.float32)
+    lib().oracle_sum_across_rows(np.ascontiguousarray(mat, dtype=np.float32), out, n, sum_mode)
+    return out
+
+
+def find_max(vec: np.ndarray) -> float:
+    return float(lib().oracle_find_max(np.ascontiguousarray(vec, dtype=np.float32), vec.shape[0]))
+
+
+def compute_eigen_vector(vec: np.ndarray, mx: float, eigen_vec: np.ndarray) -> None:
+    lib().oracle_compute_eigen_vector(vec, mx, eigen_vec, vec.shape[0])
+
+
+def stop(vec: np.ndarray, eps: float = EPS) -> int:
+    return int(lib().oracle_stop(np.ascontiguousarray(vec, dtype=np.float32), vec.shape[0], eps))
+
+
+def compute_next_matrix(mat: np.ndarray, vec: np.ndarray) -> None:
+    assert mat.flags["C_CONTIGUOUS"] and mat.dtype == np.float32
+    lib().oracle_compute_next_matrix(mat, vec, vec.shape[0])
+
+
+def similarity_transform(mat: np.ndarray, eps: float = EPS, max_itr: int = MAX_ITR,
+                         form: int = FORM_INPLACE, sum_mode: int = SUM_LANES16,
+                         ranks: int = 1) -> Tuple[np.float32, np.ndarray, float, int]:
+    """(lambda, raw eigen_vec, loop ms, iter_count) -- same tuple as the reference's Python
+    wrapper returns (wrapper/python/similarity_transform.py:78)."""
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    n = mat.shape[0]
+    assert mat.shape == (n, n)
+    val = np.empty(1, dtype=np.float32)
+    vec = np.empty(n, dtype=np.float32)
+    itr = np.zeros(1, dtype=np.uint32)
+    ms = ctypes.c_double(0.0)
+    rc = lib().oracle_similarity_transform_ex(mat, val, vec, n, itr, eps, max_itr, form, sum_mode,
+                                              ranks, ctypes.byref(ms))
+    if rc < 0:
+        raise MemoryError("oracle allocation failed")
+    return val[0], vec, ms.value, int(itr[0])
+
+
+def time_rounds(mat: np.ndarray, rounds: int, form: int = FORM_INPLACE) -> float:
+    """ms for `rounds` full reference rounds (no early exit) on all host threads."""
+    n = mat.shape[0]
+    return float(lib().oracle_time_rounds(mat, n, rounds, form))

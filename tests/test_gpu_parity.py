@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs.  Tolerances are BASELINE.json's: eigenvalue 1e-5 relative, eigenvector 1e-4 max-abs
+after normalisation, identical round count (the cases here sit away from the convergence
+boundary; boundary cases are asserted as |delta| <= 1)."""
+import numpy as np
+import pytest
+
+import oracle
+from eigen_value_b200 import EigenValue, FORM_INPLACE, FORM_READONLY
+
+pytestmark = pytest.mark.gpu
+
+LAMBDA_RTOL = 1e-5
+VEC_ATOL = 1e-4
+HILBERT_ROUNDS = {128: 9, 256: 10, 512: 12, 1024: 13, 2048: 14, 4096: 15, 8192: 17}  # README.md:70-76
+A3 = np.array([[1, 1, 2], [2, 1, 3], [2, 3, 5]], dtype=np.float32)
+
+
+def normalised(v):
+    return v / v.max()
+
+
+def assert_parity(got, want, same_rounds=True):
+    g_val, g_vec, g_it = got
+    w_val, w_vec, w_it = want
+    if same_rounds:
+        assert g_it == w_it, (g_it, w_it)
+    else:
+        assert abs(g_it - w_it) <= 1, (g_it, w_it)
+    if g_it == w_it:
+        assert abs(float(g_val) - float(w_val)) <= LAMBDA_RTOL * abs(float(w_val)), (g_val, w_val)
+        assert np.max(np.abs(normalised(g_vec) - normalised(w_vec))) <= VEC_ATOL
+
+
+# ---- the drop-in boundary: make_queue + max_eigen_value ---------------------------------------
+@pytest.fixture(scope="module")
+def ev():
+    return EigenValue()
+
+
+def test_three_by_three_golden_through_the_boundary(ev):
+    # reference tests/test.cpp:96-102
+    val, vec, ms, it = ev.similarity_transform(A3)
+    assert abs(val - 7.53114) < 1e-3
+    assert abs(vec[0] - 0.394074) < 1e-3 and abs(vec[1] - 0.578844) < 1e-3 and abs(vec[2] - 0.997451) < 1e-3
+    assert it == 4 and ms >= 0
+    o_val, o_vec, _, o_it = oracle.similarity_transform(A3)
+    assert_parity((val, vec, it), (o_val, o_vec, o_it))
+
+
+def test_reference_acceptance_test(ev):
+    # reference wrapper/python/test.py:8-18, verbatim criterion, 4 repeats on one handle
+    mat = np.random.default_rng(1234).random((1 << 10, 1 << 10)).astype("f")
+    keep = mat.copy()
+    for _ in range(4):
+        lam, v, ts, itr = ev.similarity_transform(mat)
+        assert np.all(np.isclose(np.matmul(mat, v), lam * v, atol=1e-3)), "Av = lambda v assertion failed !"
+        assert ts >= 0 and 1 <= itr < 10
+    assert np.array_equal(mat, keep), "caller's matrix must not be modified (similarity_transform.cpp:14,19)"
+
+
+def test_iter_count_slot_gets_exactly_four_bytes(ev):
+    # the reference wrapper passes an 8-byte np.uint slot, C writes a 4-byte uint (similarity_transform.py:63-73)
+    import ctypes
+    lib = ev.so_lib
+    slot = np.full(1, 0xAAAAAAAA_00000000, dtype=np.uint64)
+    val = np.empty(1, np.float32)
+    vec = np.empty(3, np.float32)
+    rc = lib.max_eigen_value(ev.sycl_q, A3.ctypes.data, val.ctypes.data, vec.ctypes.data, 3, slot.ctypes.data)
+    assert rc >= 0
+    assert int(slot[0]) == 0xAAAAAAAA_00000004
+
+
+@pytest.mark.parametrize("dim", sorted(HILBERT_ROUNDS))
+def test_hilbert_sweep_matches_published_rounds_and_oracle(ev, dim):
+    # BASELINE config 2 / reference main.cpp:23-35 + README.md:70-76
+    H = oracle.hilbert(dim)
+    val, vec, ms, it = ev.similarity_transform(H)
+    assert it == HILBERT_ROUNDS[dim]
+    o_val, o_vec, _, o_it = oracle.similarity_transform(H)
+    assert_parity((val, vec, it), (o_val, o_vec, o_it))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 5, 31, 33, 100, 257, 1000, 1023, 4100])
+def test_ragged_and_tiny_dims(ev, dim):
+    # the reference breaks on dim=1 (wg_size 0) and on dim % wg_size != 0
+    # (wrapper/similarity_transform.cpp:33); the replacement accepts any dim >= 1
+    mat = (oracle.uniform(dim, seed=dim) + np.float32(0.25)).astype(np.float32)
+    val, vec, ms, it = ev.similarity_transform(mat)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(mat)
+    assert_parity((val, vec, it), (o_val, o_vec, o_it), same_rounds=False)
+    if it == o_it and dim > 1:
+        assert np.all(np.isclose(mat @ vec, val * vec, atol=2e-3 * max(1.0, float(val))))
+
+
+def test_bad_arguments_do_not_crash(ev):
+    lib = ev.so_lib
+    assert lib.max_eigen_value(ev.sycl_q, None, None, None, 4, None) < 0
+    assert lib.max_eigen_value(None, A3.ctypes.data, A3.ctypes.data, A3.ctypes.data, 3, A3.ctypes.data) < 0
+    assert lib.st_last_error()
+
+
+# ---- per-kernel entry points vs the reference's unit fixtures (tests/test.cpp:22-73) -----------
+N = 1 << 10
+
+
+def test_kernel_sum_across_rows_identity(solver):
+    assert np.all(solver.sum_across_rows(np.eye(N, dtype=np.float32)) == 1.0)
+
+
+def test_kernel_sum_across_rows_random_vs_oracle(solver):
+    for dim in (7, 64, 1000, 2048):
+        m = oracle.uniform(dim, seed=99 + dim)
+        got, want = solver.sum_across_rows(m), oracle.sum_across_rows(m)
+        assert np.max(np.abs(got - want) / want) < 2e-6
+
+
+def test_kernel_find_max(solver):
+    assert solver.find_max(np.arange(1, N + 1, dtype=np.float32)) == N
+    assert solver.find_max(-np.ones(5, dtype=np.float32)) == 0.0   # zero-filled cell, :169
+
+
+def test_kernel_compute_eigen_vector(solver):
+    v = np.arange(1, N + 1, dtype=np.float32)
+    e = solver.initialise_eigen_vector(N)
+    assert np.all(e == 1.0)
+    e = solver.compute_eigen_vector(v, float(N), e)
+    want = np.ones(N, np.float32)
+    oracle.compute_eigen_vector(v, float(N), want)
+    assert np.array_equal(e, want)
+
+
+def test_kernel_stop(solver):
+    ok = np.full(N, np.float32(1.0) + np.float32(1e-4), dtype=np.float32)
+    bad = (np.arange(1, N + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    assert solver.stop(ok) == 1 and oracle.stop(ok) == 1
+    assert solver.stop(bad) == 0 and oracle.stop(bad) == 0          # fails through the wrap pair only
+    edge = np.array([0.0, 1e-3, 0.0, 0.0], dtype=np.float32)
+    assert solver.stop(edge) == oracle.stop(edge) == 0               # strict <
+
+
+def test_kernel_compute_next_matrix_bit_exact(solver):
+    for dim in (5, 64, 512):
+        W = oracle.uniform(dim, seed=5 + dim) + np.float32(0.5)
+        s = oracle.sum_across_rows(W)
+        got = solver.compute_next_matrix(W, s)
+        want = W.copy()
+        oracle.compute_next_matrix(want, s)
+        assert np.array_equal(got, want)
+
+
+# ---- input generation on the device -------------------------------------------------------------
+def test_device_hilbert_bit_exact(solver):
+    for dim, row0, rows in ((64, 0, 64), (1000, 0, 1000), (1000, 333, 100), (4096, 4000, 96)):
+        got = solver.hilbert(dim, row0, rows).download(np.float32, rows * dim).reshape(rows, dim)
+        assert np.array_equal(got, oracle.hilbert(dim, row0, rows))
+
+
+def test_device_uniform_bit_exact_and_shard_independent(solver):
+    for dim, row0, rows in ((64, 0, 64), (37, 0, 37), (37, 5, 9), (1001, 17, 300), (2048, 1024, 512)):
+        got = solver.uniform(dim, 0x5EED0001, row0, rows).download(np.float32, rows * dim).reshape(rows, dim)
+        assert np.array_equal(got, oracle.uniform(dim, 0x5EED0001, row0, rows))
+
+
+# ---- device-resident solves, both forms, options -------------------------------------------------
+@pytest.mark.parametrize("form", [FORM_READONLY, FORM_INPLACE])
+@pytest.mark.parametrize("dim", [3, 128, 1000, 2048])
+def test_forms_agree_with_oracle(solver, form, dim):
+    H = oracle.hilbert(dim) if dim > 3 else A3
+    info, vec = solver.solve_device(solver.upload(H), dim, form=form)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(
+        H, form=oracle.FORM_READONLY if form == FORM_READONLY else oracle.FORM_INPLACE)
+    assert_parity((info.eigen_val, vec, info.iter_count), (o_val, o_vec, o_it))
+    assert info.passes == info.iter_count + 1 and info.launches == 1
+
+
+@pytest.mark.parametrize("threads", [256, 512, 1024])
+@pytest.mark.parametrize("sweep", [0, 1])
+def test_launch_shape_and_sweep_do_not_change_results(solver, threads, sweep):
+    d = solver.hilbert(2048)
+    base, base_vec = solver.solve_device(d, 2048)
+    info, vec = solver.solve_device(d, 2048, threads=threads, sweep=sweep)
+    assert info.iter_count == base.iter_count == 14
+    assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec)
+
+
+def test_max_iter_cap_reports_cap(solver):
+    # never-converging case: iter_count == max_iter (reference similarity_transform.cpp:39,54)
+    d = solver.hilbert(512)
+    info, vec = solver.solve_device(d, 512, max_iter=5)
+    assert info.iter_count == 5 and info.passes == 5
+    o_val, o_vec, _, o_it = oracle.similarity_transform(oracle.hilbert(512), max_itr=5)
+    assert_parity((info.eigen_val, vec, info.iter_count), (o_val, o_vec, o_it))
+
+
+def test_eps_option(solver):
+    d = solver.hilbert(1024)
+    info, vec = solver.solve_device(d, 1024, eps=1e-2)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(oracle.hilbert(1024), eps=1e-2)
+    assert_parity((info.eigen_val, vec, info.iter_count), (o_val, o_vec, o_it))
+
+
+def test_multi_chunk_columns_16384(solver):
+    # N > 8192 columns exercises the chunked scale-vector staging; oracle takes ~2 s
+    H = oracle.hilbert(16384)
+    info, vec = solver.solve_device(solver.hilbert(16384), 16384)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(H, form=oracle.FORM_READONLY)
+    assert info.iter_count == 18                                     # BASELINE.md section 5 prediction
+    assert_parity((info.eigen_val, vec, info.iter_count), (o_val, o_vec, o_it))
+
+
+def test_full_size_property_uniform_32768(solver):
+    """BASELINE-size property check where the oracle is too slow: A.v ~= lambda.v on a random
+    (0,1] 32768^2 matrix after a capped run, evaluated on the GPU-generated rows."""
+    dim = 32768
+    d = solver.uniform(dim, 0x5EED0001)
+    info, vec = solver.solve_device(d, dim, max_iter=12)
+    assert info.iter_count == 12                                     # never converges in fp32
+    rows = [0, 1, 12345, dim - 1]
+    for r in rows:
+        a = oracle.uniform(dim, 0x5EED0001, row0=r, rows=1)[0].astype(np.float64)
+        lhs = float(a @ vec.astype(np.float64))
+        assert abs(lhs - float(info.eigen_val) * float(vec[r])) <= 1e-5 * abs(lhs)
