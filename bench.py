@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- the similarity_transform() round loop on B200, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hilbert-8192] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one complete similarity_transform() solve (the whole round loop, to convergence
+or to the round cap) of the workload matrix.
+  metric / value  per-round algorithmic HBM GB/s = passes * 4*N^2 bytes / loop time, whole job;
+                  the matrix is resident in HBM when the timed region starts.  `ms_to_converge`
+                  rides alongside (BASELINE.json's metric has both).
+  e2e             same metric through the C ABI with HOST buffers: max_eigen_value() at N=1,
+                  st_memcpy_h2d + st_shard_solve + read-back at N>1; pinned host input, copies timed.
+  roofline        the round-loop kernel against the measured HBM copy bandwidth.
+  cpu_baseline    the CPU oracle (a port of the reference's in-place loop, all host threads) on a
+                  bounded sample of the same workload, rank 0, N=1 only.
+--impl reference  times that CPU path instead (the reference's SYCL build cannot be compiled in
+                  this image: no dpcpp / SYCL headers).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+SEEDS = {65536: 0x5EED0001, 131072: 0x5EED0002}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None,
+                    help="hilbert-N or uniform-N; default hilbert-8192 at 1 GPU, hilbert-32768 sharded")
+    ap.add_argument("--max-iter", type=int, default=1000)
+    ap.add_argument("--form", type=int, default=0, help="0 read-only (default), 1 in-place")
+    ap.add_argument("--sweep", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep-table", action="store_true")
+    return ap.parse_args()
+
+
+def parse_workload(name: str):
+    kind, _, n = name.partition("-")
+    if kind not in ("hilbert", "uniform") or not n.isdigit():
+        raise SystemExit(f"unknown workload {name!r}")
+    return kind, int(n)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload: str):
+    """DRAM bytes per launch of the round-loop kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTED = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in {**self.BAD, **self.NOTED}.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_plan(kind: str, dim: int):
+    """(rounds per step, description): a bounded sample of the workload for the CPU."""
+    if dim <= 8192:
+        return None, "full solve to convergence per step"
+    rounds = 2 if dim <= 32768 else 1
+    return rounds, f"{rounds} full round(s) of the loop per step (no early exit)"
+
+
+def run_cpu_steps(kind: str, dim: int, steps: int, warmup: int):
+    """Times the oracle's in-place loop (reference similarity_transform.cpp:39-53 restated).
+    Returns (GB/s algorithmic, ms per step, passes per step, sample text)."""
+    import numpy as np
+    import oracle
+    if dim > 46000:
+        # working copy + input would not fit next to each other in host RAM on small boxes
+        raise SystemExit("reference arm: matrix too large for the host")
+    mat = oracle.hilbert(dim) if kind == "hilbert" else oracle.uniform(dim, SEEDS.get(dim, 0x5EED0000 + dim))
+    rounds, text = cpu_sample_plan(kind, dim)
+    times, passes = [], None
+    for i in range(warmup + steps):
+        if rounds is None:
+            _, _, ms, it = oracle.similarity_transform(mat, form=oracle.FORM_INPLACE)
+            p = min(it + 1, oracle.MAX_ITR)
+        else:
+            ms = oracle.time_rounds(mat, rounds, form=oracle.FORM_INPLACE)
+            p = rounds
+        if i >= warmup:
+            times.append(ms)
+            passes = p
+    ms_step = sum(times) / len(times)
+    gbs = passes * 4.0 * dim * dim / (ms_step * 1e-3) / 1e9
+    return gbs, ms_step, passes, text
+
+
+def reference_arm(args, kind, dim, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    steps = max(1, args.steps)
+    if dim > 8192:
+        steps = min(steps, 3)
+    t0 = time.time()
+    gbs, ms_step, passes, text = run_cpu_steps(kind, dim, steps, min(args.warmup, 1 if dim > 8192 else args.warmup))
+    cores = oracle.threads()
+    line = {
+        "impl": "reference",
+        "metric": "per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside",
+        "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload, "form": "in-place (reference as written)",
+                                        "passes_per_step": passes, "eps": 1e-3, "max_iter": 1000},
+        "ms_to_converge": round(ms_step, 3) if dim <= 8192 else None,
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{workload}: {text}; OpenMP oracle (oracle/oracle.c), {cores} threads"},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference SYCL build unavailable offline (no dpcpp); CPU port of its loop timed instead",
+        "wall_s": round(time.time() - t0, 2),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world != 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    workload = args.workload or ("hilbert-8192" if args.gpus == 1 else "hilbert-32768")
+    kind, dim = parse_workload(workload)
+
+    if args.impl == "reference":
+        return reference_arm(args, kind, dim, workload)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from eigen_value_b200 import Solver, _lib
+    from eigen_value_b200.sharded import ShardedSolver
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    solver = Solver(local_rank)
+    opts = dict(max_iter=args.max_iter, form=args.form, sweep=args.sweep, threads=args.threads, ctas=args.ctas)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        solver.synchronize()
+
+    # ---- inputs: generated on the device, this rank's row block only ----
+    if world > 1:
+        sh = ShardedSolver(solver, dim, rank, world)
+        row0, rows = sh.row0, sh.rows
+    else:
+        sh, row0, rows = None, 0, dim
+    seed = SEEDS.get(dim, 0x5EED0000 + dim)
+    d_rows = solver.hilbert(dim, row0, rows) if kind == "hilbert" else solver.uniform(dim, seed, row0, rows)
+    d_vec = solver.alloc(4 * dim)
+    solver.synchronize()
+
+    def step():
+        if sh is None:
+            info, _ = solver.solve_device(d_rows, dim, d_eigen_vec=d_vec, **opts)
+        else:
+            info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, **opts)
+        return info
+
+    # L2 hygiene: the shard is larger than L2 for the default workloads; smaller ones get a flush
+    shard_bytes = 4 * rows * dim
+    need_flush = shard_bytes <= 2 * solver.l2_bytes
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
+
+    def flush_l2():
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        flush_l2()
+        barrier()
+        step()
+
+    # ---- timed region: exactly K steps ----
+    infos = []
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            if flush is not None:
+                flush_l2()
+                barrier()
+            infos.append(step())
+        barrier()
+        wall1 = time.perf_counter()
+        if len(clocks.samples) < 5:      # very short timed region: keep sampling the same steps
+            t_end = time.perf_counter() + 1.0
+            while time.perf_counter() < t_end:
+                step()
+    clk = clocks.summary()
+
+    dev_ms = sum(i.loop_ms for i in infos)              # CUDA events on the solver's stream
+    passes = sum(i.passes for i in infos)
+    launches = sum(i.launches for i in infos)
+    t = torch.tensor([dev_ms, (wall1 - wall0) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    total_bytes = passes * 4.0 * dim * dim              # whole job: every rank's rows
+    value = total_bytes / (dev_ms * 1e-3) / 1e9
+    last = infos[-1]
+    round_us = statistics.median(i.round_us_median for i in infos)
+
+    # ---- e2e through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 5))
+        host = torch.empty((rows, dim), dtype=torch.float32).pin_memory()
+        check = _lib.check
+        check(solver.lib.st_memcpy_d2h(solver.ctx, host.data_ptr(), d_rows.ptr, 4 * rows * dim), "d2h")
+        h_np = host.numpy()
+        e2e_ms, e2e_passes = [], 0
+        if sh is None:
+            from eigen_value_b200 import EigenValue
+            ev = EigenValue()                            # make_queue(): device 0 == this process's GPU
+            val = np.empty(1, np.float32)
+            vec = np.empty(dim, np.float32)
+            slot = np.zeros(1, np.uint64)
+            for i in range(1 + e2e_steps):
+                t0 = time.perf_counter()
+                ms = solver.lib.max_eigen_value(ev.sycl_q, h_np.ctypes.data, val.ctypes.data, vec.ctypes.data,
+                                                dim, slot.ctypes.data)
+                t1 = time.perf_counter()
+                assert ms >= 0
+                if i:
+                    e2e_ms.append((t1 - t0) * 1e3)
+                    e2e_passes += min(int(slot[0]) + 1, 1000)
+            d2h = 4 * dim + 4 + 4
+        else:
+            vec = np.empty(dim, np.float32)
+            for i in range(1 + e2e_steps):
+                barrier()
+                t0 = time.perf_counter()
+                check(solver.lib.st_memcpy_h2d(solver.ctx, d_rows.ptr, host.data_ptr(), 4 * rows * dim), "h2d")
+                info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, **opts)
+                check(solver.lib.st_memcpy_d2h(solver.ctx, vec.ctypes.data, d_vec.ptr, 4 * dim), "d2h")
+                barrier()
+                t1 = time.perf_counter()
+                if i:
+                    e2e_ms.append((t1 - t0) * 1e3)
+                    e2e_passes += info.passes
+            d2h = 4 * dim + 8
+        tt = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_total_ms = float(tt[0])
+        e2e = {"value": round(e2e_passes * 4.0 * dim * dim / (e2e_total_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
+               "h2d_bytes_per_step": 4 * rows * dim, "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(e2e_total_ms / e2e_steps, 3), "steps": e2e_steps,
+               "api": "max_eigen_value (C ABI, pinned host matrix)" if sh is None
+                      else "st_memcpy_h2d + st_shard_solve + st_memcpy_d2h (C ABI, pinned host rows)"}
+
+    # ---- Hilbert sweep of the README sizes (config 2), N=1 only: ms to converge per size ----
+    table = None
+    if world == 1 and not args.no_sweep_table:
+        table = []
+        for n in (128, 256, 512, 1024, 2048, 4096, 8192):
+            d = solver.hilbert(n)
+            best = None
+            for _ in range(4):
+                info, _ = solver.solve_device(d, n, d_eigen_vec=d_vec, **opts)
+                if best is None or info.loop_ms < best.loop_ms:
+                    best = info
+            table.append({"N": n, "rounds": best.iter_count, "ms_to_converge": round(best.loop_ms, 4),
+                          "us_per_round": round(best.round_us_median, 2),
+                          "l2_resident": 4 * n * n <= solver.l2_bytes})
+            d.free()
+
+    # ---- CPU baseline beside it (rank 0, N=1) ----
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        cpu_dim = min(dim, 8192) if kind == "hilbert" else min(dim, 8192)
+        gbs, ms_step, cpu_passes, text = run_cpu_steps(kind, cpu_dim, 8 if cpu_dim >= 8192 else 20, 1)
+        cpu = {"value": round(gbs, 3), "unit": "GB/s", "cores": oracle.threads(), "kind": "port",
+               "sample": f"{kind}-{cpu_dim}: {text}, 8 steps; OpenMP oracle (oracle/oracle.c)",
+               "ms_per_step": round(ms_step, 3)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        agg_peak = peak * world
+        line = {
+            "metric": "per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside",
+            "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 5),
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "N": dim, "rows_per_gpu": rows, "form": "read-only" if args.form == 0 else "in-place",
+                       "eps": 1e-3, "max_iter": args.max_iter, "sweep": args.sweep, "grid": last.grid,
+                       "sharding": f"row-block x{world}, fused peer-store exchange" if world > 1 else "none",
+                       "l2": ("matrix shard larger than L2; no flush" if flush is None
+                              else "256 MiB L2 flush before every step")},
+            "ms_to_converge": round(dev_ms / args.steps, 5),
+            "rounds": last.iter_count, "passes_per_step": last.passes, "eigen_val": float(last.eigen_val),
+            "us_per_round": round(round_us, 3),
+            "wall_ms_per_step": round(wall_ms / args.steps, 5),
+            "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
+                         "frac": round(value / agg_peak, 4), "traffic": recorded_traffic(workload),
+                         "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+                         "kernel": "st::round_loop_kernel (one launch = one whole solve)",
+                         "bytes_per_launch": int(last.passes * 4 * dim * dim)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        }
+        if table is not None:
+            line["hilbert_sweep"] = table
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        sh.close()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
