@@ -1,0 +1,59 @@
+"""Multi-GPU parity on real GPUs.  With >= 2 visible GPUs this spawns one rank per GPU under
+torchrun (tests/sharded_worker.py); with one GPU it still drives the sharded entry points at
+world == 1.  Two mutually waiting kernels are never put on one GPU (B200_PROFILING.md)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world_one_shard_path_equals_plain_solve(solver):
+    from eigen_value_b200.sharded import ShardedSolver
+    dim = 2048
+    sh = ShardedSolver(solver, dim, 0, 1)
+    d = sh.hilbert()
+    info, vec = sh.solve(d)
+    base, base_vec = solver.solve_device(solver.hilbert(dim), dim)
+    assert info.iter_count == base.iter_count == 14
+    assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(oracle.hilbert(dim))
+    assert o_it == 14 and abs(float(info.eigen_val) - float(o_val)) <= 1e-5 * float(o_val)
+    sh.close()
+
+
+def test_shard_argument_checks(solver):
+    import ctypes
+    lib = solver.lib
+    sh = ctypes.c_void_p()
+    assert lib.st_shard_create(solver.ctx, 16, 3, 2, ctypes.byref(sh)) != 0      # rank >= world
+    assert lib.st_shard_create(solver.ctx, 4, 0, 9, ctypes.byref(sh)) != 0       # world > ST_MAX_WORLD
+    assert lib.st_shard_create(solver.ctx, 16, 0, 2, ctypes.byref(sh)) == 0
+    from eigen_value_b200._lib import StResult
+    res = StResult()
+    # not linked yet: solving must fail cleanly instead of waiting for a peer forever
+    assert lib.st_shard_solve(sh, solver.hilbert(16, 0, 8).ptr, None, None, ctypes.byref(res)) != 0
+    lib.st_shard_destroy(sh)
+
+
+def _gpu_count():
+    from eigen_value_b200 import _lib
+    return _lib.load().st_device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_exchange_multi_gpu(world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world * 7),
+           os.path.join(ROOT, "tests", "sharded_worker.py")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-4000:]
+    assert "SHARDED_OK" in proc.stdout
