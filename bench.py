@@ -46,7 +46,8 @@ def parse_args():
                     help="hilbert-N or uniform-N; default hilbert-8192 at 1 GPU, hilbert-32768 sharded")
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--form", type=int, default=0, help="0 read-only (default), 1 in-place")
-    ap.add_argument("--sweep", type=int, default=1)
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 LDG; 2-9 TMA ring; 10-19 single-chunk variants")
+    ap.add_argument("--sweep", type=int, default=None)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,7 +231,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     solver = Solver(local_rank)
-    opts = dict(max_iter=args.max_iter, form=args.form, sweep=args.sweep, threads=args.threads, ctas=args.ctas)
+    opts = dict(max_iter=args.max_iter, form=args.form, sweep=args.sweep, threads=args.threads, ctas=args.ctas,
+                kernel=args.kernel)
 
     def barrier():
         if world > 1:
@@ -386,7 +388,8 @@ def main():
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "N": dim, "rows_per_gpu": rows, "form": "read-only" if args.form == 0 else "in-place",
-                       "eps": 1e-3, "max_iter": args.max_iter, "sweep": args.sweep, "grid": last.grid,
+                       "eps": 1e-3, "max_iter": args.max_iter, "sweep": 1 if args.sweep is None else args.sweep, "kernel": args.kernel,
+                       "grid": last.grid,
                        "sharding": f"row-block x{world}, fused peer-store exchange" if world > 1 else "none",
                        "l2": ("matrix shard larger than L2; no flush" if flush is None
                               else "256 MiB L2 flush before every step")},
@@ -397,7 +400,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
                          "frac": round(value / agg_peak, 4), "traffic": recorded_traffic(workload),
                          "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
-                         "kernel": "st::round_loop_kernel (one launch = one whole solve)",
+                         "kernel": f"{last.kernel_name} id {last.kernel_id}, {last.threads} threads x {last.grid} CTAs "
+                                   "(one launch = one whole solve)",
                          "bytes_per_launch": int(last.passes * 4 * dim * dim)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }

@@ -24,7 +24,7 @@ class StOptions(ctypes.Structure):
         ("threads", ctypes.c_int32),
         ("ctas", ctypes.c_int32),
         ("kernel", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("l2_keep_pct", ctypes.c_int32),
     ]
 
 
@@ -42,6 +42,8 @@ class StResult(ctypes.Structure):
         ("bytes_per_round", ctypes.c_uint64),
         ("status", ctypes.c_int32),
         ("grid", ctypes.c_uint32),
+        ("kernel_id", ctypes.c_uint32),
+        ("threads", ctypes.c_uint32),
     ]
 
 

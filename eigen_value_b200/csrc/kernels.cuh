@@ -52,7 +52,9 @@ struct RoundParams
   float eps;
   uint32_t max_iter;
   int sweep;           // 1: alternate the row order every round (L2 reuse of the pass tail)
+  uint32_t keep_rows_pct; // share of each CTA's rows loaded L2 evict_last (rest evict_first); 0: no hints
   uint32_t chunk_cols; // columns staged per chunk (<= kChunkCols)
+  uint32_t mbar_offset; // TMA variant: byte offset of the mbarrier array in dynamic smem
   BarrierState* bar;
   unsigned long long timeout_ns;
   // row-block sharding (world == 1: unused)
@@ -126,6 +128,39 @@ ld_stream(const float* p)
   return v;
 }
 
+// Same loads with an L2 eviction-priority policy (createpolicy): rows the kernel wants to
+// find in L2 again next round are loaded evict_last, the rest evict_first.
+__device__ __forceinline__ float4
+ld_stream(const float4* p, unsigned long long pol)
+{
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float
+ld_stream(const float* p, unsigned long long pol)
+{
+  float v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ unsigned long long
+l2_policy_evict_last()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long
+l2_policy_evict_first()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 // L2-coherent loads/stores for data other CTAs (or other GPUs) write during the kernel.
 __device__ __forceinline__ float
 ld_cg(const float* p)
@@ -182,9 +217,10 @@ dot_acc(float a, float e, float acc)
 // Fixed evaluation order (depends on the segment length only): lane l owns vectors
 // l, l+32, ...; vector j of a batch goes to accumulator j; accumulators are folded pairwise,
 // then the 32 lanes by an xor-shuffle tree.  All lanes return the sum.
-template<int VEC>
+template<int VEC, bool HINT = false>
 __device__ __forceinline__ float
-row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, int lane)
+row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, int lane,
+                 unsigned long long pol = 0ull)
 {
   using V = typename Vec<VEC>::type;
   const V* __restrict__ a = reinterpret_cast<const V*>(row);
@@ -199,7 +235,7 @@ row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, 
     V v[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; u++)
-      v[u] = ld_stream(a + i + 32u * u);
+      v[u] = HINT ? ld_stream(a + i + 32u * u, pol) : ld_stream(a + i + 32u * u);
 #pragma unroll
     for (int u = 0; u < kUnroll; u++)
       acc[u] = dot_acc(v[u], es[i + 32u * u], acc[u]);
@@ -208,7 +244,7 @@ row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, 
   for (int u = 0; u < kUnroll; u++) {
     const uint32_t j = i + 32u * u;
     if (j < nv)
-      acc[u] = dot_acc(ld_stream(a + j), es[j], acc[u]);
+      acc[u] = dot_acc(HINT ? ld_stream(a + j, pol) : ld_stream(a + j), es[j], acc[u]);
   }
 #pragma unroll
   for (int s = kUnroll / 2; s >= 1; s >>= 1)
@@ -300,25 +336,60 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
 // ---------------------------------------------------------------------------------------
 // grid-wide (and, when sharded, cross-GPU) barrier at the end of round k
 // ---------------------------------------------------------------------------------------
-// Every CTA has written its row sums (locally and into every peer's S buffer).  The last CTA
-// to arrive signals the peers with one 64-bit release store each and waits for theirs, then
-// releases the local CTAs.  All waits are bounded by timeout_ns so that a missing rank turns
+// Every CTA has written its row sums (locally and into every peer's S buffer).
+//   one GPU : arrive = one release-add on a monotonically increasing counter; everybody
+//             acquire-polls the same counter (two L2 trips on the critical path, no fences).
+//   sharded : the last CTA to arrive signals the peers with one 64-bit release store each,
+//             waits for theirs, then releases the local CTAs through the generation word.
+// All waits are bounded by timeout_ns (checked every 1024 polls) so that a missing rank turns
 // into an error code instead of a hung GPU.  Returns false on timeout.
+__device__ __forceinline__ void
+red_release_gpu_add(unsigned int* p, unsigned int v)
+{
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct SpinClock
+{
+  unsigned long long t0 = 0ull;
+  unsigned int spins = 0u;
+  // true once the wait has lasted longer than limit_ns
+  __device__ __forceinline__ bool expired(unsigned long long limit_ns)
+  {
+    if ((++spins & 1023u) != 0u)
+      return false;
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0ull) {
+      t0 = now;
+      return false;
+    }
+    return now - t0 > limit_ns;
+  }
+};
+
+constexpr unsigned int kGenPoison = 0xffffffffu;
+
 __device__ __forceinline__ bool
 round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
     int fail = 0;
-    if (p.world > 1)
-      __threadfence_system();
-    else
-      __threadfence();
     const unsigned int target = (k + 1u) * gridDim.x;
-    const unsigned int prev = atomicAdd(&p.bar->count, 1u);
-    const unsigned long long t0 = globaltimer_ns();
-    if (prev + 1u == target) {
-      if (p.world > 1) {
+    SpinClock clk;
+    if (p.world == 1) {
+      red_release_gpu_add(&p.bar->count, 1u);
+      while (ld_acquire_gpu(&p.bar->count) < target) {
+        if (clk.expired(p.timeout_ns)) {
+          atomicExch(&p.bar->error, 1u);
+          fail = 1;
+          break;
+        }
+      }
+    } else {
+      __threadfence_system();
+      const unsigned int prev = atomicAdd(&p.bar->count, 1u);
+      if (prev + 1u == target) {
         __threadfence_system();
         const unsigned long long want = p.epoch + (unsigned long long)(k + 1u);
         for (uint32_t g = 0; g < p.world; g++)
@@ -327,9 +398,8 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
         for (uint32_t g = 0; g < p.world && !fail; g++) {
           if (g == p.rank)
             continue;
-          unsigned int spins = 0;
           while (ld_acquire_sys(p.flags + g) < want) {
-            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > p.timeout_ns) {
+            if (clk.expired(p.timeout_ns)) {
               fail = 1;
               break;
             }
@@ -337,21 +407,20 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
         }
         if (fail)
           atomicExch(&p.bar->error, 1u);
-      }
-      st_release_gpu(&p.bar->gen, k + 1u);
-    } else {
-      unsigned int spins = 0;
-      while (ld_acquire_gpu(&p.bar->gen) < k + 1u) {
-        if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > 2ull * p.timeout_ns) {
-          atomicExch(&p.bar->error, 1u);
-          fail = 1;
-          break;
+        st_release_gpu(&p.bar->gen, fail ? kGenPoison : k + 1u);
+      } else {
+        unsigned int g;
+        while ((g = ld_acquire_gpu(&p.bar->gen)) < k + 1u) {
+          if (clk.expired(2ull * p.timeout_ns)) {
+            atomicExch(&p.bar->error, 1u);
+            fail = 1;
+            break;
+          }
         }
+        if (g == kGenPoison)
+          fail = 1;
       }
     }
-    if (!fail && ld_acquire_gpu(&p.bar->error) != 0u)
-      fail = 1;
-    __threadfence();
     *s_abort = fail;
   }
   __syncthreads();
@@ -388,6 +457,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
 
   if (blockIdx.x == 0 && tid == 0)
     p.round_ts[0] = globaltimer_ns();
+  const unsigned long long pol_keep = l2_policy_evict_last();
+  const unsigned long long pol_stream = l2_policy_evict_first();
 
   float m_prev = 1.f;
   for (uint32_t k = 0;; ++k) {
@@ -422,7 +493,11 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
         const size_t off = (size_t)(rb + rl) * N + c0;
         float t;
         if (FORM == kFormReadOnly) {
-          t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
+          if (p.keep_rows_pct == 0u)
+            t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
+          else
+            t = row_dot_readonly<VEC, true>(p.A + off, scale_s, clen, lane,
+                                            rl * 100u < nrows * p.keep_rows_pct ? pol_keep : pol_stream);
         } else if (first) {
           t = row_pass_inplace<VEC, true>(p.A + off, p.W + off, scale_s, 1.f, clen, lane);
         } else {

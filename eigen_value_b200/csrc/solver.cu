@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "kernels_tma.cuh"
+#include "kernels_sc.cuh"
 
 namespace st {
 
@@ -168,6 +170,110 @@ launch_by_threads(int threads, const RoundParams& p, int grid, size_t smem, cuda
   }
 }
 
+// ---- TMA-streamed variant ---------------------------------------------------------------------
+struct TmaConfig
+{
+  int id, threads, stages, tile_f;
+};
+// id 2 is the default; the others are tuning variants reachable through st_options.kernel
+static const TmaConfig kTmaConfigs[] = {
+  { 2, 512, 3, 1024 }, { 3, 256, 6, 1024 }, { 4, 256, 3, 2048 }, { 5, 512, 2, 1024 },
+  { 6, 256, 4, 1024 }, { 7, 1024, 1, 1024 }, { 8, 512, 1, 2048 }, { 9, 256, 2, 2048 },
+};
+constexpr size_t kSmemLimit = 227 * 1024 - 1024; // opt-in maximum minus the kernel's static shared
+
+static size_t
+tma_smem_bytes(const TmaConfig& c, uint32_t chunk_cols, uint32_t rows_cap, uint32_t* mbar_offset)
+{
+  size_t off = (size_t)(c.threads / 32) * c.stages * c.tile_f * sizeof(float);
+  off += (size_t)chunk_cols * sizeof(float);
+  off += (size_t)rows_cap * sizeof(float);
+  off = (off + 15) & ~(size_t)15;
+  *mbar_offset = (uint32_t)off;
+  return off + (size_t)(c.threads / 32) * c.stages * sizeof(uint64_t);
+}
+
+template<int THREADS, int STAGES, int TILE_F>
+static void
+launch_tma_one(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_tma_kernel<THREADS, STAGES, TILE_F>;
+  ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
+                                      stream));
+}
+
+static void
+launch_tma(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  switch (id) {
+    case 2: return launch_tma_one<512, 3, 1024>(p, grid, smem, stream);
+    case 3: return launch_tma_one<256, 6, 1024>(p, grid, smem, stream);
+    case 4: return launch_tma_one<256, 3, 2048>(p, grid, smem, stream);
+    case 5: return launch_tma_one<512, 2, 1024>(p, grid, smem, stream);
+    case 6: return launch_tma_one<256, 4, 1024>(p, grid, smem, stream);
+    case 7: return launch_tma_one<1024, 1, 1024>(p, grid, smem, stream);
+    case 8: return launch_tma_one<512, 1, 2048>(p, grid, smem, stream);
+    case 9: return launch_tma_one<256, 2, 2048>(p, grid, smem, stream);
+    default: throw std::invalid_argument("unknown TMA kernel id");
+  }
+}
+
+// ---- single-chunk variant (N <= 8192): e resident in smem, fused tail, cross-barrier prefetch ----
+struct ScConfig
+{
+  int id, threads, pf_batches;
+};
+// the automatic choice takes the first entry that fits (id 13: 512 threads, one 4 KB batch
+// prefetched per warp -- measured best or tied at N = 1024..8192, profiles/r1_sweep_kernels_sc*.txt);
+// the others are tuning variants reachable through st_options.kernel
+static const ScConfig kScConfigs[] = {
+  { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 }, { 14, 1024, 1 }, { 15, 1024, 0 },
+  { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
+};
+
+static size_t
+sc_smem_bytes(const ScConfig& c, uint32_t chunk_cols, uint32_t rows_cap, uint32_t* mbar_offset)
+{
+  size_t off = (size_t)(c.threads / 32) * c.pf_batches * 1024 * sizeof(float);
+  off += (size_t)chunk_cols * sizeof(float);
+  off += (size_t)rows_cap * sizeof(float);
+  off = (off + 15) & ~(size_t)15;
+  *mbar_offset = (uint32_t)off;
+  return off + (size_t)(c.threads / 32) * sizeof(uint64_t);
+}
+
+template<int THREADS, int PF, int LD = kUnroll>
+static void
+launch_sc_one(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_sc_kernel<THREADS, PF, LD>;
+  if (smem > 48 * 1024)
+    ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
+                                      stream));
+}
+
+static void
+launch_sc(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  switch (id) {
+    case 10: return launch_sc_one<512, 2>(p, grid, smem, stream);
+    case 11: return launch_sc_one<512, 0>(p, grid, smem, stream);
+    case 12: return launch_sc_one<512, 3>(p, grid, smem, stream);
+    case 16: return launch_sc_one<256, 2, 16>(p, grid, smem, stream);
+    case 17: return launch_sc_one<256, 4, 16>(p, grid, smem, stream);
+    case 18: return launch_sc_one<256, 0, 16>(p, grid, smem, stream);
+    case 19: return launch_sc_one<256, 1, 16>(p, grid, smem, stream);
+    case 13: return launch_sc_one<512, 1>(p, grid, smem, stream);
+    case 14: return launch_sc_one<1024, 1>(p, grid, smem, stream);
+    case 15: return launch_sc_one<1024, 0>(p, grid, smem, stream);
+    default: throw std::invalid_argument("unknown single-chunk kernel id");
+  }
+}
+
 static bool
 aligned16(const void* p)
 {
@@ -210,6 +316,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   p.eps = opt.eps;
   p.max_iter = opt.max_iter;
   p.sweep = opt.sweep;
+  p.keep_rows_pct = (uint32_t)std::max(0, std::min(100, opt.l2_keep_pct));
   p.chunk_cols = std::min<uint32_t>((uint32_t)kChunkCols, dim);
   p.bar = d_bar_;
   p.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
@@ -239,14 +346,80 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const int warps = threads / 32;
   const int useful = (int)std::max<uint32_t>(1u, (rows + (uint32_t)warps - 1u) / (uint32_t)warps);
   grid = std::max(1, std::min(grid, std::min(useful, sm_count_)));
-  const uint32_t rows_cap = (rows + (uint32_t)grid - 1u) / (uint32_t)grid + 1u;
-  const size_t smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
+  uint32_t rows_cap = (rows + (uint32_t)grid - 1u) / (uint32_t)grid + 1u;
+  size_t smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
   const bool vec4 = (dim % 4u == 0u) && aligned16(d_rows) && (!p.W || aligned16(p.W));
+
+  // kernel choice: 0 = automatic (TMA-streamed when eligible), 1 = register-staged LDG kernel,
+  // >= 2 = a specific TMA configuration
+  const TmaConfig* tma = nullptr;
+  const ScConfig* sc = nullptr;
+  const bool sc_ok = vec4 && form == kFormReadOnly && dim <= (uint32_t)kChunkCols;
+  if ((opt.kernel == 0 || opt.kernel >= 10) && sc_ok) {
+    for (const ScConfig& c : kScConfigs) {
+      if (opt.kernel >= 10 && c.id != opt.kernel)
+        continue;
+      if (opt.kernel == 0 && opt.threads != 0 && c.threads != opt.threads)
+        continue;
+      int g = opt.ctas > 0 ? opt.ctas : sm_count_;
+      const int w = c.threads / 32;
+      const int use = (int)std::max<uint32_t>(1u, (rows + (uint32_t)w - 1u) / (uint32_t)w);
+      g = std::max(1, std::min(g, std::min(use, sm_count_)));
+      const uint32_t cap = (rows + (uint32_t)g - 1u) / (uint32_t)g + 1u;
+      uint32_t moff = 0;
+      const size_t need = sc_smem_bytes(c, p.chunk_cols, cap, &moff);
+      if (need <= kSmemLimit) {
+        sc = &c;
+        grid = g;
+        threads = c.threads;
+        rows_cap = cap;
+        smem = need;
+        p.mbar_offset = moff;
+        break;
+      }
+    }
+    if (!sc && opt.kernel >= 10)
+      throw std::invalid_argument("solve: requested single-chunk kernel configuration does not fit");
+  } else if (opt.kernel >= 10) {
+    throw std::invalid_argument("solve: single-chunk kernel needs the read-only form, dim % 4 == 0, dim <= 8192");
+  }
+  if (!sc && opt.kernel >= 2 && opt.kernel < 10 && vec4 && form == kFormReadOnly) {
+    for (const TmaConfig& c : kTmaConfigs) {
+      if (opt.kernel >= 2 && c.id != opt.kernel)
+        continue;
+      if (opt.kernel == 0 && opt.threads != 0 && c.threads != opt.threads)
+        continue;
+      int g = opt.ctas > 0 ? opt.ctas : sm_count_;
+      const int w = c.threads / 32;
+      const int use = (int)std::max<uint32_t>(1u, (rows + (uint32_t)w - 1u) / (uint32_t)w);
+      g = std::max(1, std::min(g, std::min(use, sm_count_)));
+      const uint32_t cap = (rows + (uint32_t)g - 1u) / (uint32_t)g + 1u;
+      uint32_t moff = 0;
+      const size_t need = tma_smem_bytes(c, p.chunk_cols, cap, &moff);
+      if (need <= kSmemLimit) {
+        tma = &c;
+        grid = g;
+        threads = c.threads;
+        rows_cap = cap;
+        smem = need;
+        p.mbar_offset = moff;
+        break;
+      }
+    }
+    if (!tma && opt.kernel >= 2)
+      throw std::invalid_argument("solve: requested TMA kernel configuration does not fit");
+  } else if (opt.kernel >= 2 && opt.kernel < 10) {
+    throw std::invalid_argument("solve: TMA kernel needs the read-only form and dim % 4 == 0");
+  }
 
   ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
-  if (vec4) {
+  if (sc) {
+    launch_sc(sc->id, p, grid, smem, stream_);
+  } else if (tma) {
+    launch_tma(tma->id, p, grid, smem, stream_);
+  } else if (vec4) {
     if (form == kFormInPlace)
       launch_by_threads<4, kFormInPlace>(threads, p, grid, smem, stream_);
     else
@@ -270,7 +443,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   uint32_t words[5];
   memcpy(words, hp, sizeof words);
   if (words[4] != 0u) {
-    set_last_error("round barrier timed out (a peer rank did not arrive)");
+    set_last_error(words[4] == 2u ? "bulk-copy wait timed out inside the round kernel"
+                                  : "round barrier timed out (a peer rank did not arrive)");
     if (res)
       res->status = ST_ERR_TIMEOUT;
     return ST_ERR_TIMEOUT;
@@ -288,6 +462,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->launches = 1;
     res->loop_ms = loop_ms;
     res->grid = (uint32_t)grid;
+    res->kernel_id = sc ? (uint32_t)sc->id : tma ? (uint32_t)tma->id : 1u;
+    res->threads = (uint32_t)threads;
     const uint64_t per_pass = (uint64_t)rows * dim * sizeof(float);
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;
     std::vector<float> dt;

@@ -74,12 +74,22 @@ class SolveInfo:
     round_us_min: float
     bytes_per_round: int
     grid: int
+    kernel_id: int = 0
+    threads: int = 0
+
+    KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_tma_kernel", 10: "st::round_loop_sc_kernel"}
+
+    @property
+    def kernel_name(self) -> str:
+        key = 10 if self.kernel_id >= 10 else 2 if self.kernel_id >= 2 else 1
+        return self.KERNEL_NAMES[key]
 
     @classmethod
     def from_c(cls, r: StResult) -> "SolveInfo":
         return cls(np.float32(r.eigen_val), int(r.iter_count), int(r.passes), int(r.launches),
                    float(r.loop_ms), float(r.total_ms), float(r.round_us_median),
-                   float(r.round_us_min), int(r.bytes_per_round), int(r.grid))
+                   float(r.round_us_min), int(r.bytes_per_round), int(r.grid), int(r.kernel_id),
+                   int(r.threads))
 
 
 class DeviceBuffer:
@@ -117,11 +127,16 @@ class DeviceBuffer:
 
 
 def make_options(lib, eps: float = EPS, max_iter: int = MAX_ITR, form: int = FORM_READONLY,
-                 sweep: int = 0, threads: int = 0, ctas: int = 0, kernel: int = 0) -> StOptions:
+                 sweep: Optional[int] = None, threads: int = 0, ctas: int = 0, kernel: int = 0,
+                 l2_keep_pct: Optional[int] = None) -> StOptions:
     o = StOptions()
     lib.st_default_options(ctypes.byref(o))
-    o.eps, o.max_iter, o.form, o.sweep = eps, max_iter, form, sweep
+    o.eps, o.max_iter, o.form = eps, max_iter, form
     o.threads, o.ctas, o.kernel = threads, ctas, kernel
+    if sweep is not None:
+        o.sweep = sweep
+    if l2_keep_pct is not None:
+        o.l2_keep_pct = l2_keep_pct
     return o
 
 

@@ -88,7 +88,9 @@ typedef struct st_options
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
   int32_t kernel;    /* 0 = default round kernel; others are tuning variants        */
-  int32_t reserved;
+  int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
+                          (the rest evict_first) so that part of A stays L2-resident across
+                          rounds; 0 = no cache hints                                       */
 } st_options;
 
 typedef struct st_result
@@ -104,6 +106,8 @@ typedef struct st_result
   uint64_t bytes_per_round; /* algorithmic bytes one round moves on this GPU        */
   int32_t status;
   uint32_t grid;          /* CTAs the round kernel ran with                          */
+  uint32_t kernel_id;     /* 1 general LDG loop, 2-9 TMA ring, 10-19 single-chunk    */
+  uint32_t threads;       /* CTA size the round kernel ran with                      */
 } st_result;
 
 const char* st_last_error(void);

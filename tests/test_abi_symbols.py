@@ -40,7 +40,7 @@ def test_python_binding_table_matches_header():
 
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.StOptions) == 32
-    assert ctypes.sizeof(_lib.StResult) == 48
+    assert ctypes.sizeof(_lib.StResult) == 56
 
 
 def test_library_is_sm100a_and_uses_no_cpu_fallback():
