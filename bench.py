@@ -290,6 +290,7 @@ def main():
             while time.perf_counter() < t_end:
                 step()
     clk = clocks.summary()
+    phase = solver.phase_breakdown()      # CTA 0 of this rank, last solve: pass | barrier(+exchange) | tail
 
     dev_ms = sum(i.loop_ms for i in infos)              # CUDA events on the solver's stream
     passes = sum(i.passes for i in infos)
@@ -396,6 +397,7 @@ def main():
             "ms_to_converge": round(dev_ms / args.steps, 5),
             "rounds": last.iter_count, "passes_per_step": last.passes, "eigen_val": float(last.eigen_val),
             "us_per_round": round(round_us, 3),
+            "phase_us": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phase.items()},
             "wall_ms_per_step": round(wall_ms / args.steps, 5),
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
                          "frac": round(value / agg_peak, 4), "traffic": recorded_traffic(workload),

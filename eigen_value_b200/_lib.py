@@ -74,6 +74,7 @@ SYMBOLS = {
     "st_solve_host": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP, _VP,
                                      ctypes.POINTER(StResult)]),
     "st_round_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
+    "st_phase_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
     "st_sum_across_rows": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_uint32]),
     "st_row_pass_readonly": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_uint32, ctypes.c_uint32,
                                             ctypes.c_uint32]),

@@ -296,6 +296,21 @@ st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count
   });
 }
 
+int
+st_phase_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    const auto& ts = c->phase_timestamps();
+    const uint32_t n = (uint32_t)std::min<size_t>(ts.size(), capacity);
+    if (out)
+      memcpy(out, ts.data(), sizeof(uint64_t) * n);
+    if (count)
+      *count = (uint32_t)ts.size();
+    return ST_OK;
+  });
+}
+
 // ---- per-kernel entry points ------------------------------------------------------------------
 int
 st_sum_across_rows(void* ctx, const float* d_mat, float* d_vec, uint32_t dim)

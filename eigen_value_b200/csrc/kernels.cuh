@@ -38,6 +38,8 @@ struct alignas(128) BarrierState
   unsigned int pad1[31];
   unsigned int error; // set by any CTA whose wait timed out
   unsigned int pad2[31];
+  unsigned int row_counter; // resident-e kernel: dynamic row scheduling (monotonic)
+  unsigned int pad3[31];
 };
 
 struct RoundParams
@@ -68,6 +70,7 @@ struct RoundParams
   float* out_eigen_val;  // 1 float  (device)
   uint32_t* out_iter;    // [0] iter_count, [1] passes
   unsigned long long* round_ts; // max_iter + 1 globaltimer stamps
+  unsigned long long* phase_ts; // 3 per round, CTA 0: pass done, barrier passed, tail done
 };
 
 // ---------------------------------------------------------------------------------------
@@ -107,6 +110,20 @@ __device__ __forceinline__ void
 st_release_sys(unsigned long long* p, unsigned long long v)
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long
+ld_relaxed_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void
+st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Streaming 128-bit load of matrix data that is never written while the kernel runs:
@@ -390,21 +407,25 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
       __threadfence_system();
       const unsigned int prev = atomicAdd(&p.bar->count, 1u);
       if (prev + 1u == target) {
+        // ONE system fence orders every CTA's peer stores (observed through the arrival counter)
+        // before the flag stores; the flags themselves are relaxed stores issued back to back
+        // (a release store per peer would serialise one NVLink round trip per peer).
         __threadfence_system();
         const unsigned long long want = p.epoch + (unsigned long long)(k + 1u);
         for (uint32_t g = 0; g < p.world; g++)
           if (g != p.rank)
-            st_release_sys(p.peer_flags[g] + p.rank, want);
+            st_relaxed_sys(p.peer_flags[g] + p.rank, want);
         for (uint32_t g = 0; g < p.world && !fail; g++) {
           if (g == p.rank)
             continue;
-          while (ld_acquire_sys(p.flags + g) < want) {
+          while (ld_relaxed_sys(p.flags + g) < want) {
             if (clk.expired(p.timeout_ns)) {
               fail = 1;
               break;
             }
           }
         }
+        __threadfence_system(); // acquire side: the peers' row sums are visible from here on
         if (fail)
           atomicExch(&p.bar->error, 1u);
         st_release_gpu(&p.bar->gen, fail ? kGenPoison : k + 1u);
@@ -430,9 +451,10 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
 // ---------------------------------------------------------------------------------------
 // the round loop
 // ---------------------------------------------------------------------------------------
-template<int VEC, int FORM, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParams p)
+template<int VEC, int FORM, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundParams p)
 {
+  const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
   extern __shared__ __align__(16) float smem[];
   float* scale_s = smem;               // chunk_cols floats: e (read-only) or s_prev (in-place)
   float* part_s = smem + p.chunk_cols; // one partial row sum per owned row
@@ -442,10 +464,10 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
   __shared__ int bc_ok;
   __shared__ int s_abort;
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  constexpr int kWarps = THREADS / 32;
+  const uint32_t tid = threadIdx.x;
+  const int lane = (int)(tid & 31u);
+  const uint32_t warp = tid >> 5;
+  const uint32_t kWarps = THREADS >> 5;
   const uint32_t N = p.N;
 
   // rows of this GPU's block owned by this CTA, and the slice of the N-vector it maintains
@@ -479,7 +501,9 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
     for (uint32_t c0 = 0; c0 < N; c0 += p.chunk_cols) {
       const uint32_t clen = min(p.chunk_cols, N - c0);
       __syncthreads();
-      for (uint32_t c = tid; c < clen; c += THREADS) {
+      const uint32_t rot = cb % clen; // de-phase the CTAs on the L2 lines of E and S
+      for (uint32_t cc = tid; cc < clen; cc += THREADS) {
+        const uint32_t c = cc + rot < clen ? cc + rot : cc + rot - clen;
         float v = 1.f;
         if (!first) {
           const float sp = ld_cg(Sprev + c0 + c);
@@ -508,6 +532,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
           part_s[rl] += t;
       }
     }
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k] = globaltimer_ns();
     __syncthreads();
 
     // ---- publish this CTA's row sums (to every rank when sharded) ----
@@ -526,15 +552,40 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
 
     if (!round_barrier(p, k, &s_abort))
       return;
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k + 1u] = globaltimer_ns();
 
     // ---- every CTA: max, circular stop test over the full vector ----   reference :41, :44
     float mx = 0.f; // reference zero-fills the max cell (:169)
     int ok = 1;
-    for (uint32_t c = tid; c < N; c += THREADS) {
-      const float self = ld_cg(Scur + c);
-      const float next = ld_cg(Scur + (c + 1u == N ? 0u : c + 1u));
-      mx = fmaxf(mx, self);
-      ok &= (fabsf(self - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+    // every CTA scans the same vector at the same time: start each at its own offset (cb) so
+    // they do not queue on the same L2 lines; max / AND are order-independent.  The circular
+    // neighbour comes from the next lane by shuffle, as in the reference (:413-417); four
+    // batches of loads are in flight before anything depends on them.
+    for (uint32_t b0 = 0; b0 < N; b0 += 4u * THREADS) {
+      float sf[4], nx[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+        const bool active = c0 < N;
+        const uint32_t c = c0 + cb < N ? c0 + cb : c0 + cb - N;
+        sf[j] = active ? ld_cg(Scur + c) : 0.f;
+        const bool edge = active && (lane == 31 || c0 + 1u >= N);
+        nx[j] = edge ? ld_cg(Scur + (c + 1u == N ? 0u : c + 1u)) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+        if (b0 + (uint32_t)j * THREADS < N) { // warp-uniform
+          float next = __shfl_down_sync(0xffffffffu, sf[j], 1);
+          if (lane == 31 || c0 + 1u >= N)
+            next = nx[j];
+          if (c0 < N) {
+            mx = fmaxf(mx, sf[j]);
+            ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+          }
+        }
+      }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -547,8 +598,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
     }
     __syncthreads();
     if (warp == 0) {
-      mx = lane < kWarps ? red_max[lane] : 0.f;
-      ok = lane < kWarps ? red_ok[lane] : 1;
+      mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
+      ok = (uint32_t)lane < kWarps ? red_ok[lane] : 1;
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -564,7 +615,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_kernel(const RoundParam
     const bool converged = bc_ok != 0;
 
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = globaltimer_ns();
+      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
 
     if (converged || k + 1u == p.max_iter) {
       // the eigenvector update of this round still happens before the break (:42-50)

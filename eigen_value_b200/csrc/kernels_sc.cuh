@@ -1,14 +1,17 @@
-// kernels_sc.cuh -- round loop specialised for N <= 8192 columns ("single chunk").
+// kernels_sc.cuh -- round loop with the eigenvector resident in shared memory (N <= 32768).
 //
-// When the whole eigenvector fits in one shared-memory chunk (<= 32 KB) the loop gets much
-// tighter than the general round_loop_kernel:
+// When the whole eigenvector fits in shared memory (<= 128 KB) the loop gets much tighter than
+// the general, column-chunked round_loop_kernel:
 //
 //   * e lives in shared memory for the WHOLE solve.  Every CTA updates its private copy in
 //     place from the published row sums (e *= s/m, reference similarity_transform.cpp:260);
 //     no global E buffers, no rebuild of the chunk per round.
-//   * after the round barrier each thread needs ONE L2 round trip: it loads its <= 16 entries
-//     of s (and their circular neighbours), the block reduces max / stop flag, and the same
-//     registers update e.  The general kernel needs four dependent L2 trips per round.
+//   * after the round barrier each thread needs ONE L2 round trip (N <= ~10240: its <= 5
+//     float4 of s stay in registers between the max / stop reduction and the update of e) or
+//     two (larger N: s is re-read), with every load of a batch in flight at once.  The general kernel needs four dependent L2 trips per round.
+//   * the CTA size is a RUN-TIME choice (blockDim.x, 12..16 warps): the host picks the warp
+//     count that divides the CTA's row count with the least idle warps, e.g. 14 warps for 55 or
+//     28 rows per CTA.
 //   * the matrix never changes, so before a warp enters the barrier its lane 0 issues ONE
 //     TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of the first
 //     PF_BATCHES*4 KB of the row it will process first in the NEXT round into a private
@@ -17,7 +20,7 @@
 //     from shared memory.  A prefetch issued for a round that never runs is drained at exit.
 //
 // Row sums are bit-identical to round_loop_kernel: same lane / accumulator / fold order.
-// Read-only form, N % 4 == 0, N <= kChunkCols only.
+// Read-only form, N % 4 == 0, N <= kResidentCols only.
 #pragma once
 
 #include "kernels.cuh"
@@ -25,63 +28,78 @@
 
 namespace st {
 
+constexpr int kResidentCols = 32768; // largest N whose eigenvector is kept in shared memory
+constexpr int kRegVec = 5;           // float4 of s a thread keeps in registers across the tail
+
 // one row: the leading `npre` float4 come from the prefetched shared-memory tile, the rest
-// from global memory.  npre is a multiple of 256 (one batch = 32 lanes x 8 accumulators) or nv.
-// LD = independent 128-bit loads in flight per lane (8 or 16); the accumulator a vector goes to
-// is always (index / 32) % 8, so the evaluation order does not depend on LD.
+// from global memory.  npre is a multiple of 256 (one batch = 32 lanes x 8 accumulators), at
+// most one 8192-column chunk, or nv.
+// Evaluation order = round_loop_kernel's, for any N: the row is cut into 8192-column chunks;
+// inside a chunk vector j goes to lane j % 32, accumulator (j / 32) % 8, the accumulators are
+// folded pairwise and the lanes by an xor-shuffle tree; chunk sums are added left to right.
+// LD = independent 128-bit loads in flight per lane (8 or 16) and does not affect the order.
 template<int LD>
 __device__ __forceinline__ float
 row_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane,
                    const float4* pf, uint32_t npre)
 {
   static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
-  float acc[kUnroll];
+  constexpr uint32_t kChunkVec = kChunkCols / 4;
+  float total = 0.f;
+  for (uint32_t base = 0; base < nv; base += kChunkVec) {
+    const uint32_t end = min(nv, base + kChunkVec);
+    float acc[kUnroll];
 #pragma unroll
-  for (int u = 0; u < kUnroll; u++)
-    acc[u] = 0.f;
-  for (uint32_t b0 = 0; b0 < npre; b0 += 32u * kUnroll) {
+    for (int u = 0; u < kUnroll; u++)
+      acc[u] = 0.f;
+    uint32_t i = base + (uint32_t)lane;
+    if (base == 0u) {
+      for (uint32_t b0 = 0; b0 < npre; b0 += 32u * kUnroll) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
-      const uint32_t j = b0 + lane + 32u * u;
-      if (j < npre)
-        acc[u] = dot_acc(pf[j], es[j], acc[u]);
+        for (int u = 0; u < kUnroll; u++) {
+          const uint32_t j = b0 + lane + 32u * u;
+          if (j < npre)
+            acc[u] = dot_acc(pf[j], es[j], acc[u]);
+        }
+      }
+      i += npre;
     }
+    for (; i + 32u * (LD - 1) < end; i += 32u * LD) {
+      float4 v[LD];
+#pragma unroll
+      for (int u = 0; u < LD; u++)
+        v[u] = ld_stream(a + i + 32u * u);
+#pragma unroll
+      for (int u = 0; u < LD; u++)
+        acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
+    }
+#pragma unroll
+    for (int u = 0; u < LD; u++) {
+      const uint32_t j = i + 32u * u;
+      if (j < end)
+        acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[j], acc[u % kUnroll]);
+    }
+#pragma unroll
+    for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+      for (int u = 0; u < s; u++)
+        acc[u] += acc[u + s];
+    const float t = warp_sum(acc[0]);
+    total = base == 0u ? t : total + t;
   }
-  uint32_t i = npre + (uint32_t)lane;
-  for (; i + 32u * (LD - 1) < nv; i += 32u * LD) {
-    float4 v[LD];
-#pragma unroll
-    for (int u = 0; u < LD; u++)
-      v[u] = ld_stream(a + i + 32u * u);
-#pragma unroll
-    for (int u = 0; u < LD; u++)
-      acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
-  }
-#pragma unroll
-  for (int u = 0; u < LD; u++) {
-    const uint32_t j = i + 32u * u;
-    if (j < nv)
-      acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[j], acc[u % kUnroll]);
-  }
-#pragma unroll
-  for (int s = kUnroll / 2; s >= 1; s >>= 1)
-#pragma unroll
-    for (int u = 0; u < s; u++)
-      acc[u] += acc[u + s];
-  return warp_sum(acc[0]);
+  return total;
 }
 
-template<int THREADS, int PF_BATCHES, int LD = kUnroll>
-__global__ void __launch_bounds__(THREADS, 1) round_loop_sc_kernel(const RoundParams p)
+template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll>
+__global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
-  constexpr int kWarps = THREADS / 32;
-  constexpr int kPerThread = kChunkCols / THREADS;   // entries of s each thread reduces
+  const uint32_t THREADS = blockDim.x; // run-time CTA size (a multiple of 32, <= MAX_THREADS)
+  const uint32_t kWarps = THREADS >> 5;
   constexpr uint32_t kPfFloats = PF_BATCHES * 1024u; // prefetch slot per warp
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* pf_all = reinterpret_cast<float*>(smem_raw);        // kWarps x kPfFloats
   float* e_s = pf_all + (size_t)kWarps * kPfFloats;          // N floats, lives across rounds
-  float* part_s = e_s + p.chunk_cols;                        // one row sum per owned row
   uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem_raw + p.mbar_offset);
   __shared__ float red_max[32];
   __shared__ int red_ok[32];
@@ -89,18 +107,24 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_sc_kernel(const RoundPa
   __shared__ int bc_ok;
   __shared__ int s_abort;
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+  const uint32_t tid = threadIdx.x;
+  const int lane = (int)(tid & 31u);
+  const uint32_t warp = tid >> 5;
   const uint32_t N = p.N;
   const uint32_t nv = N >> 2;
+  const bool reg_tail = nv <= (uint32_t)kRegVec * THREADS;
 
-  const uint32_t rb = (uint32_t)((uint64_t)p.rows * blockIdx.x / gridDim.x);
-  const uint32_t re = (uint32_t)((uint64_t)p.rows * (blockIdx.x + 1) / gridDim.x);
-  const uint32_t nrows = re - rb;
+  // slice of the N-vector this CTA writes at the end (and its phase offset in the tail scan)
   const uint32_t cb = (uint32_t)((uint64_t)N * blockIdx.x / gridDim.x);
   const uint32_t ce = (uint32_t)((uint64_t)N * (blockIdx.x + 1) / gridDim.x);
-  const uint32_t my_rows = nrows > (uint32_t)warp ? (nrows - warp + kWarps - 1) / kWarps : 0u;
+  // Row scheduling: warp gw of the grid takes row gw first (static, so its head can be
+  // prefetched across the barrier); the remaining R - TW rows are handed out through one
+  // atomic counter, so SMs that stream faster (L2 die locality) simply take more rows.  A
+  // row is always reduced by one warp in one fixed order: WHO takes it cannot change a bit.
+  const uint32_t R = p.rows;
+  const uint32_t TW = gridDim.x * kWarps;
+  const uint32_t gw = blockIdx.x * kWarps + warp;
+  const uint32_t D = R > TW ? R - TW : 0u; // dynamically scheduled rows per round
 
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
@@ -124,65 +148,140 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_sc_kernel(const RoundPa
 
     // ---- the pass over the matrix ----                                   reference :40 (+ :52)
     bool tma_ok = true;
-    for (uint32_t ii = 0; ii < my_rows; ii++) {
-      const uint32_t i = warp + ii * kWarps;
-      const uint32_t rl = backward ? (nrows - 1u - i) : i;
-      const float4* row = reinterpret_cast<const float4*>(p.A + (size_t)(rb + rl) * N);
-      uint32_t npre = 0;
-      if (PF_BATCHES > 0 && ii == 0 && pf_consumed < pf_issued) {
-        tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
-        pf_consumed++;
-        npre = pf_floats >> 2;
-      }
-      const float t = row_dot_prefetched<LD>(row, reinterpret_cast<const float4*>(e_s), nv, lane,
-                                         reinterpret_cast<const float4*>(my_pf), npre);
+    {
+      // the counter is monotonic: every warp makes exactly one failing grab per round, so round
+      // k hands out the values [k * (D + TW), k * (D + TW) + D)
+      const uint32_t base = k * (D + TW);
+      uint32_t cur = gw;
+      bool have = cur < R;
+      bool first_row = true;
+      uint32_t grabbed = 0;
       if (lane == 0)
-        part_s[rl] = t;
+        grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
+      for (;;) {
+        if (have) {
+          const uint32_t rl = backward ? (R - 1u - cur) : cur;
+          const float4* row = reinterpret_cast<const float4*>(p.A + (size_t)rl * N);
+          uint32_t npre = 0;
+          if (PF_BATCHES > 0 && first_row && pf_consumed < pf_issued) {
+            tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
+            pf_consumed++;
+            npre = pf_floats >> 2;
+          }
+          const float t = row_dot_prefetched<LD>(row, reinterpret_cast<const float4*>(e_s), nv, lane,
+                                                 reinterpret_cast<const float4*>(my_pf), npre);
+          // publish: s[r] = (A.e)[r] / e[r], to every rank when sharded
+          if (lane == 0) {
+            const uint32_t gr = p.row0 + rl;
+            const float s = t / e_s[gr];
+            if (p.world > 1) {
+              for (uint32_t g = 0; g < p.world; g++)
+                __stcg(p.peer_S[k & 1][g] + gr, s);
+            } else {
+              __stcg(Scur + gr, s);
+            }
+          }
+        }
+        first_row = false;
+        const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
+        if (d >= D)
+          break;
+        cur = TW + d;
+        have = true;
+        if (lane == 0)
+          grabbed = atomicAdd(&p.bar->row_counter, 1u);
+      }
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first row
-    if (PF_BATCHES > 0 && my_rows > 0u && k + 1u < p.max_iter) {
+    if (PF_BATCHES > 0 && gw < R && k + 1u < p.max_iter) {
       __syncwarp();
       if (lane == 0) {
-        const uint32_t rl = (p.sweep && ((k + 1u) & 1u)) ? (nrows - 1u - warp) : (uint32_t)warp;
+        const uint32_t rl = (p.sweep && ((k + 1u) & 1u)) ? (R - 1u - gw) : gw;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(my_bar, pf_floats * 4u);
-        bulk_load(my_pf, p.A + (size_t)(rb + rl) * N, pf_floats * 4u, my_bar);
+        bulk_load(my_pf, p.A + (size_t)rl * N, pf_floats * 4u, my_bar);
       }
       pf_issued++;
     }
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);
-    __syncthreads();
-
-    // ---- publish: s[r] = (A.e)[r] / e[r], to every rank when sharded ----
-    for (uint32_t r = tid; r < nrows; r += THREADS) {
-      const uint32_t gr = p.row0 + rb + r;
-      const float s = part_s[r] / e_s[gr];
-      if (p.world > 1) {
-        for (uint32_t g = 0; g < p.world; g++)
-          __stcg(p.peer_S[k & 1][g] + gr, s);
-      } else {
-        __stcg(Scur + gr, s);
-      }
-    }
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k] = globaltimer_ns();
 
     if (!round_barrier(p, k, &s_abort))
       break;
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k + 1u] = globaltimer_ns();
 
-    // ---- every CTA: one L2 trip for s, then max / circular stop / e update ----  :41-44
-    float sv[kPerThread];
+    // ---- every CTA: max / circular stop over the full s, then e update ----        :41-44
+    // 128-bit L2 loads, all loads of a batch issued before anything depends on them.  The
+    // circular neighbour of a vector's last element is the next lane's first element
+    // (shuffle); only lane 31 reads it from memory -- the reference does the same with
+    // shuffle_down + one global read per sub-group (:413-417).  Every CTA scans the same N
+    // floats at the same moment, so each starts at its own offset (cb) to stay off the other
+    // CTAs' L2 lines; max and the stop flag are order-independent.
+    const float4* S4 = reinterpret_cast<const float4*>(Scur);
+    float4* e4_s = reinterpret_cast<float4*>(e_s);
+    const uint32_t rotv = cb >> 2;
+    float4 sv4[kRegVec];
     float mx = 0.f; // reference zero-fills the max cell (:169)
     int ok = 1;
+    auto vec_index = [&](uint32_t idx) {
+      const uint32_t v = idx + rotv;
+      return v < nv ? v : v - nv;
+    };
+    auto scan4 = [&](const float4& v, float nxt) {
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      // strict <, wrap pair included (:413-421)
+      ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
+            (fabsf(v.w - nxt) < p.eps);
+    };
+    if (reg_tail) {
+      float nx[kRegVec];
 #pragma unroll
-    for (int j = 0; j < kPerThread; j++) {
-      const uint32_t c = tid + j * THREADS;
-      sv[j] = 0.f;
-      if (c < N) {
-        const float self = ld_cg(Scur + c);
-        const float next = ld_cg(Scur + (c + 1u == N ? 0u : c + 1u));
-        sv[j] = self;
-        mx = fmaxf(mx, self);
-        ok &= (fabsf(self - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+      for (int j = 0; j < kRegVec; j++) {
+        const uint32_t idx = tid + (uint32_t)j * THREADS;
+        const bool active = idx < nv;
+        const uint32_t vi = vec_index(idx);
+        sv4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool edge = active && (lane == 31 || idx + 1u >= nv);
+        nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kRegVec; j++) {
+        const uint32_t idx = tid + (uint32_t)j * THREADS;
+        if ((uint32_t)j * THREADS < nv) { // warp-uniform
+          float nxt = __shfl_down_sync(0xffffffffu, sv4[j].x, 1);
+          if (lane == 31 || idx + 1u >= nv)
+            nxt = nx[j];
+          if (idx < nv)
+            scan4(sv4[j], nxt);
+        }
+      }
+    } else {
+      for (uint32_t v0 = 0; v0 < nv; v0 += 4u * THREADS) {
+        float4 t4[4];
+        float nx[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
+          const bool active = idx < nv;
+          const uint32_t vi = vec_index(idx);
+          t4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool edge = active && (lane == 31 || idx + 1u >= nv);
+          nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
+          if (v0 + (uint32_t)j * THREADS < nv) { // warp-uniform
+            float nxt = __shfl_down_sync(0xffffffffu, t4[j].x, 1);
+            if (lane == 31 || idx + 1u >= nv)
+              nxt = nx[j];
+            if (idx < nv)
+              scan4(t4[j], nxt);
+          }
+        }
       }
     }
 #pragma unroll
@@ -196,8 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_sc_kernel(const RoundPa
     }
     __syncthreads();
     if (warp == 0) {
-      mx = lane < kWarps ? red_max[lane] : 0.f;
-      ok = lane < kWarps ? red_ok[lane] : 1;
+      mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
+      ok = (uint32_t)lane < kWarps ? red_ok[lane] : 1;
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -213,14 +312,39 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_sc_kernel(const RoundPa
     const bool converged = bc_ok != 0;
 
     // e_{k+1} = e_k * (s_k / m_k), in place in shared memory                       :260
+    auto update4 = [&](uint32_t vi, const float4& sv) {
+      float4 e = e4_s[vi];
+      e.x = e.x * (sv.x / m_k);
+      e.y = e.y * (sv.y / m_k);
+      e.z = e.z * (sv.z / m_k);
+      e.w = e.w * (sv.w / m_k);
+      e4_s[vi] = e;
+    };
+    if (reg_tail) {
 #pragma unroll
-    for (int j = 0; j < kPerThread; j++) {
-      const uint32_t c = tid + j * THREADS;
-      if (c < N)
-        e_s[c] = e_s[c] * (sv[j] / m_k);
+      for (int j = 0; j < kRegVec; j++) {
+        const uint32_t idx = tid + (uint32_t)j * THREADS;
+        if (idx < nv)
+          update4(vec_index(idx), sv4[j]);
+      }
+    } else {
+      for (uint32_t v0 = 0; v0 < nv; v0 += 4u * THREADS) {
+        float4 t4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
+          t4[j] = idx < nv ? ld_cg(S4 + vec_index(idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
+          if (idx < nv)
+            update4(vec_index(idx), t4[j]);
+        }
+      }
     }
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = globaltimer_ns();
+      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
     __syncthreads();
 
     if (converged || k + 1u == p.max_iter) {

@@ -207,8 +207,11 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     for (uint32_t c0 = 0; c0 < N; c0 += chunk) {
       const uint32_t clen = min(chunk, N - c0);
       __syncthreads();
-      for (uint32_t c = tid; c < clen; c += THREADS)
+      const uint32_t rot = cb % clen; // de-phase the CTAs on the L2 lines of E and S
+      for (uint32_t cc = tid; cc < clen; cc += THREADS) {
+        const uint32_t c = cc + rot < clen ? cc + rot : cc + rot - clen;
         scale_s[c] = first ? 1.f : ld_cg(Eprev + c0 + c) * (ld_cg(Sprev + c0 + c) / m_prev);
+      }
       __syncthreads();
       for (uint32_t ii = 0; ii < my_rows; ii++) {
         const uint32_t i = warp + ii * kWarps;
@@ -250,6 +253,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     }
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k] = globaltimer_ns();
     __syncthreads();
 
     for (uint32_t r = tid; r < nrows; r += THREADS) {
@@ -269,14 +274,39 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
       drain();
       return;
     }
+    if (blockIdx.x == 0 && tid == 0)
+      p.phase_ts[3u * k + 1u] = globaltimer_ns();
 
     float mx = 0.f;
     int ok = 1;
-    for (uint32_t c = tid; c < N; c += THREADS) {
-      const float self = ld_cg(Scur + c);
-      const float next = ld_cg(Scur + (c + 1u == N ? 0u : c + 1u));
-      mx = fmaxf(mx, self);
-      ok &= (fabsf(self - next) < p.eps) ? 1 : 0;
+    // every CTA scans the same vector at the same time: start each at its own offset (cb) so
+    // they do not queue on the same L2 lines; max / AND are order-independent.  The circular
+    // neighbour comes from the next lane by shuffle, as in the reference (:413-417); four
+    // batches of loads are in flight before anything depends on them.
+    for (uint32_t b0 = 0; b0 < N; b0 += 4u * THREADS) {
+      float sf[4], nx[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+        const bool active = c0 < N;
+        const uint32_t c = c0 + cb < N ? c0 + cb : c0 + cb - N;
+        sf[j] = active ? ld_cg(Scur + c) : 0.f;
+        const bool edge = active && (lane == 31 || c0 + 1u >= N);
+        nx[j] = edge ? ld_cg(Scur + (c + 1u == N ? 0u : c + 1u)) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+        if (b0 + (uint32_t)j * THREADS < N) { // warp-uniform
+          float next = __shfl_down_sync(0xffffffffu, sf[j], 1);
+          if (lane == 31 || c0 + 1u >= N)
+            next = nx[j];
+          if (c0 < N) {
+            mx = fmaxf(mx, sf[j]);
+            ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+          }
+        }
+      }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -306,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     const bool converged = bc_ok != 0;
 
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = globaltimer_ns();
+      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
 
     if (converged || k + 1u == p.max_iter) {
       for (uint32_t c = cb + tid; c < ce; c += THREADS)

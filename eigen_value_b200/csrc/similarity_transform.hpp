@@ -52,6 +52,7 @@ public:
   int solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
                  float* h_eigen_vec, st_result* res);
   const std::vector<uint64_t>& round_timestamps() const { return last_ts_; }
+  const std::vector<uint64_t>& phase_timestamps() const { return last_phase_ts_; }
 
   std::mutex& mutex() { return mu_; }
   void activate() const; // cudaSetDevice
@@ -85,6 +86,7 @@ private:
   size_t work_cap_ = 0;
   void* h_pinned_ = nullptr; // small pinned read-back block
   std::vector<uint64_t> last_ts_;
+  std::vector<uint64_t> last_phase_ts_;
 };
 
 // Row-block shard: this rank's exchange block (two N-float row-sum buffers + flags) and the

@@ -114,7 +114,8 @@ Context::reserve_vectors(uint32_t dim, uint32_t max_iter)
     cudaFree(d_ts_);
     d_ts_ = nullptr;
     ts_cap_ = 0;
-    ST_CUDA(cudaMalloc(&d_ts_, sizeof(unsigned long long) * (size_t)(max_iter + 2)));
+    // round stamps (max_iter + 2) followed by three phase stamps per round
+    ST_CUDA(cudaMalloc(&d_ts_, sizeof(unsigned long long) * 4 * (size_t)(max_iter + 2)));
     ts_cap_ = max_iter + 2;
   }
 }
@@ -144,15 +145,17 @@ Context::reserve_work(size_t elems)
 }
 
 // ---- launch of the round loop ------------------------------------------------------------
-template<int VEC, int FORM, int THREADS>
+// CTA size is a run-time value (a multiple of 32); the template parameter is only the
+// __launch_bounds__ ceiling (512 -> 128 registers/thread, 1024 -> 64).
+template<int VEC, int FORM, int MAX_THREADS>
 static void
-launch_round_loop(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+launch_round_loop(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_kernel<VEC, FORM, THREADS>;
+  auto kernel = round_loop_kernel<VEC, FORM, MAX_THREADS>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
-  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, smem,
                                       stream));
 }
 
@@ -160,14 +163,30 @@ template<int VEC, int FORM>
 static void
 launch_by_threads(int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
 {
-  switch (threads) {
-    case 256:
-      return launch_round_loop<VEC, FORM, 256>(p, grid, smem, stream);
-    case 1024:
-      return launch_round_loop<VEC, FORM, 1024>(p, grid, smem, stream);
-    default:
-      return launch_round_loop<VEC, FORM, 512>(p, grid, smem, stream);
+  if (threads <= 256)
+    return launch_round_loop<VEC, FORM, 256>(p, grid, threads, smem, stream);
+  if (threads <= 512)
+    return launch_round_loop<VEC, FORM, 512>(p, grid, threads, smem, stream);
+  return launch_round_loop<VEC, FORM, 1024>(p, grid, threads, smem, stream);
+}
+
+// Warp count for a CTA that owns `nrows` rows, one warp per row at a time: the count in
+// [lo, hi] that leaves the fewest warps idle in the last sweep (e.g. 55 rows: 14 warps x 4
+// sweeps = 56 slots instead of 16 x 4 = 64); ties go to the larger count.
+static int
+balanced_warps(uint32_t nrows, int lo, int hi)
+{
+  int best = hi;
+  double best_eff = -1.0;
+  for (int w = hi; w >= lo; w--) {
+    const uint32_t sweeps = (nrows + (uint32_t)w - 1u) / (uint32_t)w;
+    const double eff = (double)nrows / ((double)sweeps * w);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = w;
+    }
   }
+  return best;
 }
 
 // ---- TMA-streamed variant ---------------------------------------------------------------------
@@ -220,57 +239,57 @@ launch_tma(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t str
   }
 }
 
-// ---- single-chunk variant (N <= 8192): e resident in smem, fused tail, cross-barrier prefetch ----
+// ---- resident-e variant (N <= 32768): e in smem, fused tail, cross-barrier prefetch ----------
 struct ScConfig
 {
-  int id, threads, pf_batches;
+  int id, max_threads, pf_batches;
 };
-// the automatic choice takes the first entry that fits (id 13: 512 threads, one 4 KB batch
-// prefetched per warp -- measured best or tied at N = 1024..8192, profiles/r1_sweep_kernels_sc*.txt);
-// the others are tuning variants reachable through st_options.kernel
+// the automatic choice takes the first entry that fits (one 4 KB batch prefetched per warp --
+// measured best or tied at N = 1024..8192, profiles/r1_sweep_kernels_sc*.txt); the others are
+// tuning variants reachable through st_options.kernel
 static const ScConfig kScConfigs[] = {
   { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 }, { 14, 1024, 1 }, { 15, 1024, 0 },
   { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
 };
 
 static size_t
-sc_smem_bytes(const ScConfig& c, uint32_t chunk_cols, uint32_t rows_cap, uint32_t* mbar_offset)
+sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t rows_cap, uint32_t* mbar_offset)
 {
-  size_t off = (size_t)(c.threads / 32) * c.pf_batches * 1024 * sizeof(float);
-  off += (size_t)chunk_cols * sizeof(float);
+  size_t off = (size_t)(threads / 32) * pf_batches * 1024 * sizeof(float);
+  off += (size_t)cols * sizeof(float);
   off += (size_t)rows_cap * sizeof(float);
   off = (off + 15) & ~(size_t)15;
   *mbar_offset = (uint32_t)off;
-  return off + (size_t)(c.threads / 32) * sizeof(uint64_t);
+  return off + (size_t)(threads / 32) * sizeof(uint64_t);
 }
 
-template<int THREADS, int PF, int LD = kUnroll>
+template<int MAX_THREADS, int PF, int LD = kUnroll>
 static void
-launch_sc_one(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_sc_kernel<THREADS, PF, LD>;
+  auto kernel = round_loop_sc_kernel<MAX_THREADS, PF, LD>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
-  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, smem,
                                       stream));
 }
 
 static void
-launch_sc(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+launch_sc(int id, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
   switch (id) {
-    case 10: return launch_sc_one<512, 2>(p, grid, smem, stream);
-    case 11: return launch_sc_one<512, 0>(p, grid, smem, stream);
-    case 12: return launch_sc_one<512, 3>(p, grid, smem, stream);
-    case 16: return launch_sc_one<256, 2, 16>(p, grid, smem, stream);
-    case 17: return launch_sc_one<256, 4, 16>(p, grid, smem, stream);
-    case 18: return launch_sc_one<256, 0, 16>(p, grid, smem, stream);
-    case 19: return launch_sc_one<256, 1, 16>(p, grid, smem, stream);
-    case 13: return launch_sc_one<512, 1>(p, grid, smem, stream);
-    case 14: return launch_sc_one<1024, 1>(p, grid, smem, stream);
-    case 15: return launch_sc_one<1024, 0>(p, grid, smem, stream);
-    default: throw std::invalid_argument("unknown single-chunk kernel id");
+    case 10: return launch_sc_one<512, 2>(p, grid, threads, smem, stream);
+    case 11: return launch_sc_one<512, 0>(p, grid, threads, smem, stream);
+    case 12: return launch_sc_one<512, 3>(p, grid, threads, smem, stream);
+    case 13: return launch_sc_one<512, 1>(p, grid, threads, smem, stream);
+    case 14: return launch_sc_one<1024, 1>(p, grid, threads, smem, stream);
+    case 15: return launch_sc_one<1024, 0>(p, grid, threads, smem, stream);
+    case 16: return launch_sc_one<256, 2, 16>(p, grid, threads, smem, stream);
+    case 17: return launch_sc_one<256, 4, 16>(p, grid, threads, smem, stream);
+    case 18: return launch_sc_one<256, 0, 16>(p, grid, threads, smem, stream);
+    case 19: return launch_sc_one<256, 1, 16>(p, grid, threads, smem, stream);
+    default: throw std::invalid_argument("unknown resident-e kernel id");
   }
 }
 
@@ -339,55 +358,65 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   p.out_eigen_val = d_scalars_;
   p.out_iter = reinterpret_cast<uint32_t*>(d_scalars_ + 1);
   p.round_ts = d_ts_;
+  p.phase_ts = d_ts_ + ts_cap_;
 
-  // launch shape: one persistent CTA per SM, fewer when there are fewer rows than warps
-  int threads = opt.threads == 256 || opt.threads == 1024 ? opt.threads : 512;
-  int grid = opt.ctas > 0 ? opt.ctas : sm_count_;
-  const int warps = threads / 32;
-  const int useful = (int)std::max<uint32_t>(1u, (rows + (uint32_t)warps - 1u) / (uint32_t)warps);
-  grid = std::max(1, std::min(grid, std::min(useful, sm_count_)));
-  uint32_t rows_cap = (rows + (uint32_t)grid - 1u) / (uint32_t)grid + 1u;
-  size_t smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
+  // ---- launch plan ------------------------------------------------------------------------
+  // one persistent CTA per SM (fewer when there are fewer rows than warps); CTA size = the warp
+  // count that divides the CTA's rows best unless st_options.threads pins it.
+  // kernel: 0 = automatic (resident-e kernel when N <= 32768, else the general chunked loop),
+  // 1 = general loop, 2-9 = TMA ring configurations, 10-19 = resident-e configurations.
   const bool vec4 = (dim % 4u == 0u) && aligned16(d_rows) && (!p.W || aligned16(p.W));
+  const int pinned = opt.threads > 0 ? std::min(1024, (opt.threads + 31) / 32 * 32) : 0;
+  auto shape = [&](int max_threads, bool balance, int* out_grid, int* out_threads, uint32_t* out_cap) {
+    const int hi = (pinned ? std::min(pinned, max_threads) : max_threads) / 32;
+    int g = opt.ctas > 0 ? opt.ctas : sm_count_;
+    const int use = (int)std::max<uint32_t>(1u, (rows + (uint32_t)hi - 1u) / (uint32_t)hi);
+    g = std::max(1, std::min(g, std::min(use, sm_count_)));
+    const uint32_t per_cta = (rows + (uint32_t)g - 1u) / (uint32_t)g;
+    // the resident-e kernel schedules rows dynamically and always wants every warp
+    const int lo = (pinned || !balance) ? hi : std::max(1, std::min(hi, max_threads >= 512 ? 12 : 6));
+    *out_grid = g;
+    *out_threads = 32 * balanced_warps(per_cta, lo, hi);
+    *out_cap = per_cta + 1u;
+  };
 
-  // kernel choice: 0 = automatic (TMA-streamed when eligible), 1 = register-staged LDG kernel,
-  // >= 2 = a specific TMA configuration
+  int threads = 512, grid = sm_count_;
+  uint32_t rows_cap = 0;
+  size_t smem = 0;
   const TmaConfig* tma = nullptr;
   const ScConfig* sc = nullptr;
-  const bool sc_ok = vec4 && form == kFormReadOnly && dim <= (uint32_t)kChunkCols;
-  if ((opt.kernel == 0 || opt.kernel >= 10) && sc_ok) {
+  const bool readonly4 = vec4 && form == kFormReadOnly;
+  if (opt.kernel >= 10 || (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols)) {
+    if (!readonly4 || dim > (uint32_t)kResidentCols)
+      throw std::invalid_argument("solve: resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
-      if (opt.kernel == 0 && opt.threads != 0 && c.threads != opt.threads)
+      if (opt.kernel == 0 && pinned > c.max_threads)
         continue;
-      int g = opt.ctas > 0 ? opt.ctas : sm_count_;
-      const int w = c.threads / 32;
-      const int use = (int)std::max<uint32_t>(1u, (rows + (uint32_t)w - 1u) / (uint32_t)w);
-      g = std::max(1, std::min(g, std::min(use, sm_count_)));
-      const uint32_t cap = (rows + (uint32_t)g - 1u) / (uint32_t)g + 1u;
-      uint32_t moff = 0;
-      const size_t need = sc_smem_bytes(c, p.chunk_cols, cap, &moff);
+      int g, t;
+      uint32_t cap, moff = 0;
+      shape(c.max_threads, false, &g, &t, &cap);
+      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, cap, &moff);
       if (need <= kSmemLimit) {
         sc = &c;
         grid = g;
-        threads = c.threads;
+        threads = t;
         rows_cap = cap;
         smem = need;
         p.mbar_offset = moff;
+        p.chunk_cols = dim; // the whole eigenvector is resident
         break;
       }
     }
     if (!sc && opt.kernel >= 10)
-      throw std::invalid_argument("solve: requested single-chunk kernel configuration does not fit");
-  } else if (opt.kernel >= 10) {
-    throw std::invalid_argument("solve: single-chunk kernel needs the read-only form, dim % 4 == 0, dim <= 8192");
+      throw std::invalid_argument("solve: requested resident-e kernel configuration does not fit");
   }
-  if (!sc && opt.kernel >= 2 && opt.kernel < 10 && vec4 && form == kFormReadOnly) {
+  if (!sc && opt.kernel >= 2 && opt.kernel < 10) {
+    if (!readonly4)
+      throw std::invalid_argument("solve: TMA kernel needs the read-only form and dim % 4 == 0");
     for (const TmaConfig& c : kTmaConfigs) {
-      if (opt.kernel >= 2 && c.id != opt.kernel)
-        continue;
-      if (opt.kernel == 0 && opt.threads != 0 && c.threads != opt.threads)
+      if (c.id != opt.kernel)
         continue;
       int g = opt.ctas > 0 ? opt.ctas : sm_count_;
       const int w = c.threads / 32;
@@ -403,20 +432,21 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         rows_cap = cap;
         smem = need;
         p.mbar_offset = moff;
-        break;
       }
     }
-    if (!tma && opt.kernel >= 2)
+    if (!tma)
       throw std::invalid_argument("solve: requested TMA kernel configuration does not fit");
-  } else if (opt.kernel >= 2 && opt.kernel < 10) {
-    throw std::invalid_argument("solve: TMA kernel needs the read-only form and dim % 4 == 0");
+  }
+  if (!sc && !tma) {
+    shape(pinned > 512 ? 1024 : 512, true, &grid, &threads, &rows_cap);
+    smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
   }
 
   ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
   if (sc) {
-    launch_sc(sc->id, p, grid, smem, stream_);
+    launch_sc(sc->id, p, grid, threads, smem, stream_);
   } else if (tma) {
     launch_tma(tma->id, p, grid, smem, stream_);
   } else if (vec4) {
@@ -452,6 +482,9 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const uint32_t passes = words[2];
   last_ts_.assign((size_t)passes + 1, 0);
   ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)passes + 1),
+                     cudaMemcpyDeviceToHost));
+  last_phase_ts_.assign(3 * (size_t)passes, 0);
+  ST_CUDA(cudaMemcpy(last_phase_ts_.data(), d_ts_ + ts_cap_, sizeof(uint64_t) * 3 * (size_t)passes,
                      cudaMemcpyDeviceToHost));
 
   if (res) {

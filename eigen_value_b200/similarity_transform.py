@@ -225,6 +225,24 @@ class Solver:
                   "st_round_timestamps")
         return out
 
+    def phase_breakdown(self) -> dict:
+        """Median microseconds per round of the last solve, split at CTA 0's stamps:
+        matrix pass | barrier (+ exchange) | vector tail."""
+        n = ctypes.c_uint32()
+        check(self.lib.st_phase_timestamps(self.ctx, None, 0, ctypes.byref(n)), "st_phase_timestamps")
+        ph = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            check(self.lib.st_phase_timestamps(self.ctx, _ptr(ph), n.value, ctypes.byref(n)),
+                  "st_phase_timestamps")
+        rounds = self.round_timestamps().astype(np.int64)
+        ph = ph.astype(np.int64).reshape(-1, 3)
+        if len(ph) == 0:
+            return {}
+        start = rounds[:-1]
+        med = lambda a: float(np.median(a)) * 1e-3
+        return {"pass_us": med(ph[:, 0] - start), "barrier_us": med(ph[:, 1] - ph[:, 0]),
+                "tail_us": med(ph[:, 2] - ph[:, 1]), "rounds": int(len(ph))}
+
     # ---- per-kernel calls (reference L1 functions), numpy in / numpy out -------------------
     def sum_across_rows(self, mat: np.ndarray) -> np.ndarray:
         n = mat.shape[0]

@@ -145,6 +145,10 @@ int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options*
                   float* h_eigen_val, float* h_eigen_vec, st_result* res);
 /* Per-round device timestamps (ns, globaltimer) of the last solve on this context. */
 int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
+/* Three stamps per round of the last solve, taken by CTA 0: matrix pass done, round barrier
+ * (incl. the cross-GPU exchange) passed, vector tail done -- the per-phase split the
+ * reference's per-kernel benchmarks give (benchmarks/similarity_transform.md). */
+int st_phase_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
 
 /* Per-kernel entry points on device buffers, one per reference L1 function
  * (include/similarity_transform.hpp:55-100; similarity_transform.cpp:77-460). */

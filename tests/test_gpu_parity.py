@@ -184,6 +184,19 @@ def test_launch_shape_and_sweep_do_not_change_results(solver, threads, sweep):
     assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec)
 
 
+@pytest.mark.parametrize("dim", [256, 4096, 8192, 16384])
+def test_kernel_variants_are_bitwise_identical(solver, dim):
+    """general chunked loop (1), TMA ring (2, 5), resident-e kernel (13, 10, 11): one evaluation
+    order, so every variant returns the same bits."""
+    d = solver.uniform(dim, 0x5EED0000 + dim)
+    base, base_vec = solver.solve_device(d, dim, kernel=1, max_iter=6)
+    for kid in (0, 2, 5, 13, 10, 11):
+        info, vec = solver.solve_device(d, dim, kernel=kid, max_iter=6)
+        assert info.iter_count == base.iter_count, kid
+        assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec), kid
+        assert info.kernel_id == (kid if kid else 13)
+
+
 def test_max_iter_cap_reports_cap(solver):
     # never-converging case: iter_count == max_iter (reference similarity_transform.cpp:39,54)
     d = solver.hilbert(512)
