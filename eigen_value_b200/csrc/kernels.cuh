@@ -54,10 +54,13 @@ struct RoundParams
   float eps;
   uint32_t max_iter;
   int sweep;           // 1: alternate the row order every round (L2 reuse of the pass tail)
+  int dynamic;         // resident-e kernel: hand out work units through an atomic counter
   uint32_t keep_rows_pct; // share of each CTA's rows loaded L2 evict_last (rest evict_first); 0: no hints
   uint32_t chunk_cols; // columns staged per chunk (<= kChunkCols)
   uint32_t mbar_offset; // TMA variant: byte offset of the mbarrier array in dynamic smem
   BarrierState* bar;
+  float* partial;         // resident-e kernel: chunk sums of multi-unit rows, rows x units
+  unsigned int* row_done; // resident-e kernel: per-row arrival counters (monotonic)
   unsigned long long timeout_ns;
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;

@@ -31,63 +31,53 @@ namespace st {
 constexpr int kResidentCols = 32768; // largest N whose eigenvector is kept in shared memory
 constexpr int kRegVec = 5;           // float4 of s a thread keeps in registers across the tail
 
-// one row: the leading `npre` float4 come from the prefetched shared-memory tile, the rest
-// from global memory.  npre is a multiple of 256 (one batch = 32 lanes x 8 accumulators), at
-// most one 8192-column chunk, or nv.
-// Evaluation order = round_loop_kernel's, for any N: the row is cut into 8192-column chunks;
-// inside a chunk vector j goes to lane j % 32, accumulator (j / 32) % 8, the accumulators are
-// folded pairwise and the lanes by an xor-shuffle tree; chunk sums are added left to right.
-// LD = independent 128-bit loads in flight per lane (8 or 16) and does not affect the order.
+// One work unit = one 8192-column chunk of one row (<= 32 KB), reduced by one warp.  The
+// leading `npre` float4 come from the prefetched shared-memory tile, the rest from global
+// memory; npre is a multiple of 256 (one batch = 32 lanes x 8 accumulators) or the whole unit.
+// Evaluation order = round_loop_kernel's: vector j of the chunk goes to lane j % 32,
+// accumulator (j / 32) % 8, the accumulators are folded pairwise and the lanes by an
+// xor-shuffle tree; the chunk sums of a row are added left to right by whoever finishes the
+// row.  LD = independent 128-bit loads in flight per lane (8 or 16); it does not affect the order.
 template<int LD>
 __device__ __forceinline__ float
-row_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane,
-                   const float4* pf, uint32_t npre)
+chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane,
+                     const float4* pf, uint32_t npre)
 {
   static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
-  constexpr uint32_t kChunkVec = kChunkCols / 4;
-  float total = 0.f;
-  for (uint32_t base = 0; base < nv; base += kChunkVec) {
-    const uint32_t end = min(nv, base + kChunkVec);
-    float acc[kUnroll];
+  float acc[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-      acc[u] = 0.f;
-    uint32_t i = base + (uint32_t)lane;
-    if (base == 0u) {
-      for (uint32_t b0 = 0; b0 < npre; b0 += 32u * kUnroll) {
+  for (int u = 0; u < kUnroll; u++)
+    acc[u] = 0.f;
+  for (uint32_t b0 = 0; b0 < npre; b0 += 32u * kUnroll) {
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
-          const uint32_t j = b0 + lane + 32u * u;
-          if (j < npre)
-            acc[u] = dot_acc(pf[j], es[j], acc[u]);
-        }
-      }
-      i += npre;
+    for (int u = 0; u < kUnroll; u++) {
+      const uint32_t j = b0 + lane + 32u * u;
+      if (j < npre)
+        acc[u] = dot_acc(pf[j], es[j], acc[u]);
     }
-    for (; i + 32u * (LD - 1) < end; i += 32u * LD) {
-      float4 v[LD];
-#pragma unroll
-      for (int u = 0; u < LD; u++)
-        v[u] = ld_stream(a + i + 32u * u);
-#pragma unroll
-      for (int u = 0; u < LD; u++)
-        acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
-    }
-#pragma unroll
-    for (int u = 0; u < LD; u++) {
-      const uint32_t j = i + 32u * u;
-      if (j < end)
-        acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[j], acc[u % kUnroll]);
-    }
-#pragma unroll
-    for (int s = kUnroll / 2; s >= 1; s >>= 1)
-#pragma unroll
-      for (int u = 0; u < s; u++)
-        acc[u] += acc[u + s];
-    const float t = warp_sum(acc[0]);
-    total = base == 0u ? t : total + t;
   }
-  return total;
+  uint32_t i = npre + (uint32_t)lane;
+  for (; i + 32u * (LD - 1) < nv; i += 32u * LD) {
+    float4 v[LD];
+#pragma unroll
+    for (int u = 0; u < LD; u++)
+      v[u] = ld_stream(a + i + 32u * u);
+#pragma unroll
+    for (int u = 0; u < LD; u++)
+      acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
+  }
+#pragma unroll
+  for (int u = 0; u < LD; u++) {
+    const uint32_t j = i + 32u * u;
+    if (j < nv)
+      acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[j], acc[u % kUnroll]);
+  }
+#pragma unroll
+  for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+    for (int u = 0; u < s; u++)
+      acc[u] += acc[u + s];
+  return warp_sum(acc[0]);
 }
 
 template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll>
@@ -117,18 +107,25 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // slice of the N-vector this CTA writes at the end (and its phase offset in the tail scan)
   const uint32_t cb = (uint32_t)((uint64_t)N * blockIdx.x / gridDim.x);
   const uint32_t ce = (uint32_t)((uint64_t)N * (blockIdx.x + 1) / gridDim.x);
-  // Row scheduling: warp gw of the grid takes row gw first (static, so its head can be
-  // prefetched across the barrier); the remaining R - TW rows are handed out through one
-  // atomic counter, so SMs that stream faster (L2 die locality) simply take more rows.  A
-  // row is always reduced by one warp in one fixed order: WHO takes it cannot change a bit.
+  // Scheduling: the work unit is one 8192-column chunk of one row (32 KB; a row of N = 32768
+  // is 4 units).  Warp gw of the grid takes unit gw first (static, so its head can be
+  // prefetched across the barrier); the remaining U - TW units are handed out through one
+  // atomic counter, so SMs that stream faster (L2 die locality) simply take more, and the
+  // end-of-round straggle is one 32 KB unit whatever N is.  A unit is always reduced by one
+  // warp in one fixed order and the chunk sums of a row are added left to right: WHO takes a
+  // unit cannot change a bit.
   const uint32_t R = p.rows;
+  const uint32_t nch = (N + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols; // units per row
+  const uint32_t U = R * nch;
   const uint32_t TW = gridDim.x * kWarps;
   const uint32_t gw = blockIdx.x * kWarps + warp;
-  const uint32_t D = R > TW ? R - TW : 0u; // dynamically scheduled rows per round
+  // (p.dynamic == 0: the remaining units are taken round-robin, gw + TW, gw + 2 TW, ... -- for
+  // small, L2-resident matrices the one-address atomic stream costs more than the skew it removes)
+  const uint32_t D = (p.dynamic && U > TW) ? U - TW : 0u; // dynamically scheduled units per round
+  constexpr uint32_t kChunkVec = kChunkCols / 4;
 
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
-  const uint32_t pf_floats = PF_BATCHES > 0 ? min(kPfFloats, N) : 0u;
   if (PF_BATCHES > 0 && lane == 0)
     mbar_init(my_bar, 1u);
   for (uint32_t c = tid; c < N; c += THREADS)
@@ -149,57 +146,103 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     // ---- the pass over the matrix ----                                   reference :40 (+ :52)
     bool tma_ok = true;
     {
-      // the counter is monotonic: every warp makes exactly one failing grab per round, so round
-      // k hands out the values [k * (D + TW), k * (D + TW) + D)
+      // publish s[r] = (A.e)[r] / e[r] -- to every rank when sharded
+      auto publish = [&](uint32_t rl, float t) {
+        const uint32_t gr = p.row0 + rl;
+        const float s = t / e_s[gr];
+        if (p.world > 1) {
+          for (uint32_t g = 0; g < p.world; g++)
+            __stcg(p.peer_S[k & 1][g] + gr, s);
+        } else {
+          __stcg(Scur + gr, s);
+        }
+      };
+      // lane 0: a row of several units is finished by the warp whose arrival completes it
+      auto finish_row = [&](uint32_t rl, uint32_t old) {
+        if (old % nch == nch - 1u) { // the per-row counter is monotonic: + nch per round
+          __threadfence();
+          float part[4];
+#pragma unroll
+          for (uint32_t c = 0; c < 4u; c++)
+            part[c] = c < nch ? ld_cg(p.partial + (size_t)rl * nch + c) : 0.f;
+          float t = part[0];
+#pragma unroll
+          for (uint32_t c = 1; c < 4u; c++)
+            if (c < nch)
+              t = t + part[c]; // left to right, like round_loop_kernel's part_s[rl] += t
+          publish(rl, t);
+        }
+      };
+      // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
+      // so round k hands out the values [k * (D + TW), k * (D + TW) + D)
       const uint32_t base = k * (D + TW);
       uint32_t cur = gw;
-      bool have = cur < R;
-      bool first_row = true;
-      uint32_t grabbed = 0;
-      if (lane == 0)
+      bool have = cur < U;
+      bool first_unit = true;
+      uint32_t grabbed = 0, pend_row = 0, pend_old = 0;
+      bool pending = false;
+      if (p.dynamic && lane == 0)
         grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
       for (;;) {
         if (have) {
-          const uint32_t rl = backward ? (R - 1u - cur) : cur;
-          const float4* row = reinterpret_cast<const float4*>(p.A + (size_t)rl * N);
+          const uint32_t u = backward ? (U - 1u - cur) : cur;
+          const uint32_t rl = u / nch;
+          const uint32_t ch = u - rl * nch;
+          const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
+          const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
           uint32_t npre = 0;
-          if (PF_BATCHES > 0 && first_row && pf_consumed < pf_issued) {
+          if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
             tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
             pf_consumed++;
-            npre = pf_floats >> 2;
+            npre = min(kPfFloats >> 2, seg_nv);
           }
-          const float t = row_dot_prefetched<LD>(row, reinterpret_cast<const float4*>(e_s), nv, lane,
-                                                 reinterpret_cast<const float4*>(my_pf), npre);
-          // publish: s[r] = (A.e)[r] / e[r], to every rank when sharded
+          const float t = chunk_dot_prefetched<LD>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec,
+                                                   seg_nv, lane, reinterpret_cast<const float4*>(my_pf), npre);
           if (lane == 0) {
-            const uint32_t gr = p.row0 + rl;
-            const float s = t / e_s[gr];
-            if (p.world > 1) {
-              for (uint32_t g = 0; g < p.world; g++)
-                __stcg(p.peer_S[k & 1][g] + gr, s);
+            if (pending)
+              finish_row(pend_row, pend_old); // the atomic issued one unit ago has long returned
+            pending = false;
+            if (nch == 1u) {
+              publish(rl, t);
             } else {
-              __stcg(Scur + gr, s);
+              __stcg(p.partial + (size_t)rl * nch + ch, t);
+              __threadfence();
+              pend_old = atomicAdd(p.row_done + rl, 1u);
+              pend_row = rl;
+              pending = true;
             }
           }
         }
-        first_row = false;
-        const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
-        if (d >= D)
-          break;
-        cur = TW + d;
+        first_unit = false;
+        if (p.dynamic) {
+          const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
+          if (d >= D)
+            break;
+          cur = TW + d;
+          if (lane == 0)
+            grabbed = atomicAdd(&p.bar->row_counter, 1u);
+        } else {
+          cur += TW;
+          if (cur >= U)
+            break;
+        }
         have = true;
-        if (lane == 0)
-          grabbed = atomicAdd(&p.bar->row_counter, 1u);
       }
+      if (lane == 0 && pending)
+        finish_row(pend_row, pend_old);
     }
-    // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first row
-    if (PF_BATCHES > 0 && gw < R && k + 1u < p.max_iter) {
+    // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
+    if (PF_BATCHES > 0 && gw < U && k + 1u < p.max_iter) {
       __syncwarp();
       if (lane == 0) {
-        const uint32_t rl = (p.sweep && ((k + 1u) & 1u)) ? (R - 1u - gw) : gw;
+        const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - gw) : gw;
+        const uint32_t rl = u / nch;
+        const uint32_t ch = u - rl * nch;
+        const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
+        const uint32_t bytes = min(kPfFloats >> 2, seg_nv) * 16u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_expect_tx(my_bar, pf_floats * 4u);
-        bulk_load(my_pf, p.A + (size_t)rl * N, pf_floats * 4u, my_bar);
+        mbar_arrive_expect_tx(my_bar, bytes);
+        bulk_load(my_pf, p.A + (size_t)rl * N + (size_t)ch * kChunkCols, bytes, my_bar);
       }
       pf_issued++;
     }

@@ -334,7 +334,10 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   float* d_out_vec = d_eigen_vec ? d_eigen_vec : v + 4 * cap;
   p.eps = opt.eps;
   p.max_iter = opt.max_iter;
-  p.sweep = opt.sweep;
+  p.sweep = opt.sweep & 1;
+  // st_options.sweep bit 1 forces static, bit 2 forces dynamic unit scheduling; default: dynamic
+  // once a unit is a full 32 KB chunk (N >= 8192), where the matrix no longer lives in L2
+  p.dynamic = (opt.sweep & 4) ? 1 : (opt.sweep & 2) ? 0 : (dim >= (uint32_t)kChunkCols ? 1 : 0);
   p.keep_rows_pct = (uint32_t)std::max(0, std::min(100, opt.l2_keep_pct));
   p.chunk_cols = std::min<uint32_t>((uint32_t)kChunkCols, dim);
   p.bar = d_bar_;
@@ -406,6 +409,14 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         smem = need;
         p.mbar_offset = moff;
         p.chunk_cols = dim; // the whole eigenvector is resident
+        const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
+        if (units > 1u) {
+          // chunk sums + per-row arrival counters of rows that span several work units
+          reserve_work((size_t)rows * units + rows);
+          p.partial = d_work_;
+          p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
+          ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * rows, stream_));
+        }
         break;
       }
     }

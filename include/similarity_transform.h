@@ -83,8 +83,9 @@ typedef struct st_options
   float eps;         /* stop threshold, reference EPS                               */
   uint32_t max_iter; /* round cap, reference MAX_ITR                                */
   int32_t form;      /* ST_FORM_*                                                   */
-  int32_t sweep;     /* 0: rows always ascending; 1: alternate direction per round
-                        so the tail of one pass is the L2-resident head of the next */
+  int32_t sweep;     /* bit 0: alternate the row order every round so the tail of one pass is
+                        the L2-resident head of the next (default on); bit 1 / bit 2: force
+                        static / dynamic work-unit scheduling in the resident-e kernel    */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
   int32_t kernel;    /* 0 = default round kernel; others are tuning variants        */
