@@ -24,6 +24,11 @@ MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
 FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
 
+
+def sum_workgroup(wg_size: int) -> int:
+    """The reference's literal two-level summation order for a given work-group size."""
+    return 3 | (int(wg_size) << 8)
+
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 

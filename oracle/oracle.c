@@ -5,14 +5,19 @@
  * file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and there only as the checker / the timed CPU baseline.
  *
- * Parity status: PINNED against the reference's own known answers
+ * Parity status: PINNED, two ways.
+ * (1) Against the reference's own known answers (tests/test_oracle_golden.py):
  *   - 3x3 golden eigenpair            (reference tests/test.cpp:84-102, main.py:52-58)
  *   - Hilbert round counts 9..17      (reference README.md:70-76, all six devices)
  *   - per-kernel unit fixtures         (reference tests/test.cpp:22-73, utils.cpp:5-122)
  *   - A.v ~= lambda.v acceptance test  (reference wrapper/python/test.py:15-16)
- * and, additionally, against the unmodified reference sources compiled on a CPU SYCL shim
- * (oracle/_ref, see oracle/Makefile) when that build is present.
- * The reference's SYCL build itself (dpcpp) is not available in this image.
+ * (2) Against outputs of the reference ITSELF run here (tests/test_reference_golden.py): the
+ *   unmodified reference sources are compiled against a single-threaded CPU SYCL shim
+ *   (oracle/sycl_shim, `make -C oracle ref` -> oracle/_ref/libreference_cpu.so); with the
+ *   reference's own summation order (ORACLE_SUM_WORKGROUP) this file reproduces lambda, the
+ *   eigenvector and iter_count BIT FOR BIT on every case, and the committed fixture
+ *   tests/golden/reference_sycl.json carries those outputs to boxes without the reference tree.
+ * The reference's real SYCL toolchain (dpcpp) is not available in this image.
  *
  * Every function cites the reference lines it restates (paths relative to the reference
  * repository root).  Arithmetic is strict fp32: build with -ffp-contract=off and without
@@ -41,9 +46,16 @@ enum
 {
   ORACLE_SUM_SEQUENTIAL = 0, /* left-to-right fp32 */
   ORACLE_SUM_LANES16 = 1,    /* 16 strided partial sums, combined pairwise (vectorisable) */
-  ORACLE_SUM_SUBGROUP32 = 2  /* 32-wide group sums added left to right: the shape of the
+  ORACLE_SUM_SUBGROUP32 = 2, /* 32-wide group sums added left to right: the shape of the
                                 reference's reduce_over_group + atomic adds
                                 (similarity_transform.cpp:119-146), one of its legal orders */
+  ORACLE_SUM_WORKGROUP = 3   /* | (wg_size << 8): the reference's literal two-level order for a
+                                given work-group size -- per work-group of wg_size columns the
+                                32-lane butterfly sums are added into local memory in sub-group
+                                order (:119-132), the work-group totals into the row's global
+                                cell in work-group order (:139-146).  This is the order the
+                                reference executes on oracle/sycl_shim, so the oracle can be
+                                compared with the real sources bit for bit. */
 };
 
 int
@@ -101,6 +113,26 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
       for (size_t c = 0; c < n; c++)
         acc += row[c];
     return acc;
+  }
+  if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {
+    const size_t wg = (size_t)(sum_mode >> 8);
+    float cell = 0.f; /* the zero-filled global cell (:85-93) */
+    for (size_t g0 = 0; g0 < n; g0 += wg) {
+      float lds = 0.f; /* work-group leader resets local memory (:108-110) */
+      for (size_t s0 = g0; s0 < g0 + wg && s0 < n; s0 += 32) {
+        float v[32];
+        for (int l = 0; l < 32; l++) {
+          size_t c = s0 + (size_t)l;
+          v[l] = (c < g0 + wg && c < n) ? (scale ? row[c] * scale[c] : row[c]) : 0.f;
+        }
+        for (int w = 16; w >= 1; w >>= 1)
+          for (int l = 0; l < w; l++)
+            v[l] = v[l] + v[l + w];
+        lds += v[0];
+      }
+      cell += lds;
+    }
+    return cell;
   }
   if (sum_mode == ORACLE_SUM_SUBGROUP32) {
     float acc = 0.f;

@@ -234,3 +234,20 @@ def test_full_size_property_uniform_32768(solver):
         a = oracle.uniform(dim, 0x5EED0001, row0=r, rows=1)[0].astype(np.float64)
         lhs = float(a @ vec.astype(np.float64))
         assert abs(lhs - float(info.eigen_val) * float(vec[r])) <= 1e-5 * abs(lhs)
+
+
+# ---- the CUDA path against outputs of the reference itself (tests/golden/reference_sycl.json) ----
+from golden_util import build_matrix as _golden_matrix, expected as _golden_expected, load_reference_cases  # noqa: E402
+
+_GOLDEN_CASES = load_reference_cases()["cases"]
+
+
+@pytest.mark.parametrize("case", _GOLDEN_CASES, ids=[c["name"] for c in _GOLDEN_CASES])
+def test_cuda_matches_the_reference_own_outputs(ev, case):
+    """Fixture = what the unmodified reference C++ returned on the CPU SYCL shim
+    (tests/golden/make_reference_golden.py).  Through make_queue/max_eigen_value the CUDA path
+    must agree within BASELINE.json's tolerances."""
+    mat = _golden_matrix(case)
+    r_val, r_vec, r_it = _golden_expected(case)
+    val, vec, ms, it = ev.similarity_transform(mat)
+    assert_parity((val, vec, it), (r_val, r_vec, r_it), same_rounds=case["kind"] != "uniform")
