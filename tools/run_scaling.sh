@@ -6,7 +6,7 @@ TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q 2>&1 | tail -6
 for n in 2 4 8; do
   timeout 300 $TR --nproc-per-node $n --master-port $((29600 + n)) bench.py --gpus $n --steps 5 --warmup 3 2>/dev/null | grep '^{' > gpurun_out/scale_hilbert32768_n$n.json
-  cut -c1-400 gpurun_out/scale_hilbert32768_n$n.json
+  cut -c1-330 gpurun_out/scale_hilbert32768_n$n.json
 done
 timeout 300 python bench.py --workload hilbert-32768 --steps 5 --no-cpu-baseline --no-sweep-table 2>/dev/null | grep '^{' > gpurun_out/scale_hilbert32768_n1.json
 cut -c1-400 gpurun_out/scale_hilbert32768_n1.json
@@ -14,3 +14,5 @@ timeout 600 $TR --nproc-per-node 8 --master-port 29650 bench.py --gpus 8 --workl
 cut -c1-1200 gpurun_out/scale_hilbert131072_n8.json
 timeout 600 $TR --nproc-per-node 8 --master-port 29651 bench.py --gpus 8 --workload uniform-131072 --steps 1 --warmup 3 --no-e2e 2>/dev/null | grep '^{' > gpurun_out/scale_uniform131072_n8.json
 cut -c1-1200 gpurun_out/scale_uniform131072_n8.json
+timeout 600 $TR --nproc-per-node 8 --master-port 29652 bench.py --gpus 8 --workload uniform-65536 --steps 1 --warmup 3 --no-e2e 2>/dev/null | grep '^{' > gpurun_out/scale_uniform65536_n8.json
+cut -c1-1200 gpurun_out/scale_uniform65536_n8.json
