@@ -285,12 +285,20 @@ def main():
             infos.append(step())
         barrier()
         wall1 = time.perf_counter()
-        if len(clocks.samples) < 5:      # very short timed region: keep sampling the same steps
-            t_end = time.perf_counter() + 1.0
-            while time.perf_counter() < t_end:
+        phase = solver.phase_breakdown()  # CTA 0 of this rank, last timed solve: pass | barrier(+exchange) | tail
+        # Very short timed region: keep sampling clocks over more of the same steps.  A sharded
+        # solve is collective, so every rank must run the SAME number of extra steps: the count
+        # comes from the slowest rank's timed region, not from a local clock.
+        local_ms = max(1e-3, (wall1 - wall0) * 1e3)
+        t = torch.tensor([local_ms, -float(len(clocks.samples))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if -float(t[1]) < 5:
+            extra = int(min(2000, max(1, 1000.0 / (float(t[0]) / args.steps))))
+            for _ in range(extra):
                 step()
+            barrier()
     clk = clocks.summary()
-    phase = solver.phase_breakdown()      # CTA 0 of this rank, last solve: pass | barrier(+exchange) | tail
 
     dev_ms = sum(i.loop_ms for i in infos)              # CUDA events on the solver's stream
     passes = sum(i.passes for i in infos)

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q 2>&1 | tail -6
 for n in 2 4 8; do
-  timeout 300 $TR --nproc-per-node $n --master-port $((29600 + n)) bench.py --gpus $n --steps 5 --warmup 3 2>/dev/null | grep '^{' > gpurun_out/scale_hilbert32768_n$n.json
+  timeout 300 $TR --nproc-per-node $n --master-port $((29600 + n)) bench.py --gpus $n --steps 5 --warmup 3 2>gpurun_out/scale_err_n$n.txt | grep '^{' > gpurun_out/scale_hilbert32768_n$n.json
   cut -c1-330 gpurun_out/scale_hilbert32768_n$n.json
 done
 timeout 300 python bench.py --workload hilbert-32768 --steps 5 --no-cpu-baseline --no-sweep-table 2>/dev/null | grep '^{' > gpurun_out/scale_hilbert32768_n1.json
