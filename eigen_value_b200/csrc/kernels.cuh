@@ -504,15 +504,54 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     for (uint32_t c0 = 0; c0 < N; c0 += p.chunk_cols) {
       const uint32_t clen = min(p.chunk_cols, N - c0);
       __syncthreads();
-      const uint32_t rot = cb % clen; // de-phase the CTAs on the L2 lines of E and S
-      for (uint32_t cc = tid; cc < clen; cc += THREADS) {
-        const uint32_t c = cc + rot < clen ? cc + rot : cc + rot - clen;
-        float v = 1.f;
-        if (!first) {
-          const float sp = ld_cg(Sprev + c0 + c);
-          v = (FORM == kFormReadOnly) ? ld_cg(Eprev + c0 + c) * (sp / m_prev) : sp;
+      // every CTA rebuilds the same chunk of the scale vector at the same time: each starts at
+      // its own offset (de-phased on the L2 lines of E and S); 128-bit loads, four batches in
+      // flight before anything depends on them
+      if (VEC == 4) {
+        const uint32_t cv = clen >> 2;
+        const uint32_t rotv = (cb >> 2) % cv;
+        const float4* S4 = reinterpret_cast<const float4*>(Sprev + c0);
+        const float4* E4 = reinterpret_cast<const float4*>(Eprev + c0);
+        float4* sc4 = reinterpret_cast<float4*>(scale_s);
+        for (uint32_t v0 = 0; v0 < cv; v0 += 4u * THREADS) {
+          float4 sp[4], ep[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t idx = v0 + (uint32_t)j * THREADS + tid;
+            const uint32_t vi = idx + rotv < cv ? idx + rotv : idx + rotv - cv;
+            const bool active = idx < cv && !first;
+            sp[j] = active ? ld_cg(S4 + vi) : make_float4(1.f, 1.f, 1.f, 1.f);
+            ep[j] = (active && FORM == kFormReadOnly) ? ld_cg(E4 + vi) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t idx = v0 + (uint32_t)j * THREADS + tid;
+            if (idx < cv) {
+              const uint32_t vi = idx + rotv < cv ? idx + rotv : idx + rotv - cv;
+              float4 v = sp[j];
+              if (first) {
+                v = make_float4(1.f, 1.f, 1.f, 1.f);
+              } else if (FORM == kFormReadOnly) {
+                v.x = ep[j].x * (sp[j].x / m_prev);
+                v.y = ep[j].y * (sp[j].y / m_prev);
+                v.z = ep[j].z * (sp[j].z / m_prev);
+                v.w = ep[j].w * (sp[j].w / m_prev);
+              }
+              sc4[vi] = v;
+            }
+          }
         }
-        scale_s[c] = v;
+      } else {
+        const uint32_t rot = cb % clen;
+        for (uint32_t cc = tid; cc < clen; cc += THREADS) {
+          const uint32_t c = cc + rot < clen ? cc + rot : cc + rot - clen;
+          float v = 1.f;
+          if (!first) {
+            const float sp = ld_cg(Sprev + c0 + c);
+            v = (FORM == kFormReadOnly) ? ld_cg(Eprev + c0 + c) * (sp / m_prev) : sp;
+          }
+          scale_s[c] = v;
+        }
       }
       __syncthreads();
       for (uint32_t i = warp; i < nrows; i += kWarps) {
@@ -565,27 +604,62 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     // they do not queue on the same L2 lines; max / AND are order-independent.  The circular
     // neighbour comes from the next lane by shuffle, as in the reference (:413-417); four
     // batches of loads are in flight before anything depends on them.
-    for (uint32_t b0 = 0; b0 < N; b0 += 4u * THREADS) {
-      float sf[4], nx[4];
+    if (VEC == 4) {
+      const uint32_t nv = N >> 2;
+      const uint32_t rotv = cb >> 2;
+      const float4* S4 = reinterpret_cast<const float4*>(Scur);
+      for (uint32_t v0 = 0; v0 < nv; v0 += 4u * THREADS) {
+        float4 t4[4];
+        float nx[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
-        const bool active = c0 < N;
-        const uint32_t c = c0 + cb < N ? c0 + cb : c0 + cb - N;
-        sf[j] = active ? ld_cg(Scur + c) : 0.f;
-        const bool edge = active && (lane == 31 || c0 + 1u >= N);
-        nx[j] = edge ? ld_cg(Scur + (c + 1u == N ? 0u : c + 1u)) : 0.f;
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + (uint32_t)j * THREADS + tid;
+          const bool active = idx < nv;
+          const uint32_t vi = idx + rotv < nv ? idx + rotv : idx + rotv - nv;
+          t4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool edge = active && (lane == 31 || idx + 1u >= nv);
+          nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t idx = v0 + (uint32_t)j * THREADS + tid;
+          if (v0 + (uint32_t)j * THREADS < nv) { // warp-uniform
+            float nxt = __shfl_down_sync(0xffffffffu, t4[j].x, 1);
+            if (lane == 31 || idx + 1u >= nv)
+              nxt = nx[j];
+            if (idx < nv) {
+              const float4 v = t4[j];
+              mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+              // strict <, wrap pair included (:413-421)
+              ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
+                    (fabsf(v.w - nxt) < p.eps);
+            }
+          }
+        }
       }
+    } else {
+      for (uint32_t b0 = 0; b0 < N; b0 += 4u * THREADS) {
+        float sf[4], nx[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
-        if (b0 + (uint32_t)j * THREADS < N) { // warp-uniform
-          float next = __shfl_down_sync(0xffffffffu, sf[j], 1);
-          if (lane == 31 || c0 + 1u >= N)
-            next = nx[j];
-          if (c0 < N) {
-            mx = fmaxf(mx, sf[j]);
-            ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+        for (int j = 0; j < 4; j++) {
+          const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+          const bool active = c0 < N;
+          const uint32_t c = c0 + cb < N ? c0 + cb : c0 + cb - N;
+          sf[j] = active ? ld_cg(Scur + c) : 0.f;
+          const bool edge = active && (lane == 31 || c0 + 1u >= N);
+          nx[j] = edge ? ld_cg(Scur + (c + 1u == N ? 0u : c + 1u)) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t c0 = b0 + (uint32_t)j * THREADS + tid;
+          if (b0 + (uint32_t)j * THREADS < N) { // warp-uniform
+            float next = __shfl_down_sync(0xffffffffu, sf[j], 1);
+            if (lane == 31 || c0 + 1u >= N)
+              next = nx[j];
+            if (c0 < N) {
+              mx = fmaxf(mx, sf[j]);
+              ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+            }
           }
         }
       }
