@@ -74,6 +74,7 @@ struct RoundParams
   uint32_t* out_iter;    // [0] iter_count, [1] passes
   unsigned long long* round_ts; // max_iter + 1 globaltimer stamps
   unsigned long long* phase_ts; // 3 per round, CTA 0: pass done, barrier passed, tail done
+  uint32_t ts_rounds;           // rounds that have stamp storage (later rounds are not stamped)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -85,6 +86,23 @@ globaltimer_ns()
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// per-round instrumentation, written by one thread of CTA 0
+__device__ __forceinline__ void
+stamp_phase(const RoundParams& p, uint32_t k, uint32_t which)
+{
+  if (k < p.ts_rounds)
+    p.phase_ts[3u * k + which] = globaltimer_ns();
+}
+__device__ __forceinline__ void
+stamp_round_end(const RoundParams& p, uint32_t k)
+{
+  if (k < p.ts_rounds) {
+    const unsigned long long t = globaltimer_ns();
+    p.round_ts[k + 1u] = t;
+    p.phase_ts[3u * k + 2u] = t;
+  }
 }
 
 __device__ __forceinline__ unsigned int
@@ -575,7 +593,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
       }
     }
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k] = globaltimer_ns();
+      stamp_phase(p, k, 0u);
     __syncthreads();
 
     // ---- publish this CTA's row sums (to every rank when sharded) ----
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     if (!round_barrier(p, k, &s_abort))
       return;
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k + 1u] = globaltimer_ns();
+      stamp_phase(p, k, 1u);
 
     // ---- every CTA: max, circular stop test over the full vector ----   reference :41, :44
     float mx = 0.f; // reference zero-fills the max cell (:169)
@@ -692,7 +710,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     const bool converged = bc_ok != 0;
 
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
+      stamp_round_end(p, k);
 
     if (converged || k + 1u == p.max_iter) {
       // the eigenvector update of this round still happens before the break (:42-50)

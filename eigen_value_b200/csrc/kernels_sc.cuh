@@ -249,12 +249,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k] = globaltimer_ns();
+      stamp_phase(p, k, 0u);
 
     if (!round_barrier(p, k, &s_abort))
       break;
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k + 1u] = globaltimer_ns();
+      stamp_phase(p, k, 1u);
 
     // ---- every CTA: max / circular stop over the full s, then e update ----        :41-44
     // 128-bit L2 loads, all loads of a batch issued before anything depends on them.  The
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       }
     }
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
+      stamp_round_end(p, k);
     __syncthreads();
 
     if (converged || k + 1u == p.max_iter) {

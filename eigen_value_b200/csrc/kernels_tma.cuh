@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k] = globaltimer_ns();
+      stamp_phase(p, k, 0u);
     __syncthreads();
 
     for (uint32_t r = tid; r < nrows; r += THREADS) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
       return;
     }
     if (blockIdx.x == 0 && tid == 0)
-      p.phase_ts[3u * k + 1u] = globaltimer_ns();
+      stamp_phase(p, k, 1u);
 
     float mx = 0.f;
     int ok = 1;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     const bool converged = bc_ok != 0;
 
     if (blockIdx.x == 0 && tid == 0)
-      p.round_ts[k + 1] = p.phase_ts[3u * k + 2u] = globaltimer_ns();
+      stamp_round_end(p, k);
 
     if (converged || k + 1u == p.max_iter) {
       for (uint32_t c = cb + tid; c < ce; c += THREADS)

@@ -99,6 +99,10 @@ Context::activate() const
   ST_CUDA(cudaSetDevice(device_));
 }
 
+// rounds beyond this are still executed but not time-stamped (bounds the stamp buffers when a
+// caller raises max_iter far above the reference's 1000)
+constexpr uint32_t kMaxStampedRounds = 1u << 16;
+
 void
 Context::reserve_vectors(uint32_t dim, uint32_t max_iter)
 {
@@ -110,13 +114,14 @@ Context::reserve_vectors(uint32_t dim, uint32_t max_iter)
     ST_CUDA(cudaMalloc(&d_vec_, sizeof(float) * 5 * (size_t)need));
     vec_cap_ = need;
   }
-  if (max_iter + 2 > ts_cap_) {
+  const uint32_t stamped = std::min<uint32_t>(max_iter, kMaxStampedRounds);
+  if (stamped + 2 > ts_cap_) {
     cudaFree(d_ts_);
     d_ts_ = nullptr;
     ts_cap_ = 0;
-    // round stamps (max_iter + 2) followed by three phase stamps per round
-    ST_CUDA(cudaMalloc(&d_ts_, sizeof(unsigned long long) * 4 * (size_t)(max_iter + 2)));
-    ts_cap_ = max_iter + 2;
+    // round stamps (stamped + 2) followed by three phase stamps per round
+    ST_CUDA(cudaMalloc(&d_ts_, sizeof(unsigned long long) * 4 * (size_t)(stamped + 2)));
+    ts_cap_ = stamped + 2;
   }
 }
 
@@ -362,6 +367,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   p.out_iter = reinterpret_cast<uint32_t*>(d_scalars_ + 1);
   p.round_ts = d_ts_;
   p.phase_ts = d_ts_ + ts_cap_;
+  p.ts_rounds = std::min<uint32_t>(opt.max_iter, kMaxStampedRounds);
 
   // ---- launch plan ------------------------------------------------------------------------
   // one persistent CTA per SM (fewer when there are fewer rows than warps); CTA size = the warp
@@ -491,11 +497,12 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     return ST_ERR_TIMEOUT;
   }
   const uint32_t passes = words[2];
-  last_ts_.assign((size_t)passes + 1, 0);
-  ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)passes + 1),
+  const uint32_t stamped = std::min<uint32_t>(passes, p.ts_rounds);
+  last_ts_.assign((size_t)stamped + 1, 0);
+  ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)stamped + 1),
                      cudaMemcpyDeviceToHost));
-  last_phase_ts_.assign(3 * (size_t)passes, 0);
-  ST_CUDA(cudaMemcpy(last_phase_ts_.data(), d_ts_ + ts_cap_, sizeof(uint64_t) * 3 * (size_t)passes,
+  last_phase_ts_.assign(3 * (size_t)stamped, 0);
+  ST_CUDA(cudaMemcpy(last_phase_ts_.data(), d_ts_ + ts_cap_, sizeof(uint64_t) * 3 * (size_t)stamped,
                      cudaMemcpyDeviceToHost));
 
   if (res) {
@@ -511,7 +518,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     const uint64_t per_pass = (uint64_t)rows * dim * sizeof(float);
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;
     std::vector<float> dt;
-    for (uint32_t k = 0; k < passes; k++)
+    for (uint32_t k = 0; k < stamped; k++)
       dt.push_back((float)(last_ts_[k + 1] - last_ts_[k]) * 1e-3f);
     if (!dt.empty()) {
       std::sort(dt.begin(), dt.end());

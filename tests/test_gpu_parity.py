@@ -197,6 +197,31 @@ def test_kernel_variants_are_bitwise_identical(solver, dim):
         assert info.kernel_id == (kid if kid else 13)
 
 
+def test_zero_copy_torch_tensor_solve(solver):
+    # device-resident input without PCIe staging
+    import torch
+    H = torch.from_numpy(oracle.hilbert(1024)).cuda()
+    info, vec = solver.solve_tensor(H)
+    assert info.iter_count == 13 and vec.is_cuda and vec.shape == (1024,)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(oracle.hilbert(1024))
+    assert_parity((info.eigen_val, vec.cpu().numpy(), info.iter_count), (o_val, o_vec, o_it))
+    with pytest.raises(ValueError):
+        solver.solve_tensor(H[:, :512])                 # not square
+    with pytest.raises(ValueError):
+        solver.solve_tensor(H.double())                 # not float32
+    with pytest.raises(ValueError):
+        solver.solve_tensor(H.t())                      # not C-contiguous
+
+
+def test_many_rounds_beyond_the_stamp_buffer(solver):
+    # max_iter far above the reference's 1000: rounds past the stamp buffer still run
+    d = solver.upload(np.array([[2.0, 1.0], [1.0, 3.0]], dtype=np.float32))
+    info, vec = solver.solve_device(d, 2, eps=0.0, max_iter=70000)    # eps 0 never converges
+    assert info.iter_count == 70000 and info.passes == 70000
+    lam = (5 + 5 ** 0.5) / 2
+    assert abs(float(info.eigen_val) - lam) < 1e-5 * lam
+
+
 def test_max_iter_cap_reports_cap(solver):
     # never-converging case: iter_count == max_iter (reference similarity_transform.cpp:39,54)
     d = solver.hilbert(512)
