@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
 #include "kernels_sc.cuh"
+#include "kernels_cluster.cuh"
 
 namespace st {
 
@@ -298,6 +299,50 @@ launch_sc(int id, const RoundParams& p, int grid, int threads, size_t smem, cuda
   }
 }
 
+// ---- on-chip variant (N <= 512): matrix resident in the shared memory of one cluster -----------
+constexpr int kClusterKernelId = 20;
+constexpr int kClusterThreads = 512;
+
+// Cluster size (1, 2, 4, 8 CTAs): the largest that still leaves every CTA >= 16 rows (one per
+// warp) -- the loop is latency-bound, so more SMs means shorter per-warp row chains -- and never
+// smaller than what it takes to hold rows + e + both s buffers in each CTA's shared memory.
+static int
+cluster_ctas_for(uint32_t dim, size_t* smem_bytes)
+{
+  int best = 0;
+  for (int c = 1; c <= kClusterMaxCtas; c *= 2) {
+    const size_t rows_cap = (dim + (uint32_t)c - 1u) / (uint32_t)c;
+    const size_t need = sizeof(float) * (rows_cap * dim + 3 * (size_t)dim);
+    const bool fits = need <= kClusterSmemBudget;
+    const bool useful = c == 1 || dim / (uint32_t)c >= 16u;
+    if (fits && (useful || !best)) {
+      best = c;
+      *smem_bytes = need;
+    }
+  }
+  return best;
+}
+
+static void
+launch_cluster(const RoundParams& p, int ctas, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_cluster_kernel<kClusterThreads>;
+  ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ST_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+}
+
 static bool
 aligned16(const void* p)
 {
@@ -367,7 +412,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   p.out_iter = reinterpret_cast<uint32_t*>(d_scalars_ + 1);
   p.round_ts = d_ts_;
   p.phase_ts = d_ts_ + ts_cap_;
-  p.ts_rounds = std::min<uint32_t>(opt.max_iter, kMaxStampedRounds);
+  // st_options.sweep bit 3 switches the per-round instrumentation off (no %globaltimer reads)
+  p.ts_rounds = (opt.sweep & 8) ? 0u : std::min<uint32_t>(opt.max_iter, kMaxStampedRounds);
 
   // ---- launch plan ------------------------------------------------------------------------
   // one persistent CTA per SM (fewer when there are fewer rows than warps); CTA size = the warp
@@ -395,7 +441,18 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const TmaConfig* tma = nullptr;
   const ScConfig* sc = nullptr;
   const bool readonly4 = vec4 && form == kFormReadOnly;
-  if (opt.kernel >= 10 || (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols)) {
+  int cluster_ctas = 0;
+  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && dim <= (uint32_t)kClusterCols)) {
+    if (!readonly4 || shard || dim > (uint32_t)kClusterCols)
+      throw std::invalid_argument("solve: on-chip kernel needs one GPU, the read-only form, dim % 4 == 0, dim <= 512");
+    cluster_ctas = cluster_ctas_for(dim, &smem);
+    if (!cluster_ctas)
+      throw std::invalid_argument("solve: matrix does not fit the cluster's shared memory");
+    grid = cluster_ctas;
+    threads = kClusterThreads;
+  }
+  if (!cluster_ctas && ((opt.kernel >= 10 && opt.kernel < kClusterKernelId) ||
+                        (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols))) {
     if (!readonly4 || dim > (uint32_t)kResidentCols)
       throw std::invalid_argument("solve: resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
     for (const ScConfig& c : kScConfigs) {
@@ -454,7 +511,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     if (!tma)
       throw std::invalid_argument("solve: requested TMA kernel configuration does not fit");
   }
-  if (!sc && !tma) {
+  if (!sc && !tma && !cluster_ctas) {
     shape(pinned > 512 ? 1024 : 512, true, &grid, &threads, &rows_cap);
     smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
   }
@@ -462,7 +519,9 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
-  if (sc) {
+  if (cluster_ctas) {
+    launch_cluster(p, cluster_ctas, smem, stream_);
+  } else if (sc) {
     launch_sc(sc->id, p, grid, threads, smem, stream_);
   } else if (tma) {
     launch_tma(tma->id, p, grid, smem, stream_);
@@ -513,7 +572,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->launches = 1;
     res->loop_ms = loop_ms;
     res->grid = (uint32_t)grid;
-    res->kernel_id = sc ? (uint32_t)sc->id : tma ? (uint32_t)tma->id : 1u;
+    res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : tma ? (uint32_t)tma->id : 1u;
     res->threads = (uint32_t)threads;
     const uint64_t per_pass = (uint64_t)rows * dim * sizeof(float);
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;

@@ -77,11 +77,12 @@ class SolveInfo:
     kernel_id: int = 0
     threads: int = 0
 
-    KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_tma_kernel", 10: "st::round_loop_sc_kernel"}
+    KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_tma_kernel", 10: "st::round_loop_sc_kernel",
+                    20: "st::round_loop_cluster_kernel"}
 
     @property
     def kernel_name(self) -> str:
-        key = 10 if self.kernel_id >= 10 else 2 if self.kernel_id >= 2 else 1
+        key = 20 if self.kernel_id >= 20 else 10 if self.kernel_id >= 10 else 2 if self.kernel_id >= 2 else 1
         return self.KERNEL_NAMES[key]
 
     @classmethod

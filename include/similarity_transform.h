@@ -88,7 +88,9 @@ typedef struct st_options
                         static / dynamic work-unit scheduling in the resident-e kernel    */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
-  int32_t kernel;    /* 0 = default round kernel; others are tuning variants        */
+  int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, one GPU), resident-e
+                        kernel (N <= 32768), general chunked loop otherwise; 1 = general loop,
+                        2-9 = TMA-ring variants, 10-19 = resident-e variants, 20 = on-chip   */
   int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
@@ -107,7 +109,7 @@ typedef struct st_result
   uint64_t bytes_per_round; /* algorithmic bytes one round moves on this GPU        */
   int32_t status;
   uint32_t grid;          /* CTAs the round kernel ran with                          */
-  uint32_t kernel_id;     /* 1 general LDG loop, 2-9 TMA ring, 10-19 single-chunk    */
+  uint32_t kernel_id;     /* 1 general loop, 2-9 TMA ring, 10-19 resident-e, 20 on-chip */
   uint32_t threads;       /* CTA size the round kernel ran with                      */
 } st_result;
 

@@ -186,15 +186,32 @@ def test_launch_shape_and_sweep_do_not_change_results(solver, threads, sweep):
 
 @pytest.mark.parametrize("dim", [256, 4096, 8192, 16384])
 def test_kernel_variants_are_bitwise_identical(solver, dim):
-    """general chunked loop (1), TMA ring (2, 5), resident-e kernel (13, 10, 11): one evaluation
-    order, so every variant returns the same bits."""
+    """general chunked loop (1), TMA ring (2, 5), resident-e kernel (13, 10, 11), on-chip cluster
+    kernel (20, N <= 512): one evaluation order, so every variant returns the same bits."""
     d = solver.uniform(dim, 0x5EED0000 + dim)
     base, base_vec = solver.solve_device(d, dim, kernel=1, max_iter=6)
-    for kid in (0, 2, 5, 13, 10, 11):
+    kids = (0, 2, 5, 13, 10, 11) + ((20,) if dim <= 512 else ())
+    for kid in kids:
         info, vec = solver.solve_device(d, dim, kernel=kid, max_iter=6)
         assert info.iter_count == base.iter_count, kid
         assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec), kid
-        assert info.kernel_id == (kid if kid else 13)
+        assert info.kernel_id == (kid if kid else (20 if dim <= 512 else 13))
+
+
+@pytest.mark.parametrize("dim", [4, 8, 100, 128, 256, 384, 512])
+def test_on_chip_cluster_kernel_matches_general_loop(solver, dim):
+    """N <= 512: matrix resident in the shared memory of one cluster (1/2/4/8 CTAs), row sums
+    exchanged through distributed shared memory.  Same bits as the general loop, same rounds as
+    the oracle."""
+    mat = oracle.hilbert(dim)
+    d = solver.upload(mat)
+    base, base_vec = solver.solve_device(d, dim, kernel=1)
+    info, vec = solver.solve_device(d, dim, kernel=20)
+    assert info.kernel_id == 20 and info.grid in (1, 2, 4, 8)
+    assert info.iter_count == base.iter_count and info.eigen_val == base.eigen_val
+    assert np.array_equal(vec, base_vec)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(mat)
+    assert_parity((info.eigen_val, vec, info.iter_count), (o_val, o_vec, o_it))
 
 
 def test_zero_copy_torch_tensor_solve(solver):
