@@ -59,6 +59,7 @@ public:
 
 private:
   friend struct Shard;
+  void preload_kernels();
   void reserve_vectors(uint32_t dim, uint32_t max_iter);
   void reserve_matrix(size_t elems);
   void reserve_work(size_t elems);

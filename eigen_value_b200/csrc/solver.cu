@@ -51,6 +51,24 @@ struct CudaError : std::runtime_error
   } while (0)
 
 // ---- Context --------------------------------------------------------------------------------
+// With lazy module loading the first launch of a kernel pays for loading it (milliseconds); the
+// reference shows the same first-use cost in its published N=128 row (README.md:70,146).  Touch
+// the kernels the automatic choice uses when the handle is created, so that the first
+// max_eigen_value() already returns steady-state loop times.
+void
+Context::preload_kernels()
+{
+  cudaFuncAttributes attr{};
+  const void* kernels[] = {
+    (const void*)round_loop_cluster_kernel<512>,
+    (const void*)round_loop_sc_kernel<512, 1, kUnroll>,
+    (const void*)round_loop_kernel<4, kFormReadOnly, 512>,
+    (const void*)round_loop_kernel<1, kFormReadOnly, 512>,
+  };
+  for (const void* k : kernels)
+    ST_CUDA(cudaFuncGetAttributes(&attr, k));
+}
+
 Context::Context(int device)
   : device_(device)
 {
@@ -76,6 +94,7 @@ Context::Context(int device)
   ST_CUDA(cudaMalloc(&d_bar_, sizeof(BarrierState)));
   ST_CUDA(cudaMalloc(&d_scalars_, 64));
   ST_CUDA(cudaHostAlloc(&h_pinned_, 64, cudaHostAllocDefault));
+  preload_kernels();
 }
 
 Context::~Context()
