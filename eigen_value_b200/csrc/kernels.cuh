@@ -9,6 +9,13 @@
 // next eigenvector -- the work of the reference's five kernels + three fills + blocking
 // host read per round (:40-52).
 //
+// This file holds what every round kernel shares (parameters, the round barrier with its
+// cross-GPU exchange, the canonical row reduction) and the GENERAL loop: any N, both forms,
+// column-chunked scale vector.  The specialised loops build on it:
+//   kernels_cluster.cuh  N <= 512    matrix resident in the shared memory of one cluster
+//   kernels_sc.cuh       N <= 32768  eigenvector resident in shared memory (the default)
+//   kernels_tma.cuh      tuning variant streaming the matrix through per-warp TMA rings
+//
 // The small standalone kernels at the bottom are the per-kernel entry points mirroring the
 // reference's L1 functions (similarity_transform.cpp:77-460) and the input generators
 // (utils.cpp:136-154, :124-134).
