@@ -145,6 +145,16 @@ abs(float x)
 {
   return std::fabs(x);
 }
+inline double
+abs(double x) // tests/test.cpp:99-102 calls abs(float - double) under `using namespace sycl`
+{
+  return std::fabs(x);
+}
+inline int
+abs(int x)
+{
+  return x < 0 ? -x : x;
+}
 
 // ---------------------------------------------------------------------------------------------
 // device / context / queue

@@ -61,6 +61,26 @@ needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not buil
 
 
 @needs_ref
+def test_reference_own_test_program_passes_on_the_shim():
+    """oracle/_ref/reference_tests is the reference's tests/test.cpp, unmodified, with its asserts
+    live (no -DNDEBUG): if the shim mis-implemented a SYCL collective the reference's own checks
+    (identity row sums :29, max :40, 3x3 golden :99-102) would abort."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ref.SO), "reference_tests")
+    if not os.path.exists(exe):
+        pytest.skip("reference_tests not built")
+    proc = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout
+    out = proc.stdout
+    assert "sum across row works !" in out and "max from vector works !" in out
+    assert "maximum deviation in computing eigen vector 0" in out
+    assert "stopping criteria test result [success]: 1" in out
+    assert "stopping criteria test result [fail]: 0" in out          # fails through the wrap pair only
+    assert "[ 4 iterations ]" in out
+
+
+@needs_ref
 @pytest.mark.parametrize("dim,wg", [(64, 32), (96, 32), (256, 128), (250, 125), (48, 48)])
 def test_live_per_kernel_parity(dim, wg):
     L = ref.lib()
