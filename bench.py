@@ -419,7 +419,9 @@ def main():
             "phase_us": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phase.items()},
             "wall_ms_per_step": round(wall_ms / args.steps, 5),
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
-                         "frac": round(value / agg_peak, 4), "traffic": recorded_traffic(workload),
+                         "frac": round(value / agg_peak, 4),
+                         # the ncu captures are single-GPU launches; no capture exists for a shard
+                         "traffic": recorded_traffic(workload) if world == 1 else None,
                          "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                          "kernel": f"{last.kernel_name} id {last.kernel_id}, {last.threads} threads x {last.grid} CTAs "
                                    "(one launch = one whole solve)",
