@@ -139,9 +139,25 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
 
   uint32_t pf_issued = 0, pf_consumed = 0; // bulk copies issued / waited for by this warp
 
+  // Matrix resident on chip: when no warp has more than one unit (U <= TW) and a whole unit fits
+  // the warp's prefetch slot, the "prefetch" is issued once, before the first round, and the
+  // unit simply stays in shared memory for the whole solve -- N = 1024 (4 KB rows, 64 CTAs) and
+  // N = 2048 (8 KB rows, 128 CTAs) never touch the matrix in L2 again after round 0.
+  const bool resident = PF_BATCHES > 0 && U <= TW && min(kChunkVec, nv) <= (kPfFloats >> 2);
+  if (resident && gw < U) {
+    if (lane == 0) {
+      const uint32_t rl = gw / nch;
+      const uint32_t ch = gw - rl * nch;
+      const uint32_t bytes = min(kChunkVec, nv - ch * kChunkVec) * 16u;
+      mbar_arrive_expect_tx(my_bar, bytes);
+      bulk_load(my_pf, p.A + (size_t)rl * N + (size_t)ch * kChunkCols, bytes, my_bar);
+    }
+    pf_issued++;
+  }
+
   for (uint32_t k = 0;; ++k) {
     float* Scur = p.S[k & 1];
-    const bool backward = p.sweep && (k & 1);
+    const bool backward = !resident && p.sweep && (k & 1); // resident units never change owner
 
     // ---- the pass over the matrix ----                                   reference :40 (+ :52)
     bool tma_ok = true;
@@ -195,6 +211,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
             tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
             pf_consumed++;
             npre = min(kPfFloats >> 2, seg_nv);
+          } else if (resident && first_unit) {
+            npre = seg_nv; // landed before round 0 and never evicted
           }
           const float t = chunk_dot_prefetched<LD>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec,
                                                    seg_nv, lane, reinterpret_cast<const float4*>(my_pf), npre);
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         finish_row(pend_row, pend_old);
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
-    if (PF_BATCHES > 0 && gw < U && k + 1u < p.max_iter) {
+    if (PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {
       __syncwarp();
       if (lane == 0) {
         const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - gw) : gw;

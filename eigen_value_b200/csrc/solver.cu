@@ -474,10 +474,18 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
                         (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols))) {
     if (!readonly4 || dim > (uint32_t)kResidentCols)
       throw std::invalid_argument("solve: resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
+    // Automatic slot size: one 4 KB batch per warp, unless a whole row fits a 2- or 3-batch slot
+    // and no warp would own more than one row -- then the rows stay in shared memory for the
+    // whole solve (matrix resident on chip, N <= ~2368 on 148 SMs).
+    int want_pf = 1;
+    if (opt.kernel == 0 && dim > 1024u && dim <= 3072u && (uint64_t)rows <= (uint64_t)sm_count_ * 16u)
+      want_pf = (int)((dim + 1023u) / 1024u);
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
       if (opt.kernel == 0 && pinned > c.max_threads)
+        continue;
+      if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
       uint32_t cap, moff = 0;

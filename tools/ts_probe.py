@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eigen_value_b200 import Solver  # noqa: E402
 
 s = Solver(0)
-for n in (128, 256, 512, 1024):
+for n in (512, 1024, 1536, 2048, 2304, 4096):
     d = s.hilbert(n)
     for kernel in (0, 13, 1):
         best = None
