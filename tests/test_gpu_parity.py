@@ -98,6 +98,26 @@ def test_bad_arguments_do_not_crash(ev):
     assert lib.max_eigen_value(ev.sycl_q, None, None, None, 4, None) < 0
     assert lib.max_eigen_value(None, A3.ctypes.data, A3.ctypes.data, A3.ctypes.data, 3, A3.ctypes.data) < 0
     assert lib.st_last_error()
+    # empty input: dim == 0 is rejected, nothing is written
+    val = np.full(1, -1.0, np.float32)
+    slot = np.full(1, 77, np.uint32)
+    assert lib.max_eigen_value(ev.sycl_q, A3.ctypes.data, val.ctypes.data, A3.ctypes.data, 0, slot.ctypes.data) < 0
+    assert val[0] == -1.0 and slot[0] == 77
+
+
+@pytest.mark.parametrize("dim", [3, 64, 1000])
+def test_nan_input_never_converges_and_hits_the_cap(ev, dim):
+    """A NaN anywhere makes every comparison of the stop test false, so the reference runs its
+    full MAX_ITR = 1000 rounds (similarity_transform.cpp:39,54); so must we,
+    and the handle has to stay usable afterwards."""
+    mat = (oracle.uniform(dim, 5) + np.float32(0.5)).astype(np.float32)
+    mat[dim // 2, dim // 3] = np.nan
+    val, vec, ms, it = ev.similarity_transform(mat)
+    assert it == 1000
+    o_val, o_vec, _, o_it = oracle.similarity_transform(mat)
+    assert o_it == 1000
+    val, vec, ms, it = ev.similarity_transform(A3)          # still fine after the poisoned solve
+    assert it == 4 and abs(val - 7.53114) < 1e-3
 
 
 # ---- per-kernel entry points vs the reference's unit fixtures (tests/test.cpp:22-73) -----------
