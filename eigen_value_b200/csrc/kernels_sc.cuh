@@ -8,16 +8,20 @@
 //     no global E buffers, no rebuild of the chunk per round.
 //   * after the round barrier each thread needs ONE L2 round trip (N <= ~10240: its <= 5
 //     float4 of s stay in registers between the max / stop reduction and the update of e) or
-//     two (larger N: s is re-read), with every load of a batch in flight at once.  The general kernel needs four dependent L2 trips per round.
-//   * the CTA size is a RUN-TIME choice (blockDim.x, 12..16 warps): the host picks the warp
-//     count that divides the CTA's row count with the least idle warps, e.g. 14 warps for 55 or
-//     28 rows per CTA.
+//     two (larger N: s is re-read), with every load of a batch in flight at once.  The general
+//     kernel needs four dependent L2 trips per round.
+//   * the work unit is one 8192-column chunk of one row (32 KB), handed out dynamically through
+//     one atomic counter once the matrix no longer lives in L2 (N >= 8192), round-robin below;
+//     rows of several units are finished, in order, by the warp whose arrival completes them.
 //   * the matrix never changes, so before a warp enters the barrier its lane 0 issues ONE
 //     TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of the first
-//     PF_BATCHES*4 KB of the row it will process first in the NEXT round into a private
+//     PF_BATCHES*4 KB of the unit it will process first in the NEXT round into a private
 //     shared-memory slot.  The L2->SM pipe keeps moving matrix bytes while the CTA sits in the
 //     barrier and the vector tail; the first batches of the next round are then consumed
 //     from shared memory.  A prefetch issued for a round that never runs is drained at exit.
+//     When a whole row fits the slot and no warp owns more than one row, the row is fetched
+//     once and stays in shared memory for the whole solve.
+//   * the CTA size is blockDim.x (a run-time value; every warp is used).
 //
 // Row sums are bit-identical to round_loop_kernel: same lane / accumulator / fold order.
 // Read-only form, N % 4 == 0, N <= kResidentCols only.
