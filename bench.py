@@ -206,11 +206,37 @@ def reference_arm(args, kind, dim, workload):
                          "sample": f"{workload}: {text}; OpenMP oracle (oracle/oracle.c), {cores} threads"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference SYCL build unavailable offline (no dpcpp); CPU port of its loop timed instead",
-        "wall_s": round(time.time() - t0, 2),
+        "note": "reference SYCL toolchain (dpcpp) unavailable offline; the OpenMP port of its loop is timed. "
+                "oracle/_ref (the unmodified reference sources on a single-threaded CPU SYCL shim) is a "
+                "correctness reference, not a performance baseline: see ref_shim_sample",
+        "ref_shim_sample": ref_shim_sample(),
     }
+    line["wall_s"] = round(time.time() - t0, 2)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def ref_shim_sample():
+    """One small solve through oracle/_ref (the reference's own C++ on the fiber-emulated SYCL
+    shim), so the line shows what that build does and why it is not the timed baseline."""
+    try:
+        import numpy as np
+        import oracle
+        from oracle import ref
+        if not ref.available():
+            return None
+        dim = 256
+        mat = oracle.hilbert(dim)
+        t0 = time.perf_counter()
+        val, vec, _, it = ref.max_eigen_value(mat)
+        ms = (time.perf_counter() - t0) * 1e3
+        o_val, o_vec, _, o_it = oracle.similarity_transform(
+            mat, form=oracle.FORM_INPLACE, sum_mode=oracle.sum_workgroup(ref.wrapper_wg_size(dim)))
+        return {"workload": f"hilbert-{dim}", "rounds": it, "ms": round(ms, 1), "threads": 1,
+                "value": round((it + 1) * 4.0 * dim * dim / (ms * 1e-3) / 1e9, 4), "unit": "GB/s",
+                "bit_identical_to_oracle": bool(o_it == it and o_val == val and np.array_equal(o_vec, vec))}
+    except Exception as exc:  # never let the side sample break the arm
+        return {"error": str(exc)[:200]}
 
 
 # ---------------------------------------------------------------------------------------------
