@@ -23,6 +23,7 @@ MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
 
 FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
+SUM_CUDA = 4   # the CUDA kernels' evaluation order: with FORM_READONLY bit-identical to the GPU
 
 
 def sum_workgroup(wg_size: int) -> int:

@@ -18,6 +18,10 @@
  *   eigenvector and iter_count BIT FOR BIT on every case, and the committed fixture
  *   tests/golden/reference_sycl.json carries those outputs to boxes without the reference tree.
  * The reference's real SYCL toolchain (dpcpp) is not available in this image.
+ * (3) ORACLE_SUM_CUDA additionally restates the summation order of the CUDA round kernels, so
+ *   that the GPU can be held to the oracle bit for bit (tests/test_zz_gpu_bitexact.py); that
+ *   order is pinned on the CPU by tests/test_oracle_cuda_order.py (an independent numpy
+ *   restatement, and eigenvalues recorded on B200s: tests/golden/gpu_recorded.json).
  *
  * Every function cites the reference lines it restates (paths relative to the reference
  * repository root).  Arithmetic is strict fp32: build with -ffp-contract=off and without
@@ -49,13 +53,16 @@ enum
   ORACLE_SUM_SUBGROUP32 = 2, /* 32-wide group sums added left to right: the shape of the
                                 reference's reduce_over_group + atomic adds
                                 (similarity_transform.cpp:119-146), one of its legal orders */
-  ORACLE_SUM_WORKGROUP = 3   /* | (wg_size << 8): the reference's literal two-level order for a
+  ORACLE_SUM_WORKGROUP = 3,  /* | (wg_size << 8): the reference's literal two-level order for a
                                 given work-group size -- per work-group of wg_size columns the
                                 32-lane butterfly sums are added into local memory in sub-group
                                 order (:119-132), the work-group totals into the row's global
                                 cell in work-group order (:139-146).  This is the order the
                                 reference executes on oracle/sycl_shim, so the oracle can be
                                 compared with the real sources bit for bit. */
+  ORACLE_SUM_CUDA = 4        /* the evaluation order of the CUDA round kernels (lane / accumulator /
+                                fold / shuffle tree, FMA): with ORACLE_FORM_READONLY the oracle
+                                then matches the GPU bit for bit (row_dot_cuda_order below) */
 };
 
 int
@@ -100,6 +107,55 @@ reduce16(const float* acc)
   return (a4[0] + a4[2]) + (a4[1] + a4[3]);
 }
 
+/* The evaluation order of the CUDA round kernels (eigen_value_b200/csrc: row_dot_readonly,
+ * chunk_dot_prefetched, the cluster kernel), restated so that the GPU can be compared with the
+ * oracle BIT FOR BIT, not only within a tolerance:
+ *   - the row is cut into 8192-column chunks; chunk sums are added left to right;
+ *   - inside a chunk the unit is a float4 when n % 4 == 0 (a single float otherwise); unit j
+ *     belongs to lane j % 32 and accumulator (j / 32) % 8 of that lane; a float4 is folded into
+ *     its accumulator with four sequential FMAs (x, y, z, w);
+ *   - per lane the 8 accumulators are folded pairwise (u += u+4, u += u+2, u += u+1), then the
+ *     32 lanes by an xor-shuffle tree (offsets 16, 8, 4, 2, 1).
+ * scale == NULL behaves like a vector of ones (fmaf(a, 1, acc) == a + acc exactly). */
+#define ORACLE_CUDA_CHUNK 8192
+static float
+row_dot_cuda_order(const float* row, const float* scale, size_t n)
+{
+  const size_t vec = (n % 4 == 0) ? 4 : 1;
+  float total = 0.f;
+  for (size_t c0 = 0; c0 < n; c0 += ORACLE_CUDA_CHUNK) {
+    const size_t clen = n - c0 < ORACLE_CUDA_CHUNK ? n - c0 : ORACLE_CUDA_CHUNK;
+    const size_t nv = clen / vec;
+    float acc[32][8];
+    for (int l = 0; l < 32; l++)
+      for (int u = 0; u < 8; u++)
+        acc[l][u] = 0.f;
+    for (size_t j = 0; j < nv; j++) {
+      const int l = (int)(j % 32), u = (int)((j / 32) % 8);
+      for (size_t k = 0; k < vec; k++) {
+        const size_t c = c0 + j * vec + k;
+        acc[l][u] = fmaf(row[c], scale ? scale[c] : 1.f, acc[l][u]);
+      }
+    }
+    float lane[32];
+    for (int l = 0; l < 32; l++) {
+      for (int s = 4; s >= 1; s >>= 1)
+        for (int u = 0; u < s; u++)
+          acc[l][u] += acc[l][u + s];
+      lane[l] = acc[l][0];
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+      float next[32];
+      for (int l = 0; l < 32; l++)
+        next[l] = lane[l] + lane[l ^ o];
+      for (int l = 0; l < 32; l++)
+        lane[l] = next[l];
+    }
+    total = c0 == 0 ? lane[0] : total + lane[0];
+  }
+  return total;
+}
+
 /* sum_c row[c] * (scale ? scale[c] : 1)   -- scale == NULL is the plain row sum */
 static float
 row_dot(const float* row, const float* scale, size_t n, int sum_mode)
@@ -114,6 +170,8 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
         acc += row[c];
     return acc;
   }
+  if (sum_mode == ORACLE_SUM_CUDA)
+    return row_dot_cuda_order(row, scale, n);
   if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {
     const size_t wg = (size_t)(sum_mode >> 8);
     float cell = 0.f; /* the zero-filled global cell (:85-93) */

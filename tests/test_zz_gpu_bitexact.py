@@ -1,0 +1,121 @@
+"""GPU parity, strongest form: the CUDA path against the CPU oracle BIT FOR BIT.
+
+tests/test_gpu_parity.py holds the CUDA path to BASELINE.json's tolerances against the oracle in
+the reference's summation orders.  Every CUDA round kernel evaluates a row in one fixed order
+(DESIGN.md section 2); oracle.SUM_CUDA restates that order on the CPU (oracle.c:
+row_dot_cuda_order, pinned in tests/test_oracle_cuda_order.py -- among others against eigenvalues
+recorded on B200s in round 1), so here eigenvalue, raw eigenvector and round count must be
+IDENTICAL, for every kernel the automatic choice can pick, both forms, vector and scalar loads.
+
+(The file name sorts last on purpose: these are the newest assertions of the suite and must not
+shadow the tolerance-parity tests under `pytest -x`.)
+"""
+import numpy as np
+import pytest
+
+import oracle
+from eigen_value_b200 import EigenValue, FORM_INPLACE, FORM_READONLY
+
+pytestmark = pytest.mark.gpu
+
+A3 = np.array([[1, 1, 2], [2, 1, 3], [2, 3, 5]], dtype=np.float32)     # reference tests/test.cpp:84-94
+
+
+def _oracle(mat, form=FORM_READONLY, **kw):
+    o_form = oracle.FORM_READONLY if form == FORM_READONLY else oracle.FORM_INPLACE
+    val, vec, _, it = oracle.similarity_transform(mat, form=o_form, sum_mode=oracle.SUM_CUDA, **kw)
+    return val, vec, it
+
+
+def _assert_same_bits(got, want, what=""):
+    g_val, g_vec, g_it = got
+    w_val, w_vec, w_it = want
+    assert g_it == w_it, (what, g_it, w_it)
+    assert np.float32(g_val).view(np.uint32) == np.float32(w_val).view(np.uint32), (what, float(g_val), float(w_val))
+    assert np.array_equal(g_vec.view(np.uint32), w_vec.view(np.uint32)), what
+
+
+def _matrix(kind, dim):
+    if kind == "hilbert":
+        return oracle.hilbert(dim)
+    return (oracle.uniform(dim, seed=1000 + dim) + np.float32(0.25)).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def ev():
+    return EigenValue()
+
+
+# on-chip cluster kernel (dim % 4 == 0, <= 512), resident-e kernel (dim % 4 == 0, <= 32768), general
+# loop with scalar loads (dim % 4 != 0); 8196 / 12288: rows of two work units
+DIMS = [1, 2, 3, 4, 5, 31, 33, 100, 128, 257, 512, 640, 1000, 1023, 1024, 2048, 4100, 8192, 8196, 12288]
+
+
+@pytest.mark.parametrize("kind", ["hilbert", "uniform"])
+@pytest.mark.parametrize("dim", DIMS)
+def test_drop_in_boundary_is_bit_identical_to_the_oracle(ev, kind, dim):
+    mat = _matrix(kind, dim)
+    val, vec, ms, it = ev.similarity_transform(mat)                     # make_queue + max_eigen_value
+    _assert_same_bits((val, vec, it), _oracle(mat), f"{kind}-{dim}")
+
+
+def test_three_by_three_golden_bit_identical(ev):
+    val, vec, ms, it = ev.similarity_transform(A3)
+    assert it == 4
+    _assert_same_bits((val, vec, it), _oracle(A3), "3x3 golden")
+
+
+@pytest.mark.parametrize("dim", [3, 100, 1000, 2048, 4100])
+def test_in_place_form_is_bit_identical_to_the_oracle(solver, dim):
+    # the literal W <- D^-1 W D rescale (reference similarity_transform.cpp:324-325): same ops, same order
+    mat = _matrix("hilbert", dim) if dim > 3 else A3
+    info, vec = solver.solve_device(solver.upload(mat), dim, form=FORM_INPLACE)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, FORM_INPLACE), f"in-place {dim}")
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 13, 11])
+def test_every_kernel_family_is_bit_identical_to_the_oracle(solver, kernel):
+    # general loop, TMA ring, resident-e with and without the cross-barrier prefetch, at a size where
+    # rows span two work units (two 8192-column chunks)
+    dim = 9216
+    mat = _matrix("uniform", dim)
+    info, vec = solver.solve_device(solver.upload(mat), dim, kernel=kernel, max_iter=8)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=8), f"kernel {kernel}")
+
+
+def test_multi_chunk_16384_bit_identical(solver):
+    dim = 16384
+    info, vec = solver.solve_device(solver.hilbert(dim), dim)
+    assert info.iter_count == 18
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(oracle.hilbert(dim)), "hilbert-16384")
+
+
+def test_general_loop_beyond_the_resident_limit_bit_identical(solver):
+    # N > 32768 takes the general column-chunked loop (5 chunks here); capped at 3 rounds so the
+    # oracle needs ~10 s for the 6.25 GiB matrix
+    dim = 40960
+    if solver.hbm_bytes < 16 * 2**30:
+        pytest.skip("needs 6.25 GiB of device memory")
+    d = solver.uniform(dim, 0x5EED0003)
+    info, vec = solver.solve_device(d, dim, max_iter=3)
+    d.free()
+    assert info.kernel_id == 1
+    mat = oracle.uniform(dim, 0x5EED0003)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=3), "uniform-40960")
+
+
+@pytest.mark.parametrize("dim", [7, 64, 1000, 2048, 8200])
+def test_standalone_row_sum_kernel_bit_identical(solver, dim):
+    # st_sum_across_rows (reference similarity_transform.cpp:77-152) shares the fused kernels' order
+    m = oracle.uniform(dim, seed=99 + dim)
+    assert np.array_equal(solver.sum_across_rows(m), oracle.sum_across_rows(m, oracle.SUM_CUDA))
+
+
+def test_eps_and_cap_options_bit_identical(solver):
+    dim = 1024
+    mat = oracle.hilbert(dim)
+    d = solver.upload(mat)
+    info, vec = solver.solve_device(d, dim, eps=1e-2)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, eps=1e-2), "eps 1e-2")
+    info, vec = solver.solve_device(d, dim, max_iter=5)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=5), "cap 5")
