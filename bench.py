@@ -46,6 +46,10 @@ def parse_args():
                     help="hilbert-N or uniform-N; default hilbert-8192 at 1 GPU, hilbert-32768 sharded")
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--form", type=int, default=0, help="0 read-only (default), 1 in-place")
+    ap.add_argument("--eps", type=float, default=1e-3, help="stop threshold (reference EPS = 1e-3)")
+    ap.add_argument("--stop", default="absolute", choices=["absolute", "relative"],
+                    help="absolute = the reference's stop test (default; the only one the headline is quoted on); "
+                         "relative = extension, max adjacent diff < eps * max(s)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 LDG; 2-9 TMA ring; 10-19 single-chunk variants")
     ap.add_argument("--sweep", type=int, default=None)
     ap.add_argument("--threads", type=int, default=0)
@@ -269,7 +273,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     solver = Solver(local_rank)
     opts = dict(max_iter=args.max_iter, form=args.form, sweep=args.sweep, threads=args.threads, ctas=args.ctas,
-                kernel=args.kernel)
+                kernel=args.kernel, eps=args.eps, stop=1 if args.stop == "relative" else 0)
 
     def barrier():
         if world > 1:
@@ -434,7 +438,8 @@ def main():
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "N": dim, "rows_per_gpu": rows, "form": "read-only" if args.form == 0 else "in-place",
-                       "eps": 1e-3, "max_iter": args.max_iter, "sweep": 1 if args.sweep is None else args.sweep, "kernel": args.kernel,
+                       "eps": args.eps, "stop": args.stop, "max_iter": args.max_iter,
+                       "sweep": 1 if args.sweep is None else args.sweep, "kernel": args.kernel,
                        "grid": last.grid,
                        "sharding": f"row-block x{world}, fused peer-store exchange" if world > 1 else "none",
                        "l2": ("matrix shard larger than L2; no flush" if flush is None

@@ -25,6 +25,7 @@ class StOptions(ctypes.Structure):
         ("ctas", ctypes.c_int32),
         ("kernel", ctypes.c_int32),
         ("l2_keep_pct", ctypes.c_int32),
+        ("stop", ctypes.c_int32),
     ]
 
 

@@ -36,6 +36,28 @@ enum : int
   kFormInPlace = 1   // W <- D^-1 W D, s = rowsum(W)
 };
 
+// Stop test of a round (template parameter STOP of the round kernels).
+//   absolute: every circular adjacent pair |s[r] - s[r+1]| < eps        -- the reference's test
+//             (similarity_transform.cpp:413-421), the default and the only parity-relevant one
+//   relative: max_r |s[r] - s[r+1]| < eps * max(0, max_r s[r])          -- scale-free extension
+//             (SURVEY 8(f) rank 3): the absolute test can never hold once one ulp of lambda
+//             exceeds eps (uniform matrices from N = 16384 up)
+enum : int
+{
+  kStopAbsolute = 0,
+  kStopRelative = 1
+};
+
+// Relative stop test: the largest adjacent difference is reduced as the BIT PATTERN of a
+// non-negative float -- for x >= 0 the unsigned order of the bits is the numeric order, and a
+// NaN (0x7fc00000...) sorts above +inf, so the max is NaN-propagating and a NaN anywhere makes
+// `dmax < threshold` false, exactly like the per-pair comparison of the absolute test.
+__device__ __forceinline__ uint32_t
+diff_bits(float a, float b)
+{
+  return __float_as_uint(fabsf(a - b));
+}
+
 // Barrier words live on their own 128-byte lines.
 struct alignas(128) BarrierState
 {
@@ -479,7 +501,7 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
 // ---------------------------------------------------------------------------------------
 // the round loop
 // ---------------------------------------------------------------------------------------
-template<int VEC, int FORM, int MAX_THREADS>
+template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundParams p)
 {
   const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
@@ -625,6 +647,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     // ---- every CTA: max, circular stop test over the full vector ----   reference :41, :44
     float mx = 0.f; // reference zero-fills the max cell (:169)
     int ok = 1;
+    uint32_t dbits = 0u; // relative stop test only: bits of the largest adjacent difference
     // every CTA scans the same vector at the same time: start each at its own offset (cb) so
     // they do not queue on the same L2 lines; max / AND are order-independent.  The circular
     // neighbour comes from the next lane by shuffle, as in the reference (:413-417); four
@@ -655,9 +678,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
             if (idx < nv) {
               const float4 v = t4[j];
               mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-              // strict <, wrap pair included (:413-421)
-              ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
-                    (fabsf(v.w - nxt) < p.eps);
+              if (STOP == kStopRelative) {
+                dbits = max(max(dbits, diff_bits(v.x, v.y)),
+                            max(max(diff_bits(v.y, v.z), diff_bits(v.z, v.w)), diff_bits(v.w, nxt)));
+              } else {
+                // strict <, wrap pair included (:413-421)
+                ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
+                      (fabsf(v.w - nxt) < p.eps);
+              }
             }
           }
         }
@@ -683,16 +711,24 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
               next = nx[j];
             if (c0 < N) {
               mx = fmaxf(mx, sf[j]);
-              ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+              if (STOP == kStopRelative)
+                dbits = max(dbits, diff_bits(sf[j], next));
+              else
+                ok &= (fabsf(sf[j] - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
             }
           }
         }
       }
     }
+    if (STOP == kStopRelative)
+      ok = (int)dbits; // from here on `ok` carries the difference bits; max instead of AND
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+      if (STOP == kStopRelative)
+        ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+      else
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
     }
     if (lane == 0) {
       red_max[warp] = mx;
@@ -701,15 +737,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     __syncthreads();
     if (warp == 0) {
       mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
-      ok = (uint32_t)lane < kWarps ? red_ok[lane] : 1;
+      ok = (uint32_t)lane < kWarps ? red_ok[lane] : (STOP == kStopRelative ? 0 : 1);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        if (STOP == kStopRelative)
+          ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+        else
+          ok &= __shfl_xor_sync(0xffffffffu, ok, o);
       }
       if (lane == 0) {
         bc_max = mx;
-        bc_ok = ok;
+        bc_ok = STOP == kStopRelative ? (__uint_as_float((uint32_t)ok) < p.eps * mx ? 1 : 0) : ok;
       }
     }
     __syncthreads();

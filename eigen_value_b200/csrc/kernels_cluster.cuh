@@ -29,7 +29,7 @@ constexpr int kClusterMaxCtas = 8;       // portable cluster size
 constexpr size_t kClusterSmemBudget = 200 * 1024;
 constexpr int kRowsAtOnce = 4;           // independent rows a warp keeps in flight
 
-template<int THREADS>
+template<int THREADS, int STOP = kStopAbsolute>
 __global__ void __launch_bounds__(THREADS, 1) round_loop_cluster_kernel(const RoundParams p)
 {
   namespace cg = cooperative_groups;
@@ -142,17 +142,23 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_cluster_kernel(const Ro
 
     // ---- max, circular stop test, eigenvector update: all from shared memory ----  :41-44
     float mx = 0.f; // reference zero-fills the max cell (:169)
-    int ok = 1;
+    int ok = STOP == kStopRelative ? 0 : 1;
     for (uint32_t c = tid; c < N; c += THREADS) {
       const float self = Scur[c];
       const float next = Scur[c + 1u == N ? 0u : c + 1u];
       mx = fmaxf(mx, self);
-      ok &= (fabsf(self - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
+      if (STOP == kStopRelative) // `ok` carries the bits of the largest adjacent difference (see diff_bits)
+        ok = (int)max((uint32_t)ok, diff_bits(self, next));
+      else
+        ok &= (fabsf(self - next) < p.eps) ? 1 : 0; // strict <, wrap pair included (:413-421)
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+      if (STOP == kStopRelative)
+        ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+      else
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
     }
     if (lane == 0) {
       red_max[warp] = mx;
@@ -161,15 +167,18 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_cluster_kernel(const Ro
     __syncthreads();
     if (warp == 0) {
       mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
-      ok = (uint32_t)lane < kWarps ? red_ok[lane] : 1;
+      ok = (uint32_t)lane < kWarps ? red_ok[lane] : (STOP == kStopRelative ? 0 : 1);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        if (STOP == kStopRelative)
+          ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+        else
+          ok &= __shfl_xor_sync(0xffffffffu, ok, o);
       }
       if (lane == 0) {
         bc_max = mx;
-        bc_ok = ok;
+        bc_ok = STOP == kStopRelative ? (__uint_as_float((uint32_t)ok) < p.eps * mx ? 1 : 0) : ok;
       }
     }
     __syncthreads();

@@ -84,7 +84,7 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return warp_sum(acc[0]);
 }
 
-template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll>
+template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
   const uint32_t THREADS = blockDim.x; // run-time CTA size (a multiple of 32, <= MAX_THREADS)
@@ -291,15 +291,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     float4 sv4[kRegVec];
     float mx = 0.f; // reference zero-fills the max cell (:169)
     int ok = 1;
+    uint32_t dbits = 0u; // relative stop test only: bits of the largest adjacent difference
     auto vec_index = [&](uint32_t idx) {
       const uint32_t v = idx + rotv;
       return v < nv ? v : v - nv;
     };
     auto scan4 = [&](const float4& v, float nxt) {
       mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-      // strict <, wrap pair included (:413-421)
-      ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
-            (fabsf(v.w - nxt) < p.eps);
+      if (STOP == kStopRelative) {
+        dbits = max(max(dbits, diff_bits(v.x, v.y)),
+                    max(max(diff_bits(v.y, v.z), diff_bits(v.z, v.w)), diff_bits(v.w, nxt)));
+      } else {
+        // strict <, wrap pair included (:413-421)
+        ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
+              (fabsf(v.w - nxt) < p.eps);
+      }
     };
     if (reg_tail) {
       float nx[kRegVec];
@@ -349,10 +355,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
       }
     }
+    if (STOP == kStopRelative)
+      ok = (int)dbits; // from here on `ok` carries the difference bits; max instead of AND
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+      if (STOP == kStopRelative)
+        ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+      else
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
     }
     if (lane == 0) {
       red_max[warp] = mx;
@@ -361,15 +372,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     __syncthreads();
     if (warp == 0) {
       mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
-      ok = (uint32_t)lane < kWarps ? red_ok[lane] : 1;
+      ok = (uint32_t)lane < kWarps ? red_ok[lane] : (STOP == kStopRelative ? 0 : 1);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        if (STOP == kStopRelative)
+          ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
+        else
+          ok &= __shfl_xor_sync(0xffffffffu, ok, o);
       }
       if (lane == 0) {
         bc_max = mx;
-        bc_ok = ok;
+        bc_ok = STOP == kStopRelative ? (__uint_as_float((uint32_t)ok) < p.eps * mx ? 1 : 0) : ok;
       }
     }
     __syncthreads();

@@ -60,10 +60,10 @@ Context::preload_kernels()
 {
   cudaFuncAttributes attr{};
   const void* kernels[] = {
-    (const void*)round_loop_cluster_kernel<512>,
-    (const void*)round_loop_sc_kernel<512, 1, kUnroll>,
-    (const void*)round_loop_kernel<4, kFormReadOnly, 512>,
-    (const void*)round_loop_kernel<1, kFormReadOnly, 512>,
+    (const void*)round_loop_cluster_kernel<512, kStopAbsolute>,
+    (const void*)round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute>,
+    (const void*)round_loop_kernel<4, kFormReadOnly, 512, kStopAbsolute>,
+    (const void*)round_loop_kernel<1, kFormReadOnly, 512, kStopAbsolute>,
   };
   for (const void* k : kernels)
     ST_CUDA(cudaFuncGetAttributes(&attr, k));
@@ -172,11 +172,11 @@ Context::reserve_work(size_t elems)
 // ---- launch of the round loop ------------------------------------------------------------
 // CTA size is a run-time value (a multiple of 32); the template parameter is only the
 // __launch_bounds__ ceiling (512 -> 128 registers/thread, 1024 -> 64).
-template<int VEC, int FORM, int MAX_THREADS>
+template<int VEC, int FORM, int MAX_THREADS, int STOP>
 static void
 launch_round_loop(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_kernel<VEC, FORM, MAX_THREADS>;
+  auto kernel = round_loop_kernel<VEC, FORM, MAX_THREADS, STOP>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
@@ -184,15 +184,24 @@ launch_round_loop(const RoundParams& p, int grid, int threads, size_t smem, cuda
                                       stream));
 }
 
-template<int VEC, int FORM>
+template<int VEC, int FORM, int STOP>
 static void
 launch_by_threads(int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
 {
   if (threads <= 256)
-    return launch_round_loop<VEC, FORM, 256>(p, grid, threads, smem, stream);
+    return launch_round_loop<VEC, FORM, 256, STOP>(p, grid, threads, smem, stream);
   if (threads <= 512)
-    return launch_round_loop<VEC, FORM, 512>(p, grid, threads, smem, stream);
-  return launch_round_loop<VEC, FORM, 1024>(p, grid, threads, smem, stream);
+    return launch_round_loop<VEC, FORM, 512, STOP>(p, grid, threads, smem, stream);
+  return launch_round_loop<VEC, FORM, 1024, STOP>(p, grid, threads, smem, stream);
+}
+
+template<int VEC, int FORM>
+static void
+launch_by_stop(int stop, int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  if (stop == kStopRelative)
+    return launch_by_threads<VEC, FORM, kStopRelative>(threads, p, grid, smem, stream);
+  return launch_by_threads<VEC, FORM, kStopAbsolute>(threads, p, grid, smem, stream);
 }
 
 // Warp count for a CTA that owns `nrows` rows, one warp per row at a time: the count in
@@ -288,11 +297,11 @@ sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t rows_cap, uin
   return off + (size_t)(threads / 32) * sizeof(uint64_t);
 }
 
-template<int MAX_THREADS, int PF, int LD = kUnroll>
+template<int MAX_THREADS, int PF, int LD = kUnroll, int STOP = kStopAbsolute>
 static void
 launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_sc_kernel<MAX_THREADS, PF, LD>;
+  auto kernel = round_loop_sc_kernel<MAX_THREADS, PF, LD, STOP>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
@@ -301,8 +310,17 @@ launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStre
 }
 
 static void
-launch_sc(int id, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
+launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
+  if (stop == kStopRelative) {
+    // the configurations the automatic choice can pick (1, 2 or 3 prefetch batches, 512 threads)
+    switch (id) {
+      case 10: return launch_sc_one<512, 2, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
+      case 12: return launch_sc_one<512, 3, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
+      case 13: return launch_sc_one<512, 1, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
+      default: throw std::invalid_argument("this resident-e tuning variant supports ST_STOP_ABSOLUTE only");
+    }
+  }
   switch (id) {
     case 10: return launch_sc_one<512, 2>(p, grid, threads, smem, stream);
     case 11: return launch_sc_one<512, 0>(p, grid, threads, smem, stream);
@@ -342,10 +360,11 @@ cluster_ctas_for(uint32_t dim, size_t* smem_bytes)
   return best;
 }
 
+template<int STOP>
 static void
 launch_cluster(const RoundParams& p, int ctas, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_cluster_kernel<kClusterThreads>;
+  auto kernel = round_loop_cluster_kernel<kClusterThreads, STOP>;
   ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
@@ -383,6 +402,9 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const uint32_t row0 = shard ? shard->row0 : 0u;
   const uint32_t rows = shard ? shard->rows : dim;
   const int form = opt.form == ST_FORM_INPLACE ? kFormInPlace : kFormReadOnly;
+  if (opt.stop != ST_STOP_ABSOLUTE && opt.stop != ST_STOP_RELATIVE)
+    throw std::invalid_argument("solve: unknown st_options.stop");
+  const int stop = opt.stop == ST_STOP_RELATIVE ? kStopRelative : kStopAbsolute;
 
   RoundParams p{};
   p.A = d_rows;
@@ -485,6 +507,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         continue;
       if (opt.kernel == 0 && pinned > c.max_threads)
         continue;
+      if (opt.kernel == 0 && stop == kStopRelative && c.id != 13 && c.id != 10 && c.id != 12)
+        continue; // only the automatic configurations are built with the relative stop test
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
@@ -516,6 +540,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   if (!sc && opt.kernel >= 2 && opt.kernel < 10) {
     if (!readonly4)
       throw std::invalid_argument("solve: TMA kernel needs the read-only form and dim % 4 == 0");
+    if (stop != kStopAbsolute)
+      throw std::invalid_argument("solve: the TMA tuning variants support ST_STOP_ABSOLUTE only");
     for (const TmaConfig& c : kTmaConfigs) {
       if (c.id != opt.kernel)
         continue;
@@ -547,21 +573,24 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
   if (cluster_ctas) {
-    launch_cluster(p, cluster_ctas, smem, stream_);
+    if (stop == kStopRelative)
+      launch_cluster<kStopRelative>(p, cluster_ctas, smem, stream_);
+    else
+      launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
   } else if (sc) {
-    launch_sc(sc->id, p, grid, threads, smem, stream_);
+    launch_sc(sc->id, stop, p, grid, threads, smem, stream_);
   } else if (tma) {
     launch_tma(tma->id, p, grid, smem, stream_);
   } else if (vec4) {
     if (form == kFormInPlace)
-      launch_by_threads<4, kFormInPlace>(threads, p, grid, smem, stream_);
+      launch_by_stop<4, kFormInPlace>(stop, threads, p, grid, smem, stream_);
     else
-      launch_by_threads<4, kFormReadOnly>(threads, p, grid, smem, stream_);
+      launch_by_stop<4, kFormReadOnly>(stop, threads, p, grid, smem, stream_);
   } else {
     if (form == kFormInPlace)
-      launch_by_threads<1, kFormInPlace>(threads, p, grid, smem, stream_);
+      launch_by_stop<1, kFormInPlace>(stop, threads, p, grid, smem, stream_);
     else
-      launch_by_threads<1, kFormReadOnly>(threads, p, grid, smem, stream_);
+      launch_by_stop<1, kFormReadOnly>(stop, threads, p, grid, smem, stream_);
   }
   ST_CUDA(cudaEventRecord(ev1_, stream_));
 

@@ -78,6 +78,17 @@ enum
   ST_FORM_INPLACE = 1   /* literal W <- D^-1 W D on a working copy (reference :52)       */
 };
 
+enum
+{
+  ST_STOP_ABSOLUTE = 0, /* every circular adjacent pair |s[r] - s[r+1]| < eps: the reference's
+                           test (similarity_transform.cpp:413-421), the default                */
+  ST_STOP_RELATIVE = 1  /* max_r |s[r] - s[r+1]| < eps * max(0, max_r s[r]): scale-free extension.
+                           The absolute test cannot hold once one ulp of lambda exceeds eps
+                           (e.g. uniform (0,1] matrices from N = 16384 up run the full max_iter
+                           rounds); the relative test stops those after a handful of rounds.
+                           Changes WHEN the loop stops, never the arithmetic of a round.        */
+};
+
 typedef struct st_options
 {
   float eps;         /* stop threshold, reference EPS                               */
@@ -94,6 +105,7 @@ typedef struct st_options
   int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
+  int32_t stop;        /* ST_STOP_*; tuning kernels 2-9, 11, 14-19 support ST_STOP_ABSOLUTE only */
 } st_options;
 
 typedef struct st_result

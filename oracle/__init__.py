@@ -23,7 +23,8 @@ MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
 
 FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
-SUM_CUDA = 4   # the CUDA kernels' evaluation order: with FORM_READONLY bit-identical to the GPU
+SUM_CUDA = 4   # the CUDA kernels' evaluation order: bit-identical to the GPU (tests/test_zz_gpu_bitexact.py)
+STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # the reference's stop test | extension: threshold eps * max(s)
 
 
 def sum_workgroup(wg_size: int) -> int:
@@ -71,6 +72,14 @@ def lib() -> ctypes.CDLL:
             ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
             ctypes.POINTER(ctypes.c_double)]
         L.oracle_similarity_transform_ex.restype = ctypes.c_int64
+        L.oracle_similarity_transform_ex2.argtypes = [
+            _f32p, _f32p, _f32p, ctypes.c_uint32,
+            np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS"),
+            ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
+            ctypes.POINTER(ctypes.c_double)]
+        L.oracle_similarity_transform_ex2.restype = ctypes.c_int64
+        L.oracle_stop_relative.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float]
+        L.oracle_stop_relative.restype = ctypes.c_uint32
         L.oracle_time_rounds.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
         L.oracle_time_rounds.restype = ctypes.c_double
         _lib = L
@@ -120,6 +129,12 @@ def stop(vec: np.ndarray, eps: float = EPS) -> int:
     return int(lib().oracle_stop(np.ascontiguousarray(vec, dtype=np.float32), vec.shape[0], eps))
 
 
+def stop_relative(vec: np.ndarray, eps: float = EPS) -> int:
+    """Extension (not reference behaviour): all circular adjacent |diff| < eps * max(0, max(vec))."""
+    v = np.ascontiguousarray(vec, dtype=np.float32)
+    return int(lib().oracle_stop_relative(v, v.shape[0], eps, find_max(v)))
+
+
 def compute_next_matrix(mat: np.ndarray, vec: np.ndarray) -> None:
     assert mat.flags["C_CONTIGUOUS"] and mat.dtype == np.float32
     lib().oracle_compute_next_matrix(mat, vec, vec.shape[0])
@@ -127,7 +142,7 @@ def compute_next_matrix(mat: np.ndarray, vec: np.ndarray) -> None:
 
 def similarity_transform(mat: np.ndarray, eps: float = EPS, max_itr: int = MAX_ITR,
                          form: int = FORM_INPLACE, sum_mode: int = SUM_LANES16,
-                         ranks: int = 1) -> Tuple[np.float32, np.ndarray, float, int]:
+                         ranks: int = 1, stop: int = STOP_ABSOLUTE) -> Tuple[np.float32, np.ndarray, float, int]:
     """(lambda, raw eigen_vec, loop ms, iter_count) -- same tuple as the reference's Python
     wrapper returns (wrapper/python/similarity_transform.py:78)."""
     mat = np.ascontiguousarray(mat, dtype=np.float32)
@@ -137,8 +152,8 @@ def similarity_transform(mat: np.ndarray, eps: float = EPS, max_itr: int = MAX_I
     vec = np.empty(n, dtype=np.float32)
     itr = np.zeros(1, dtype=np.uint32)
     ms = ctypes.c_double(0.0)
-    rc = lib().oracle_similarity_transform_ex(mat, val, vec, n, itr, eps, max_itr, form, sum_mode,
-                                              ranks, ctypes.byref(ms))
+    rc = lib().oracle_similarity_transform_ex2(mat, val, vec, n, itr, eps, max_itr, form, sum_mode,
+                                               ranks, stop, ctypes.byref(ms))
     if rc < 0:
         raise MemoryError("oracle allocation failed")
     return val[0], vec, ms.value, int(itr[0])

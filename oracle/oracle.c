@@ -283,6 +283,23 @@ oracle_stop(const float* vec, uint32_t dim, float eps)
   return ok;
 }
 
+/* Relative stop test -- an EXTENSION, not reference behaviour (the CUDA side is
+ * ST_STOP_RELATIVE / st::kStopRelative): 1 iff |s[r] - s[(r+1) % dim]| < eps * m for every r, with
+ * m = max(0, max_r s[r]) the value find_max() returns.  Same strict <, same wrap pair, same NaN
+ * behaviour (any NaN difference fails) as stop(); only the threshold scales with the row sums. */
+uint32_t
+oracle_stop_relative(const float* vec, uint32_t dim, float eps, float m)
+{
+  const float thr = eps * m;
+  uint32_t ok = 1;
+  for (uint32_t r = 0; r < dim; r++) {
+    float diff = fabsf(vec[r] - vec[(r + 1) % dim]);
+    if (!(diff < thr))
+      ok = 0;
+  }
+  return ok;
+}
+
 /* compute_next_matrix(): W[r][c] *= (1.f / s[r]) * s[c]
  *                                                 similarity_transform.cpp:286-330 (:324-325) */
 void
@@ -401,10 +418,16 @@ readonly_row_pass(const float* mat, const float* e, float* s, uint32_t dim, uint
  * executes the row-block sharded algorithm (rank g owns rows [g*dim/ranks, (g+1)*dim/ranks)),
  * each "rank" writing only its slice of s before the gather point.
  */
+enum
+{
+  ORACLE_STOP_ABSOLUTE = 0, /* the reference's test, stop()            similarity_transform.cpp:44 */
+  ORACLE_STOP_RELATIVE = 1  /* oracle_stop_relative(): extension, threshold eps * max(s)          */
+};
+
 int64_t
-oracle_similarity_transform_ex(const float* mat, float* eigen_val, float* eigen_vec, uint32_t dim,
-                               uint32_t* iter_count, float eps, uint32_t max_itr, int form,
-                               int sum_mode, uint32_t ranks, double* elapsed_ms)
+oracle_similarity_transform_ex2(const float* mat, float* eigen_val, float* eigen_vec, uint32_t dim,
+                                uint32_t* iter_count, float eps, uint32_t max_itr, int form,
+                                int sum_mode, uint32_t ranks, int stop_mode, double* elapsed_ms)
 {
   const size_t n = dim;
   if (dim == 0 || ranks == 0)
@@ -446,7 +469,10 @@ oracle_similarity_transform_ex(const float* mat, float* eigen_val, float* eigen_
     /* ---- gather point: every rank now holds the full s ---- */
     float m = oracle_find_max(sum_vec, dim);                  /* :41 */
     oracle_compute_eigen_vector(sum_vec, m, eigen_vec, dim);  /* :42-43 */
-    if (oracle_stop(sum_vec, dim, eps) == 1)                  /* :44-50 */
+    const uint32_t converged = stop_mode == ORACLE_STOP_RELATIVE
+                                 ? oracle_stop_relative(sum_vec, dim, eps, m)
+                                 : oracle_stop(sum_vec, dim, eps);
+    if (converged == 1) /* :44-50 */
       break;
     if (form == ORACLE_FORM_INPLACE)
       oracle_compute_next_matrix(work, sum_vec, dim); /* :52 */
@@ -460,6 +486,16 @@ oracle_similarity_transform_ex(const float* mat, float* eigen_val, float* eigen_
   free(sum_vec);
   free(work);
   return (int64_t)(t1 - t0); /* :57-58 duration_cast<milliseconds> truncates */
+}
+
+/* The reference's stop test (the only one parity is defined on). */
+int64_t
+oracle_similarity_transform_ex(const float* mat, float* eigen_val, float* eigen_vec, uint32_t dim,
+                               uint32_t* iter_count, float eps, uint32_t max_itr, int form,
+                               int sum_mode, uint32_t ranks, double* elapsed_ms)
+{
+  return oracle_similarity_transform_ex2(mat, eigen_val, eigen_vec, dim, iter_count, eps, max_itr, form,
+                                         sum_mode, ranks, ORACLE_STOP_ABSOLUTE, elapsed_ms);
 }
 
 /* Reference defaults: EPS, MAX_ITR, the literal in-place form. */

@@ -21,7 +21,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import oracle  # noqa: E402
-from eigen_value_b200 import Solver  # noqa: E402
+from eigen_value_b200 import STOP_RELATIVE, Solver  # noqa: E402
 from eigen_value_b200.sharded import CudaRoundBackend, ShardedSolver, collective_round_loop  # noqa: E402
 
 
@@ -61,6 +61,22 @@ def main():
         report.append({"case": f"{kind}-{dim}-form{form}", "rounds": info.iter_count,
                        "lambda": float(info.eigen_val), "us_per_round": info.round_us_median,
                        "us_per_round_1gpu": one.round_us_median})
+        d_rows.free()
+        d_full.free()
+        sh.close()
+
+    # ST_STOP_RELATIVE (extension): the decision is taken redundantly on every rank from identical
+    # inputs, so the sharded solve stops in the same round with the same bits as one GPU
+    for kind, dim in (("uniform", 4096), ("hilbert", 16384)):
+        sh = ShardedSolver(solver, dim, rank, world)
+        d_rows = sh.hilbert() if kind == "hilbert" else sh.uniform(0x5EED0001)
+        dist.barrier()
+        info, vec = sh.solve(d_rows, eps=1e-6, stop=STOP_RELATIVE, max_iter=60)
+        d_full = solver.hilbert(dim) if kind == "hilbert" else solver.uniform(dim, 0x5EED0001)
+        one, one_vec = solver.solve_device(d_full, dim, eps=1e-6, stop=STOP_RELATIVE, max_iter=60)
+        assert info.iter_count == one.iter_count and info.eigen_val == one.eigen_val, (kind, dim)
+        assert np.array_equal(vec, one_vec), (kind, dim)
+        report.append({"case": f"{kind}-{dim}-relative-stop", "rounds": info.iter_count, "lambda": float(info.eigen_val)})
         d_rows.free()
         d_full.free()
         sh.close()

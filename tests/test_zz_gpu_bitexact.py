@@ -119,3 +119,49 @@ def test_eps_and_cap_options_bit_identical(solver):
     _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, eps=1e-2), "eps 1e-2")
     info, vec = solver.solve_device(d, dim, max_iter=5)
     _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=5), "cap 5")
+
+
+# ---- ST_STOP_RELATIVE (extension): same bits as the oracle's relative test ----------
+from eigen_value_b200 import STOP_RELATIVE  # noqa: E402
+
+
+@pytest.mark.parametrize("form", [FORM_READONLY, FORM_INPLACE])
+@pytest.mark.parametrize("dim", [3, 100, 512, 1000, 1023, 2048, 8192])
+def test_relative_stop_is_bit_identical_to_the_oracle(solver, form, dim):
+    # cluster kernel (<= 512), resident-e kernel, general loop with vector and scalar loads, both forms
+    mat = _matrix("uniform", dim) if dim > 3 else A3
+    for eps in (1e-3, 1e-6):
+        info, vec = solver.solve_device(solver.upload(mat), dim, form=form, eps=eps, stop=STOP_RELATIVE, max_iter=60)
+        want = _oracle(mat, form, eps=eps, stop=oracle.STOP_RELATIVE, max_itr=60)
+        _assert_same_bits((info.eigen_val, vec, info.iter_count), want, f"relative {dim} eps={eps}")
+
+
+def test_relative_stop_converges_where_the_reference_test_cannot(solver):
+    """uniform (0,1] 16384^2: the reference's absolute test never holds in fp32 and the loop
+    runs to the cap; the relative test stops after a few rounds with A.v ~= lambda.v to 1e-5."""
+    dim = 16384
+    d = solver.uniform(dim, 0x5EED0001)
+    capped, _ = solver.solve_device(d, dim, max_iter=12)
+    assert capped.iter_count == 12
+    info, vec = solver.solve_device(d, dim, eps=1e-6, stop=STOP_RELATIVE)
+    mat = oracle.uniform(dim, 0x5EED0001)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count),
+                      _oracle(mat, eps=1e-6, stop=oracle.STOP_RELATIVE), "uniform-16384 relative")
+    assert 2 <= info.iter_count <= 8
+    rows = [0, 1, 8191, dim - 1]
+    lhs = mat[rows].astype(np.float64) @ vec.astype(np.float64)
+    assert np.max(np.abs(lhs - float(info.eigen_val) * vec[rows]) / np.abs(lhs)) < 1e-5
+
+
+def test_relative_stop_with_nan_hits_the_cap_and_tuning_kernels_refuse_it(solver):
+    mat = (oracle.uniform(64, 5) + np.float32(0.5)).astype(np.float32)
+    mat[32, 21] = np.nan
+    info, _ = solver.solve_device(solver.upload(mat), 64, stop=STOP_RELATIVE, max_iter=50)
+    assert info.iter_count == 50
+    d = solver.hilbert(1024)
+    with pytest.raises(Exception):
+        solver.solve_device(d, 1024, kernel=2, stop=STOP_RELATIVE)     # TMA tuning variant
+    with pytest.raises(Exception):
+        solver.solve_device(d, 1024, stop=7)                           # unknown mode
+    info, _ = solver.solve_device(d, 1024)                             # the handle stays usable
+    assert info.iter_count == 13

@@ -1,0 +1,63 @@
+"""Prove that a source change left the MEASURED kernels untouched: compare the instruction streams of
+every kernel in two builds of libsimilarity_transform.so.
+
+    cuobjdump -sass eigen_value_b200/libsimilarity_transform.so > /tmp/before.sass    # before the change
+    ... edit, rebuild ...
+    cuobjdump -sass eigen_value_b200/libsimilarity_transform.so > /tmp/after.sass
+    python tools/sass_diff.py /tmp/before.sass /tmp/after.sass [--append-arg Li0E]
+
+Instruction text is compared (addresses and encodings are ignored).  `--append-arg` maps the old
+mangled names to new ones when a trailing template argument was added to the round kernels (e.g.
+`Li0E` for `int STOP = 0`), so that `round_loop_kernel<4,0,512>` is compared with
+`round_loop_kernel<4,0,512,0>`.  Exit code 1 if any kernel of the first build is missing or differs.
+
+Used in round 1 when the stop-test template parameter was added without GPU time left to re-measure:
+all 41 kernels of the measured build are instruction-identical in the new one.
+"""
+import argparse
+import re
+import sys
+
+
+def split(path):
+    funcs, cur = {}, None
+    for line in open(path):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+            continue
+        if cur is not None:
+            m2 = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+            if m2:
+                funcs[cur].append(m2.group(1).strip())
+    return funcs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("before")
+    ap.add_argument("after")
+    ap.add_argument("--append-arg", default=None,
+                    help="mangled template argument appended to kernels taking RoundParams, e.g. Li0E")
+    args = ap.parse_args()
+    b, a = split(args.before), split(args.after)
+    bad = 0
+    for name, body in b.items():
+        cands = [name]
+        if args.append_arg and "RoundParams" in name:
+            cands.append(name.replace("EEvNS_11RoundParamsE", args.append_arg + "EEvNS_11RoundParamsE"))
+        found = next((c for c in cands if c in a), None)
+        if found is None:
+            print("MISSING in second build:", name)
+            bad += 1
+        elif a[found] != body:
+            print(f"DIFF ({len(body)} vs {len(a[found])} instructions): {name}")
+            bad += 1
+    print(f"kernels compared: {len(b)}; missing or different: {bad}; kernels only in the second build: "
+          f"{len(a) - (len(b) - bad)}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
