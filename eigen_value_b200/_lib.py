@@ -76,6 +76,8 @@ SYMBOLS = {
                                      ctypes.POINTER(StResult)]),
     "st_round_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
     "st_phase_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
+    "st_timer_start": (ctypes.c_int, [_VP]),
+    "st_timer_stop": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_float)]),
     "st_sum_across_rows": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_uint32]),
     "st_row_pass_readonly": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_uint32, ctypes.c_uint32,
                                             ctypes.c_uint32]),

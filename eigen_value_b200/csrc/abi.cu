@@ -311,11 +311,35 @@ st_phase_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count
   });
 }
 
+int
+st_timer_start(void* ctx)
+{
+  return guarded([&] {
+    as_ctx(ctx)->timer_start();
+    return ST_OK;
+  });
+}
+
+int
+st_timer_stop(void* ctx, float* ms)
+{
+  return guarded([&] {
+    if (!ms)
+      throw std::invalid_argument("st_timer_stop: null out pointer");
+    *ms = as_ctx(ctx)->timer_stop();
+    return ST_OK;
+  });
+}
+
 // ---- per-kernel entry points ------------------------------------------------------------------
 int
 st_sum_across_rows(void* ctx, const float* d_mat, float* d_vec, uint32_t dim)
 {
-  return guarded([&] { return sum_across_rows(*as_ctx(ctx), d_mat, d_vec, dim, 0); });
+  return guarded([&] {
+    if (!d_mat || !d_vec || dim == 0)
+      throw std::invalid_argument("st_sum_across_rows: bad argument");
+    return sum_across_rows(*as_ctx(ctx), d_mat, d_vec, dim, 0);
+  });
 }
 int
 st_row_pass_readonly(void* ctx, const float* d_rows, const float* d_e, float* d_vec, uint32_t dim,
@@ -330,28 +354,48 @@ st_row_pass_readonly(void* ctx, const float* d_rows, const float* d_e, float* d_
 int
 st_find_max(void* ctx, const float* d_vec, float* d_max, uint32_t dim)
 {
-  return guarded([&] { return find_max(*as_ctx(ctx), d_vec, d_max, dim, 0); });
+  return guarded([&] {
+    if (!d_vec || !d_max || dim == 0)
+      throw std::invalid_argument("st_find_max: bad argument");
+    return find_max(*as_ctx(ctx), d_vec, d_max, dim, 0);
+  });
 }
 int
 st_compute_eigen_vector(void* ctx, const float* d_vec, const float* d_max, float* d_eigen_vec,
                         uint32_t dim)
 {
-  return guarded([&] { return compute_eigen_vector(*as_ctx(ctx), d_vec, d_max, d_eigen_vec, dim, 0); });
+  return guarded([&] {
+    if (!d_vec || !d_max || !d_eigen_vec || dim == 0)
+      throw std::invalid_argument("st_compute_eigen_vector: bad argument");
+    return compute_eigen_vector(*as_ctx(ctx), d_vec, d_max, d_eigen_vec, dim, 0);
+  });
 }
 int
 st_initialise_eigen_vector(void* ctx, float* d_eigen_vec, uint32_t dim)
 {
-  return guarded([&] { return initialise_eigen_vector(*as_ctx(ctx), d_eigen_vec, dim); });
+  return guarded([&] {
+    if (!d_eigen_vec || dim == 0)
+      throw std::invalid_argument("st_initialise_eigen_vector: bad argument");
+    return initialise_eigen_vector(*as_ctx(ctx), d_eigen_vec, dim);
+  });
 }
 int
 st_compute_next_matrix(void* ctx, float* d_mat, const float* d_vec, uint32_t dim)
 {
-  return guarded([&] { return compute_next_matrix(*as_ctx(ctx), d_mat, d_vec, dim, 0); });
+  return guarded([&] {
+    if (!d_mat || !d_vec || dim == 0)
+      throw std::invalid_argument("st_compute_next_matrix: bad argument");
+    return compute_next_matrix(*as_ctx(ctx), d_mat, d_vec, dim, 0);
+  });
 }
 int
 st_stop(void* ctx, const float* d_vec, uint32_t* d_ret, uint32_t dim, float eps)
 {
-  return guarded([&] { return stop(*as_ctx(ctx), d_vec, d_ret, dim, 0, eps); });
+  return guarded([&] {
+    if (!d_vec || !d_ret || dim == 0)
+      throw std::invalid_argument("st_stop: bad argument");
+    return stop(*as_ctx(ctx), d_vec, d_ret, dim, 0, eps);
+  });
 }
 
 // ---- row-block sharding -------------------------------------------------------------------------

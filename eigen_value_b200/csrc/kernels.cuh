@@ -811,13 +811,15 @@ __global__ void __launch_bounds__(256) sum_across_rows_kernel(const float* __res
   }
 }
 
-// find_max()  reference :154-227 -- single CTA, m = max(0, max_r s[r]).
+// find_max()  reference :154-227: m = max(0, max_r s[r]).  The host zero-fills the cell first, like
+// the reference does (:162-170); blocks combine with an integer atomicMax on the bit pattern, which
+// orders non-negative floats correctly (the running max starts at +0 and fmaxf drops NaNs).
 __global__ void __launch_bounds__(1024) find_max_kernel(const float* __restrict__ vec,
                                                         float* __restrict__ out, uint32_t dim)
 {
   __shared__ float red[32];
   float mx = 0.f;
-  for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x)
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x)
     mx = fmaxf(mx, vec[c]);
   for (int o = 16; o >= 1; o >>= 1)
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -829,7 +831,7 @@ __global__ void __launch_bounds__(1024) find_max_kernel(const float* __restrict_
     for (int o = 16; o >= 1; o >>= 1)
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (threadIdx.x == 0)
-      *out = mx;
+      atomicMax(reinterpret_cast<int*>(out), __float_as_int(mx));
   }
 }
 
@@ -851,19 +853,28 @@ fill_kernel(float* __restrict__ v, float value, uint32_t dim)
     v[r] = value;
 }
 
-// stop()  reference :332-460 -- single CTA; ret = 1 iff every circular adjacent pair differs by < eps
+// stop()  reference :332-460: ret = 1 iff every circular adjacent pair differs by < eps.  The host
+// fills the flag with 1 first, like the reference does (:351-359); a block that sees a failing
+// pair clears it (the reference combines with an atomic min, :438-446).
 __global__ void __launch_bounds__(1024) stop_kernel(const float* __restrict__ vec,
                                                     uint32_t* __restrict__ ret, uint32_t dim, float eps)
 {
   int ok = 1;
-  for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x) {
     const float self = vec[c];
     const float next = vec[c + 1u == dim ? 0u : c + 1u];
     ok &= (fabsf(self - next) < eps) ? 1 : 0;
   }
   ok = __syncthreads_and(ok);
-  if (threadIdx.x == 0)
-    *ret = ok ? 1u : 0u;
+  if (threadIdx.x == 0 && !ok)
+    atomicAnd(ret, 0u);
+}
+
+__global__ void
+fill_u32_kernel(uint32_t* __restrict__ v, uint32_t value, uint32_t n)
+{
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    v[r] = value;
 }
 
 // compute_next_matrix()  reference :286-330: W[r][c] *= (1.f / s[r]) * s[c]

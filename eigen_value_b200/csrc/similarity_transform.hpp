@@ -54,6 +54,10 @@ public:
   const std::vector<uint64_t>& round_timestamps() const { return last_ts_; }
   const std::vector<uint64_t>& phase_timestamps() const { return last_phase_ts_; }
 
+  // CUDA-event stopwatch on the context's stream (st_timer_start / st_timer_stop)
+  void timer_start();
+  float timer_stop();
+
   std::mutex& mutex() { return mu_; }
   void activate() const; // cudaSetDevice
 
@@ -72,6 +76,7 @@ private:
   CUstream_st* stream_ = nullptr;
   CUevent_st* ev0_ = nullptr;
   CUevent_st* ev1_ = nullptr;
+  CUevent_st* ev_timer_[2] = { nullptr, nullptr };
   std::mutex mu_;
 
   // scratch

@@ -91,6 +91,8 @@ Context::Context(int device)
   ST_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   ST_CUDA(cudaEventCreate(&ev0_));
   ST_CUDA(cudaEventCreate(&ev1_));
+  ST_CUDA(cudaEventCreate(&ev_timer_[0]));
+  ST_CUDA(cudaEventCreate(&ev_timer_[1]));
   ST_CUDA(cudaMalloc(&d_bar_, sizeof(BarrierState)));
   ST_CUDA(cudaMalloc(&d_scalars_, 64));
   ST_CUDA(cudaHostAlloc(&h_pinned_, 64, cudaHostAllocDefault));
@@ -110,6 +112,8 @@ Context::~Context()
   cudaFreeHost(h_pinned_);
   cudaEventDestroy(ev0_);
   cudaEventDestroy(ev1_);
+  cudaEventDestroy(ev_timer_[0]);
+  cudaEventDestroy(ev_timer_[1]);
   cudaStreamDestroy(stream_);
 }
 
@@ -117,6 +121,24 @@ void
 Context::activate() const
 {
   ST_CUDA(cudaSetDevice(device_));
+}
+
+void
+Context::timer_start()
+{
+  activate();
+  ST_CUDA(cudaEventRecord(ev_timer_[0], stream_));
+}
+
+float
+Context::timer_stop()
+{
+  activate();
+  ST_CUDA(cudaEventRecord(ev_timer_[1], stream_));
+  ST_CUDA(cudaEventSynchronize(ev_timer_[1]));
+  float ms = 0.f;
+  ST_CUDA(cudaEventElapsedTime(&ms, ev_timer_[0], ev_timer_[1]));
+  return ms;
 }
 
 // rounds beyond this are still executed but not time-stamped (bounds the stamp buffers when a
@@ -739,7 +761,8 @@ int
 find_max(st::Context& q, const float* d_vec, float* d_max, const uint dim, const uint)
 {
   q.activate();
-  find_max_kernel<<<1, 1024, 0, q.stream()>>>(d_vec, d_max, dim);
+  ST_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), q.stream())); // the zero-filled cell, reference :162-170
+  find_max_kernel<<<blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream()>>>(d_vec, d_max, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -783,7 +806,8 @@ int
 stop(st::Context& q, const float* d_vec, uint* d_ret, const uint dim, const uint, float eps)
 {
   q.activate();
-  stop_kernel<<<1, 1024, 0, q.stream()>>>(d_vec, d_ret, dim, eps);
+  fill_u32_kernel<<<1, 32, 0, q.stream()>>>(d_ret, 1u, 1u); // the flag starts at 1, reference :351-359
+  stop_kernel<<<blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream()>>>(d_vec, d_ret, dim, eps);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }

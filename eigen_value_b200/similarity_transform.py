@@ -287,6 +287,16 @@ class Solver:
         return {"pass_us": med(ph[:, 0] - start), "barrier_us": med(ph[:, 1] - ph[:, 0]),
                 "tail_us": med(ph[:, 2] - ph[:, 1]), "rounds": int(len(ph))}
 
+    def timer_start(self) -> None:
+        """CUDA-event stopwatch on the solver's stream (st_timer_start)."""
+        check(self.lib.st_timer_start(self.ctx), "st_timer_start")
+
+    def timer_stop(self) -> float:
+        """Milliseconds since timer_start(), measured on the device (st_timer_stop; synchronises)."""
+        ms = ctypes.c_float()
+        check(self.lib.st_timer_stop(self.ctx, ctypes.byref(ms)), "st_timer_stop")
+        return float(ms.value)
+
     # ---- per-kernel calls (reference L1 functions), numpy in / numpy out -------------------
     def sum_across_rows(self, mat: np.ndarray) -> np.ndarray:
         n = mat.shape[0]

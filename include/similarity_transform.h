@@ -165,6 +165,13 @@ int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* c
  * reference's per-kernel benchmarks give (benchmarks/similarity_transform.md). */
 int st_phase_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
 
+/* CUDA-event stopwatch on the context's stream: st_timer_start records an event, st_timer_stop
+ * records a second one, waits for it and returns the milliseconds between the two.  For timing the
+ * per-kernel entry points below the way the reference's per-kernel benchmarks do
+ * (benchmarks/benchmark_similarity_transform.cpp:24-433, main.cpp:37-159). */
+int st_timer_start(void* ctx);
+int st_timer_stop(void* ctx, float* ms);
+
 /* Per-kernel entry points on device buffers, one per reference L1 function
  * (include/similarity_transform.hpp:55-100; similarity_transform.cpp:77-460). */
 int st_sum_across_rows(void* ctx, const float* d_mat, float* d_vec, uint32_t dim);      /* :77-152  */
