@@ -1,0 +1,24 @@
+#!/bin/bash
+# First GPU call after a stretch of CPU-only work: everything that was written without hardware,
+# in the order that gives the most information if the call is cut short.  One B200:
+#
+#   gpurun --timeout 1500 -- 'bash tools/run_first_gpu_call.sh'
+#
+# Writes into gpurun_out/ (scratch); copy what should be judged into profiles/.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+{
+  echo "== smoke"
+  timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
+  echo "== bit-exact + relative-stop tests (new)"
+  timeout 900 python -m pytest tests/test_zz_gpu_bitexact.py -q -x 2>&1 | tail -15
+  echo "== full gpu suite"
+  timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8
+} > $O/first_call_tests.txt 2>&1
+timeout 600 python bench.py > $O/first_call_bench_n1.json 2> $O/first_call_bench_n1.err
+timeout 600 python tools/bench_kernels.py --json $O/first_call_bench_kernels.json > $O/first_call_bench_kernels.txt 2>&1
+# relative stop on BASELINE config 4's generator at a single-GPU size: converges instead of running 1000 rounds
+timeout 600 python bench.py --workload uniform-32768 --stop relative --eps 1e-6 --steps 5 --no-e2e --no-cpu-baseline \
+  --no-sweep-table > $O/first_call_bench_uniform32768_relative.json 2>> $O/first_call_bench_n1.err
+tail -5 $O/first_call_tests.txt
