@@ -282,6 +282,32 @@ st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt
 }
 
 int
+st_convert_f32_to_bf16(void* ctx, const float* d_src, uint16_t* d_dst, size_t count)
+{
+  return guarded([&] {
+    if (!d_src || !d_dst || count == 0)
+      throw std::invalid_argument("st_convert_f32_to_bf16: bad argument");
+    return convert_to_bf16(*as_ctx(ctx), d_src, d_dst, count);
+  });
+}
+
+int
+st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const st_options* opt,
+                     float* d_eigen_vec, st_result* res)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve(reinterpret_cast<const float*>(d_mat), dim, o, nullptr, d_eigen_vec, res, true);
+  });
+}
+
+int
 st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count)
 {
   return guarded([&] {
@@ -531,6 +557,22 @@ st_shard_solve(void* shard, const float* d_rows, const st_options* opt, float* d
       st_default_options(&o);
     std::lock_guard<std::mutex> lock(s->ctx->mutex());
     return s->ctx->solve(d_rows, s->dim, o, s, d_eigen_vec, res);
+  });
+}
+
+int
+st_shard_solve_bf16(void* shard, const uint16_t* d_rows, const st_options* opt, float* d_eigen_vec,
+                    st_result* res)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(s->ctx->mutex());
+    return s->ctx->solve(reinterpret_cast<const float*>(d_rows), s->dim, o, s, d_eigen_vec, res, true);
   });
 }
 

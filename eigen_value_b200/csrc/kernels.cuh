@@ -280,6 +280,92 @@ dot_acc(float a, float e, float acc)
   return fmaf(a, e, acc);
 }
 
+// ---- bf16 STORAGE of the matrix (opt-in, outside reference parity) ----------
+// The matrix is held as bfloat16 (2 bytes per element: half the HBM bytes per round); everything
+// else -- the eigenvector, the row sums, every accumulation -- stays fp32.  bf16 -> fp32 is exact
+// (the 16 bits become the high half of the float), so a solve on bf16 storage returns exactly the
+// bits an fp32-storage solve returns on the bf16-rounded matrix, evaluated in this order: the unit
+// is one 128-bit load = 8 consecutive elements, folded into its accumulator with 8 sequential FMAs;
+// unit j -> lane j % 32, accumulator (j / 32) % 8, as for fp32 (oracle: ORACLE_SUM_CUDA_BF16).
+struct bf16_t
+{
+  unsigned short bits;
+};
+
+__device__ __forceinline__ uint4
+ld_stream(const uint4* p)
+{
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p));
+  return v;
+}
+
+// little-endian: the element at the lower address is the low half of the 32-bit word
+__device__ __forceinline__ float
+bf16_lo(uint32_t w)
+{
+  return __uint_as_float(w << 16);
+}
+__device__ __forceinline__ float
+bf16_hi(uint32_t w)
+{
+  return __uint_as_float(w & 0xffff0000u);
+}
+
+__device__ __forceinline__ float
+dot_acc(uint4 a, float4 e0, float4 e1, float acc)
+{
+  acc = fmaf(bf16_lo(a.x), e0.x, acc);
+  acc = fmaf(bf16_hi(a.x), e0.y, acc);
+  acc = fmaf(bf16_lo(a.y), e0.z, acc);
+  acc = fmaf(bf16_hi(a.y), e0.w, acc);
+  acc = fmaf(bf16_lo(a.z), e1.x, acc);
+  acc = fmaf(bf16_hi(a.z), e1.y, acc);
+  acc = fmaf(bf16_lo(a.w), e1.z, acc);
+  acc = fmaf(bf16_hi(a.w), e1.w, acc);
+  return acc;
+}
+
+// One row segment of bf16 storage, one warp: `nu` units of 8 elements starting at `a`; the matching
+// eigenvector entries are es[2 j], es[2 j + 1] (float4, shared memory).  Same loop shape as
+// row_dot_readonly; LD = independent 128-bit loads in flight per lane.
+template<int LD>
+__device__ __forceinline__ float
+row_dot_bf16(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lane)
+{
+  static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
+  float acc[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++)
+    acc[u] = 0.f;
+  uint32_t i = (uint32_t)lane;
+  for (; i + 32u * (LD - 1) < nu; i += 32u * LD) {
+    uint4 v[LD];
+#pragma unroll
+    for (int u = 0; u < LD; u++)
+      v[u] = ld_stream(a + i + 32u * u);
+#pragma unroll
+    for (int u = 0; u < LD; u++) {
+      const uint32_t j = i + 32u * u;
+      acc[u % kUnroll] = dot_acc(v[u], es[2u * j], es[2u * j + 1u], acc[u % kUnroll]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < LD; u++) {
+    const uint32_t j = i + 32u * u;
+    if (j < nu)
+      acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[2u * j], es[2u * j + 1u], acc[u % kUnroll]);
+  }
+#pragma unroll
+  for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+    for (int u = 0; u < s; u++)
+      acc[u] += acc[u + s];
+  return warp_sum(acc[0]);
+}
+
 // Read-only form: sum over one row segment of A[r][c] * e[c]; e staged in shared memory.
 // Fixed evaluation order (depends on the segment length only): lane l owns vectors
 // l, l+32, ...; vector j of a batch goes to accumulator j; accumulators are folded pairwise,
@@ -501,9 +587,11 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
 // ---------------------------------------------------------------------------------------
 // the round loop
 // ---------------------------------------------------------------------------------------
-template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute>
+template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute, typename T = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundParams p)
 {
+  constexpr bool kBf16 = sizeof(T) == 2; // p.A then points to bf16 storage (read-only form, N % 8 == 0)
+  static_assert(!kBf16 || (VEC == 4 && FORM == kFormReadOnly), "bf16 storage: read-only form, vector loads");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
   extern __shared__ __align__(16) float smem[];
   float* scale_s = smem;               // chunk_cols floats: e (read-only) or s_prev (in-place)
@@ -605,7 +693,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
         const uint32_t rl = backward ? (nrows - 1u - i) : i;
         const size_t off = (size_t)(rb + rl) * N + c0;
         float t;
-        if (FORM == kFormReadOnly) {
+        if (kBf16) {
+          const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
+          t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(scale_s), clen >> 3, lane);
+        } else if (FORM == kFormReadOnly) {
           if (p.keep_rows_pct == 0u)
             t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
           else
@@ -909,6 +1000,36 @@ __global__ void __launch_bounds__(256) hilbert_kernel(float* __restrict__ out, u
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x)
       row[c] = __fdiv_rn(1.f, (float)(base + c));
   }
+}
+
+// fp32 -> bf16, round to nearest even (cvt.rn.bf16.f32), for the bf16-storage solves.
+__device__ __forceinline__ unsigned short
+f32_to_bf16_rn(float x)
+{
+  unsigned short h;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+
+__global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src,
+                                                           unsigned short* __restrict__ dst, size_t n)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0);
+  size_t done = 0;
+  if (vec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = ld_stream(reinterpret_cast<const float4*>(src) + i);
+      uint2 o;
+      o.x = (uint32_t)f32_to_bf16_rn(v.x) | ((uint32_t)f32_to_bf16_rn(v.y) << 16);
+      o.y = (uint32_t)f32_to_bf16_rn(v.z) | ((uint32_t)f32_to_bf16_rn(v.w) << 16);
+      reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+    done = n4 << 2;
+  }
+  for (size_t i = done + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = f32_to_bf16_rn(src[i]);
 }
 
 // Philox-4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): counter (ctr, 0), key = seed.

@@ -84,9 +84,13 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return warp_sum(acc[0]);
 }
 
-template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute>
+template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
+  // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
+  // of one row (16 KB); built without the cross-barrier prefetch
+  constexpr bool kBf16 = sizeof(T) == 2;
+  static_assert(!kBf16 || PF_BATCHES == 0, "bf16 storage: no prefetch slots");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (a multiple of 32, <= MAX_THREADS)
   const uint32_t kWarps = THREADS >> 5;
   constexpr uint32_t kPfFloats = PF_BATCHES * 1024u; // prefetch slot per warp
@@ -218,8 +222,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           } else if (resident && first_unit) {
             npre = seg_nv; // landed before round 0 and never evicted
           }
-          const float t = chunk_dot_prefetched<LD>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec,
-                                                   seg_nv, lane, reinterpret_cast<const float4*>(my_pf), npre);
+          float t;
+          if (kBf16) {
+            // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
+            const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
+                                 ch * (kChunkVec >> 1);
+            t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
+          } else {
+            t = chunk_dot_prefetched<LD>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
+                                         reinterpret_cast<const float4*>(my_pf), npre);
+          }
           if (lane == 0) {
             if (pending)
               finish_row(pend_row, pend_old); // the atomic issued one unit ago has long returned

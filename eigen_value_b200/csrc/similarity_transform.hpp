@@ -47,8 +47,9 @@ public:
   CUstream_st* stream() const { return stream_; }
 
   // Whole round loop on device-resident rows.  shard == nullptr: single GPU (rows == dim).
+  // bf16 == true: d_rows points to bfloat16 storage (read-only form, dim % 8 == 0); fp32 otherwise.
   int solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
-            float* d_eigen_vec, st_result* res);
+            float* d_eigen_vec, st_result* res, bool bf16 = false);
   int solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
                  float* h_eigen_vec, st_result* res);
   const std::vector<uint64_t>& round_timestamps() const { return last_ts_; }
@@ -140,6 +141,8 @@ int generate_hilbert_matrix(st::Context& q, float* d_rows, const uint dim, const
                             const uint rows = 0);
 int generate_uniform_matrix(st::Context& q, float* d_rows, const uint dim, uint64_t seed,
                             const uint row0 = 0, const uint rows = 0);
+// fp32 -> bf16 (round to nearest even) on the device, for the bf16-storage solves
+int convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t count);
 
 namespace st {
 void set_last_error(const std::string& msg);

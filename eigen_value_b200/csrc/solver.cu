@@ -358,6 +358,43 @@ launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t 
   }
 }
 
+// ---- bf16 storage (read-only form, N % 8 == 0): resident-e kernel without prefetch slots for
+// N <= 32768, the general chunked loop above it --------------------------------------------------
+constexpr int kScBf16Id = 11; // {512 threads, no prefetch}: the one resident-e configuration built for bf16
+
+template<int STOP>
+static void
+launch_sc_bf16(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_sc_kernel<512, 0, kUnroll, STOP, bf16_t>;
+  if (smem > 48 * 1024)
+    ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, smem,
+                                      stream));
+}
+
+template<int MAX_THREADS, int STOP>
+static void
+launch_general_bf16_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
+{
+  auto kernel = round_loop_kernel<4, kFormReadOnly, MAX_THREADS, STOP, bf16_t>;
+  if (smem > 48 * 1024)
+    ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, smem,
+                                      stream));
+}
+
+template<int STOP>
+static void
+launch_general_bf16(int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  if (threads <= 512)
+    return launch_general_bf16_one<512, STOP>(p, grid, threads, smem, stream);
+  return launch_general_bf16_one<1024, STOP>(p, grid, threads, smem, stream);
+}
+
 // ---- on-chip variant (N <= 512): matrix resident in the shared memory of one cluster -----------
 constexpr int kClusterKernelId = 20;
 constexpr int kClusterThreads = 512;
@@ -411,10 +448,13 @@ aligned16(const void* p)
 
 int
 Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
-               float* d_eigen_vec, st_result* res)
+               float* d_eigen_vec, st_result* res, bool bf16)
 {
   if (!d_rows || dim == 0 || opt.max_iter == 0 || !(opt.eps >= 0.f))
     throw std::invalid_argument("solve: bad argument");
+  // the round barrier counts arrivals in 32 bits: (max_iter + 1) * grid must not wrap
+  if (opt.max_iter > (1u << 24))
+    throw std::invalid_argument("solve: max_iter above 2^24 is not supported");
   if (shard && (shard->dim != dim || !shard->linked))
     throw std::invalid_argument("solve: shard not linked or dimension mismatch");
   const auto host_t0 = std::chrono::steady_clock::now();
@@ -427,6 +467,15 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   if (opt.stop != ST_STOP_ABSOLUTE && opt.stop != ST_STOP_RELATIVE)
     throw std::invalid_argument("solve: unknown st_options.stop");
   const int stop = opt.stop == ST_STOP_RELATIVE ? kStopRelative : kStopAbsolute;
+  if (bf16) {
+    // d_rows points to bfloat16 storage: 128-bit loads of 8 elements, fp32 everywhere else
+    if (form != kFormReadOnly || dim % 8u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
+      throw std::invalid_argument("solve: bf16 storage needs the read-only form, dim % 8 == 0 and a 16-byte aligned matrix");
+    if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != kScBf16Id)
+      throw std::invalid_argument("solve: bf16 storage is built for kernel 0 (automatic), 1 (general loop) and 11 (resident-e)");
+    if (opt.kernel == kScBf16Id && dim > (uint32_t)kResidentCols)
+      throw std::invalid_argument("solve: resident-e kernel needs dim <= 32768");
+  }
 
   RoundParams p{};
   p.A = d_rows;
@@ -505,7 +554,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const ScConfig* sc = nullptr;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
-  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && dim <= (uint32_t)kClusterCols)) {
+  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !bf16 && dim <= (uint32_t)kClusterCols)) {
     if (!readonly4 || shard || dim > (uint32_t)kClusterCols)
       throw std::invalid_argument("solve: on-chip kernel needs one GPU, the read-only form, dim % 4 == 0, dim <= 512");
     cluster_ctas = cluster_ctas_for(dim, &smem);
@@ -524,12 +573,16 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     int want_pf = 1;
     if (opt.kernel == 0 && dim > 1024u && dim <= 3072u && (uint64_t)rows <= (uint64_t)sm_count_ * 16u)
       want_pf = (int)((dim + 1023u) / 1024u);
+    if (bf16)
+      want_pf = 0; // bf16 storage is built without prefetch slots (configuration 11)
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
       if (opt.kernel == 0 && pinned > c.max_threads)
         continue;
-      if (opt.kernel == 0 && stop == kStopRelative && c.id != 13 && c.id != 10 && c.id != 12)
+      if (bf16 && c.id != kScBf16Id)
+        continue; // bf16 storage is built for configuration 11 only
+      if (opt.kernel == 0 && !bf16 && stop == kStopRelative && c.id != 13 && c.id != 10 && c.id != 12)
         continue; // only the automatic configurations are built with the relative stop test
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
@@ -594,7 +647,19 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
-  if (cluster_ctas) {
+  if (bf16 && sc) {
+    if (sc->id != kScBf16Id)
+      throw std::invalid_argument("solve: bf16 storage needs resident-e configuration 11");
+    if (stop == kStopRelative)
+      launch_sc_bf16<kStopRelative>(p, grid, threads, smem, stream_);
+    else
+      launch_sc_bf16<kStopAbsolute>(p, grid, threads, smem, stream_);
+  } else if (bf16) {
+    if (stop == kStopRelative)
+      launch_general_bf16<kStopRelative>(threads, p, grid, smem, stream_);
+    else
+      launch_general_bf16<kStopAbsolute>(threads, p, grid, smem, stream_);
+  } else if (cluster_ctas) {
     if (stop == kStopRelative)
       launch_cluster<kStopRelative>(p, cluster_ctas, smem, stream_);
     else
@@ -652,7 +717,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->grid = (uint32_t)grid;
     res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : tma ? (uint32_t)tma->id : 1u;
     res->threads = (uint32_t)threads;
-    const uint64_t per_pass = (uint64_t)rows * dim * sizeof(float);
+    const uint64_t per_pass = (uint64_t)rows * dim * (bf16 ? 2u : sizeof(float));
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;
     std::vector<float> dt;
     for (uint32_t k = 0; k < stamped; k++)
@@ -819,6 +884,17 @@ generate_hilbert_matrix(st::Context& q, float* d_rows, const uint dim, const uin
   const uint rows = rows_ ? rows_ : dim - row0;
   const dim3 grid(blocks_for(dim, 256, 32), (unsigned)std::min<uint32_t>(rows, 32768u));
   hilbert_kernel<<<grid, 256, 0, q.stream()>>>(d_rows, dim, row0, rows);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t count)
+{
+  q.activate();
+  const size_t work = (count + 3) / 4;
+  const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)q.sm_count() * 16);
+  convert_bf16_kernel<<<std::max(1, grid), 256, 0, q.stream()>>>(d_src, d_dst, count);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }

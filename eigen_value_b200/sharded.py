@@ -75,7 +75,7 @@ class ShardedSolver:
         return self.solver.uniform(self.dim, seed, self.row0, self.rows)
 
     def solve(self, d_rows: DeviceBuffer, d_eigen_vec: Optional[DeviceBuffer] = None,
-              **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
+              bf16: bool = False, **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
         """Collective: every rank calls it with its own rows.  Every rank gets the full
         eigenvector and identical (lambda, iter_count).  The eigenvector is downloaded only
         when no device output buffer is supplied."""
@@ -83,8 +83,8 @@ class ShardedSolver:
         res = StResult()
         own = d_eigen_vec is None
         vec = self.solver.alloc(4 * self.dim) if own else d_eigen_vec
-        check(self.lib.st_shard_solve(self.shard, d_rows.ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res)),
-              "st_shard_solve")
+        fn = self.lib.st_shard_solve_bf16 if bf16 else self.lib.st_shard_solve   # bf16: rows in bfloat16 storage
+        check(fn(self.shard, d_rows.ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res)), "st_shard_solve")
         out = vec.download(np.float32, self.dim) if own else None
         if own:
             vec.free()

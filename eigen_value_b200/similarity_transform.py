@@ -186,20 +186,28 @@ class Solver:
         check(self.lib.st_generate_uniform(self.ctx, buf.ptr, dim, row0, rows, seed), "st_generate_uniform")
         return buf
 
+    def to_bf16(self, d_src: DeviceBuffer, count: int) -> DeviceBuffer:
+        """fp32 -> bfloat16 (round to nearest even) on the device: storage for solve_device(..., bf16=True)."""
+        out = self.alloc(2 * count)
+        check(self.lib.st_convert_f32_to_bf16(self.ctx, d_src.ptr, out.ptr, count), "st_convert_f32_to_bf16")
+        return out
+
     def synchronize(self) -> None:
         check(self.lib.st_synchronize(self.ctx), "st_synchronize")
 
     # ---- the round loop -------------------------------------------------------------------
     def solve_device(self, d_mat: DeviceBuffer, dim: int, d_eigen_vec: Optional[DeviceBuffer] = None,
-                     **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
+                     bf16: bool = False, **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
         """similarity_transform() on a device-resident matrix.  Returns (info, eigen_vec);
-        eigen_vec is downloaded only when no device output buffer was supplied."""
+        eigen_vec is downloaded only when no device output buffer was supplied.  bf16=True: d_mat
+        holds bfloat16 storage (see to_bf16; opt-in, changes results, dim % 8 == 0)."""
         o = make_options(self.lib, **opts)
         res = StResult()
         own = d_eigen_vec is None
         vec = self.alloc(4 * dim) if own else d_eigen_vec
-        check(self.lib.st_solve_device(self.ctx, d_mat.ptr, dim, ctypes.byref(o), vec.ptr,
-                                       ctypes.byref(res)), "st_solve_device")
+        fn, what = (self.lib.st_solve_device_bf16, "st_solve_device_bf16") if bf16 else \
+                   (self.lib.st_solve_device, "st_solve_device")
+        check(fn(self.ctx, d_mat.ptr, dim, ctypes.byref(o), vec.ptr, ctypes.byref(res)), what)
         out = vec.download(np.float32, dim) if own else None
         if own:
             vec.free()

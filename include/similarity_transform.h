@@ -92,7 +92,7 @@ enum
 typedef struct st_options
 {
   float eps;         /* stop threshold, reference EPS                               */
-  uint32_t max_iter; /* round cap, reference MAX_ITR                                */
+  uint32_t max_iter; /* round cap, reference MAX_ITR; 1 .. 2^24                     */
   int32_t form;      /* ST_FORM_*                                                   */
   int32_t sweep;     /* bit 0: alternate the row order every round so the tail of one pass is
                         the L2-resident head of the next (default on); bit 1 / bit 2: force
@@ -158,6 +158,15 @@ int st_solve_device(void* ctx, const float* d_mat, uint32_t dim, const st_option
 /* Same with host buffers (what max_eigen_value calls with default options). */
 int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt,
                   float* h_eigen_val, float* h_eigen_vec, st_result* res);
+/* bf16 STORAGE of the matrix (opt-in; changes results, so outside reference parity): the matrix is
+ * held as bfloat16 -- half the HBM bytes per round -- while the eigenvector, the row sums and every
+ * accumulation stay fp32.  bf16 -> fp32 is exact, so the result is bit-identical to an fp32 solve of
+ * the bf16-rounded matrix evaluated in 8-element units.  Read-only form only; dim % 8 == 0; kernels 0
+ * (automatic), 1 and 11.  st_convert_f32_to_bf16 rounds to nearest even on the device; `count`
+ * elements, d_dst 2-byte elements. */
+int st_convert_f32_to_bf16(void* ctx, const float* d_src, uint16_t* d_dst, size_t count);
+int st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const st_options* opt,
+                         float* d_eigen_vec, st_result* res);
 /* Per-round device timestamps (ns, globaltimer) of the last solve on this context. */
 int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
 /* Three stamps per round of the last solve, taken by CTA 0: matrix pass done, round barrier
@@ -205,6 +214,9 @@ int st_shard_link_local(void** shards, uint32_t world);
 int st_shard_rows(void* shard, uint32_t* row0, uint32_t* rows);
 int st_shard_solve(void* shard, const float* d_rows, const st_options* opt, float* d_eigen_vec,
                    st_result* res);
+/* st_shard_solve on bf16 storage of this rank's rows (see st_solve_device_bf16). */
+int st_shard_solve_bf16(void* shard, const uint16_t* d_rows, const st_options* opt, float* d_eigen_vec,
+                        st_result* res);
 void st_shard_destroy(void* shard);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@ MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
 FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
 SUM_CUDA = 4   # the CUDA kernels' evaluation order: bit-identical to the GPU (tests/test_zz_gpu_bitexact.py)
+SUM_CUDA_BF16 = 5   # the same with 8-element units: the kernels' order on bf16 storage (feed to_bf16(mat)[0])
 STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # the reference's stop test | extension: threshold eps * max(s)
 
 
@@ -102,6 +103,17 @@ def uniform(dim: int, seed: int, row0: int = 0, rows: int | None = None) -> np.n
     out = np.empty((rows, dim), dtype=np.float32)
     lib().oracle_generate_uniform(out, dim, row0, rows, seed)
     return out
+
+
+def to_bf16(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """fp32 -> bfloat16, round to nearest even (what cvt.rn.bf16.f32 / st_convert_f32_to_bf16 does for
+    finite inputs).  Returns (the rounded values widened back to fp32 -- exact --, the uint16 bit patterns)."""
+    a = np.ascontiguousarray(mat, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    rounded = (u + 0x7FFF + ((u >> 16) & 1)) >> 16            # ties to even on the kept bit
+    bits = rounded.astype(np.uint16)
+    back = (bits.astype(np.uint32) << 16).view(np.float32)
+    return back.reshape(a.shape), bits.reshape(a.shape)
 
 
 def philox_block(ctr: int, key: int) -> np.ndarray:

@@ -60,9 +60,13 @@ enum
                                 cell in work-group order (:139-146).  This is the order the
                                 reference executes on oracle/sycl_shim, so the oracle can be
                                 compared with the real sources bit for bit. */
-  ORACLE_SUM_CUDA = 4        /* the evaluation order of the CUDA round kernels (lane / accumulator /
+  ORACLE_SUM_CUDA = 4,       /* the evaluation order of the CUDA round kernels (lane / accumulator /
                                 fold / shuffle tree, FMA): with ORACLE_FORM_READONLY the oracle
                                 then matches the GPU bit for bit (row_dot_cuda_order below) */
+  ORACLE_SUM_CUDA_BF16 = 5   /* the same order with 8-element units: what the CUDA kernels do on
+                                bf16 STORAGE of the matrix (one 128-bit load = 8 elements).  Feed
+                                the oracle the bf16-rounded matrix (as fp32): bf16 -> fp32 is
+                                exact, so the bits must match the GPU's bf16-storage solve */
 };
 
 int
@@ -119,9 +123,10 @@ reduce16(const float* acc)
  * scale == NULL behaves like a vector of ones (fmaf(a, 1, acc) == a + acc exactly). */
 #define ORACLE_CUDA_CHUNK 8192
 static float
-row_dot_cuda_order(const float* row, const float* scale, size_t n)
+row_dot_cuda_order(const float* row, const float* scale, size_t n, size_t unit)
 {
-  const size_t vec = (n % 4 == 0) ? 4 : 1;
+  /* unit == 0: fp32 storage (float4 when n % 4 == 0, else scalar); unit == 8: bf16 storage */
+  const size_t vec = unit ? unit : ((n % 4 == 0) ? 4 : 1);
   float total = 0.f;
   for (size_t c0 = 0; c0 < n; c0 += ORACLE_CUDA_CHUNK) {
     const size_t clen = n - c0 < ORACLE_CUDA_CHUNK ? n - c0 : ORACLE_CUDA_CHUNK;
@@ -171,7 +176,9 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
     return acc;
   }
   if (sum_mode == ORACLE_SUM_CUDA)
-    return row_dot_cuda_order(row, scale, n);
+    return row_dot_cuda_order(row, scale, n, 0);
+  if (sum_mode == ORACLE_SUM_CUDA_BF16)
+    return row_dot_cuda_order(row, scale, n, 8); /* n % 8 == 0 required, like the kernels */
   if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {
     const size_t wg = (size_t)(sum_mode >> 8);
     float cell = 0.f; /* the zero-filled global cell (:85-93) */

@@ -42,12 +42,13 @@ def fma32(a, b, c):
     return bits.view(np.float64).astype(np.float32)
 
 
-def row_dot_cuda_order_numpy(row, scale):
+def row_dot_cuda_order_numpy(row, scale, unit=0):
     """One row in the kernels' order: 8192-column chunks added left to right; inside a chunk unit j
-    (a float4 when n % 4 == 0, else one float) belongs to lane j % 32, accumulator (j / 32) % 8,
-    folded with sequential FMAs; accumulators folded pairwise (4, 2, 1); lanes by an xor tree."""
+    (a float4 when n % 4 == 0, else one float; 8 elements on bf16 storage, unit=8) belongs to lane
+    j % 32, accumulator (j / 32) % 8, folded with sequential FMAs; accumulators folded pairwise
+    (4, 2, 1); lanes by an xor tree."""
     n = row.shape[0]
-    vec = 4 if n % 4 == 0 else 1
+    vec = unit if unit else (4 if n % 4 == 0 else 1)
     total = None
     for c0 in range(0, n, 8192):
         clen = min(8192, n - c0)
@@ -171,3 +172,45 @@ def test_cuda_order_is_shard_neutral():
     for ranks in (2, 3, 8):
         got = oracle.similarity_transform(H, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA, ranks=ranks)
         assert got[3] == base[3] and got[0] == base[0] and np.array_equal(got[1], base[1])
+
+
+# ---- bf16 STORAGE of the matrix (opt-in extension) -----------------------------
+@pytest.mark.parametrize("dim", [8, 64, 264, 1000, 8192, 8200, 16392])
+def test_bf16_storage_order_matches_the_numpy_restatement(dim):
+    rng = np.random.default_rng(dim)
+    rows = min(3, dim)
+    mat = np.zeros((dim, dim), dtype=np.float32)
+    mat[:rows] = oracle.to_bf16((rng.random((rows, dim)) + 0.25).astype(np.float32))[0]
+    got = oracle.sum_across_rows(mat, oracle.SUM_CUDA_BF16)[:rows]
+    ones = np.ones(dim, dtype=np.float32)
+    want = np.array([row_dot_cuda_order_numpy(mat[r], ones, unit=8) for r in range(rows)], dtype=np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_to_bf16_rounds_to_nearest_even_like_the_hardware_conversion():
+    import torch
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(100000).astype(np.float32), (rng.random(100000) * 1e6).astype(np.float32),
+                        np.array([1.0, 1.00390625, 1.005859375, 1.001953125, 3.4e38, 1e-38, 0.0], dtype=np.float32)])
+    # exact ties: 1 + 2^-8 sits half way between 1 and 1 + 2^-7 -> even (1.0); 1 + 3*2^-8 -> 1 + 2^-6
+    back, bits = oracle.to_bf16(x)
+    t = torch.from_numpy(x).to(torch.bfloat16)          # torch's CPU conversion is round-to-nearest-even
+    assert np.array_equal(t.view(torch.int16).numpy().view(np.uint16), bits)
+    assert np.array_equal(t.to(torch.float32).numpy(), back)
+    assert oracle.to_bf16(np.array([1.00390625], np.float32))[0][0] == 1.0
+    assert oracle.to_bf16(np.array([1.01171875], np.float32))[0][0] == 1.015625
+    assert np.max(np.abs(back[:200000] - x[:200000]) / x[:200000]) <= 2.0 ** -8
+
+
+def test_bf16_storage_solve_is_an_fp32_solve_of_the_rounded_matrix():
+    H = oracle.hilbert(1024)
+    Hb, _ = oracle.to_bf16(H)
+    full = oracle.similarity_transform(H, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    low = oracle.similarity_transform(Hb, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_BF16)
+    same_matrix_fp32_order = oracle.similarity_transform(Hb, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    # the storage format moves lambda by the rounding of the entries (<= 2^-9 relative each) ...
+    assert 1e-5 < abs(float(low[0]) - float(full[0])) / float(full[0]) < 2.0 ** -9
+    # ... while the 8-element order alone is within the usual summation-order tolerance
+    assert low[3] == same_matrix_fp32_order[3]
+    assert abs(float(low[0]) - float(same_matrix_fp32_order[0])) <= 1e-5 * float(low[0])
+    assert np.max(np.abs(low[1] / low[1].max() - same_matrix_fp32_order[1] / same_matrix_fp32_order[1].max())) <= 1e-4

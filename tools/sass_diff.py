@@ -11,8 +11,9 @@ mangled names to new ones when a trailing template argument was added to the rou
 `Li0E` for `int STOP = 0`), so that `round_loop_kernel<4,0,512>` is compared with
 `round_loop_kernel<4,0,512,0>`.  Exit code 1 if any kernel of the first build is missing or differs.
 
-Used in round 1 when the stop-test template parameter was added without GPU time left to re-measure:
-all 41 kernels of the measured build are instruction-identical in the new one.
+Used in round 1 when the stop-test and storage-type template parameters were added without GPU time
+left to re-measure (`--append-arg Li0E,Li0Ef`): every round-loop kernel of the measured build is
+instruction-identical in the new one; only the standalone find_max / stop kernels changed, on purpose.
 """
 import argparse
 import re
@@ -39,14 +40,16 @@ def main():
     ap.add_argument("before")
     ap.add_argument("after")
     ap.add_argument("--append-arg", default=None,
-                    help="mangled template argument appended to kernels taking RoundParams, e.g. Li0E")
+                    help="mangled template argument(s) appended to kernels taking RoundParams, e.g. Li0E; "
+                         "several alternatives separated by commas (Li0E,Li0Ef)")
     args = ap.parse_args()
     b, a = split(args.before), split(args.after)
     bad = 0
     for name, body in b.items():
         cands = [name]
         if args.append_arg and "RoundParams" in name:
-            cands.append(name.replace("EEvNS_11RoundParamsE", args.append_arg + "EEvNS_11RoundParamsE"))
+            for extra in args.append_arg.split(","):
+                cands.append(name.replace("EEvNS_11RoundParamsE", extra + "EEvNS_11RoundParamsE"))
         found = next((c for c in cands if c in a), None)
         if found is None:
             print("MISSING in second build:", name)
