@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--stop", default="absolute", choices=["absolute", "relative"],
                     help="absolute = the reference's stop test (default; the only one the headline is quoted on); "
                          "relative = extension, max adjacent diff < eps * max(s)")
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
+                    help="f32 = the reference's matrix format (default, the headline); bf16 = opt-in bfloat16 storage "
+                         "of the matrix with fp32 accumulation (changes results; bytes counted at 2 per element)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 LDG; 2-9 TMA ring; 10-19 single-chunk variants")
     ap.add_argument("--sweep", type=int, default=None)
     ap.add_argument("--threads", type=int, default=0)
@@ -291,16 +294,25 @@ def main():
     d_rows = solver.hilbert(dim, row0, rows) if kind == "hilbert" else solver.uniform(dim, seed, row0, rows)
     d_vec = solver.alloc(4 * dim)
     solver.synchronize()
+    bf16 = args.storage == "bf16"
+    elem_bytes = 2 if bf16 else 4
+    if bf16:
+        # opt-in storage format: convert this rank's rows on the device, keep only the 2-byte copy
+        d16 = solver.to_bf16(d_rows, rows * dim)
+        solver.synchronize()
+        d_rows.free()
+        d_rows = d16
+        args.no_e2e = True          # the e2e leg is defined on the reference's fp32 host matrix
 
     def step():
         if sh is None:
-            info, _ = solver.solve_device(d_rows, dim, d_eigen_vec=d_vec, **opts)
+            info, _ = solver.solve_device(d_rows, dim, d_eigen_vec=d_vec, bf16=bf16, **opts)
         else:
-            info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, **opts)
+            info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, bf16=bf16, **opts)
         return info
 
     # L2 hygiene: the shard is larger than L2 for the default workloads; smaller ones get a flush
-    shard_bytes = 4 * rows * dim
+    shard_bytes = elem_bytes * rows * dim
     need_flush = shard_bytes <= 2 * solver.l2_bytes
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
 
@@ -348,7 +360,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
     dev_ms, wall_ms = float(t[0]), float(t[1])
-    total_bytes = passes * 4.0 * dim * dim              # whole job: every rank's rows
+    total_bytes = passes * float(elem_bytes) * dim * dim   # whole job: every rank's rows
     value = total_bytes / (dev_ms * 1e-3) / 1e9
     last = infos[-1]
     round_us = statistics.median(i.round_us_median for i in infos)
@@ -432,13 +444,14 @@ def main():
         peak, peak_src = measured_peak()
         agg_peak = peak * world
         line = {
-            "metric": "per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside",
+            "metric": ("per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside" if not bf16 else
+                       "per-round algorithmic HBM GB/s on bf16 storage (passes * 2*N^2 B / loop time); ms_to_converge alongside"),
             "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 5),
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "N": dim, "rows_per_gpu": rows, "form": "read-only" if args.form == 0 else "in-place",
-                       "eps": args.eps, "stop": args.stop, "max_iter": args.max_iter,
+                       "eps": args.eps, "stop": args.stop, "max_iter": args.max_iter, "storage": args.storage,
                        "sweep": 1 if args.sweep is None else args.sweep, "kernel": args.kernel,
                        "grid": last.grid,
                        "sharding": f"row-block x{world}, fused peer-store exchange" if world > 1 else "none",
@@ -452,11 +465,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
                          "frac": round(value / agg_peak, 4),
                          # the ncu captures are single-GPU launches; no capture exists for a shard
-                         "traffic": recorded_traffic(workload) if world == 1 else None,
+                         "traffic": recorded_traffic(workload) if world == 1 and not bf16 else None,
                          "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                          "kernel": f"{last.kernel_name} id {last.kernel_id}, {last.threads} threads x {last.grid} CTAs "
                                    "(one launch = one whole solve)",
-                         "bytes_per_launch": int(last.passes * 4 * dim * dim)},
+                         "bytes_per_launch": int(last.passes * elem_bytes * dim * dim)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
         if table is not None:
