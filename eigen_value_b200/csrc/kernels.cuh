@@ -24,6 +24,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Every line of inline PTX sits behind this one header, so that the kernel LOGIC in this directory
+// can also be compiled for the host by the CPU emulation harness (tests/cuda_emu), which supplies
+// its own implementation of the same functions through ST_PTX_HEADER.
+#ifdef ST_PTX_HEADER
+#include ST_PTX_HEADER
+#else
+#include "ptx.cuh"
+#endif
+
 namespace st {
 
 constexpr int kMaxWorld = 8;      // ST_MAX_WORLD
@@ -107,17 +116,10 @@ struct RoundParams
 };
 
 // ---------------------------------------------------------------------------------------
-// small PTX helpers
+// per-round instrumentation (the PTX helpers live in ptx.cuh)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long
-globaltimer_ns()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
-// per-round instrumentation, written by one thread of CTA 0
+// written by one thread of CTA 0
 __device__ __forceinline__ void
 stamp_phase(const RoundParams& p, uint32_t k, uint32_t which)
 {
@@ -134,99 +136,13 @@ stamp_round_end(const RoundParams& p, uint32_t k)
   }
 }
 
-__device__ __forceinline__ unsigned int
-ld_acquire_gpu(const unsigned int* p)
-{
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
-__device__ __forceinline__ void
-st_release_gpu(unsigned int* p, unsigned int v)
-{
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
-__device__ __forceinline__ unsigned long long
-ld_acquire_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
-__device__ __forceinline__ void
-st_release_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
-__device__ __forceinline__ unsigned long long
-ld_relaxed_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
-__device__ __forceinline__ void
-st_relaxed_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
-// Streaming 128-bit load of matrix data that is never written while the kernel runs:
-// read-only path, no L1 allocation (each byte is used exactly once per round).
-__device__ __forceinline__ float4
-ld_stream(const float4* p)
-{
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float
-ld_stream(const float* p)
-{
-  float v;
-  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
 
-// Same loads with an L2 eviction-priority policy (createpolicy): rows the kernel wants to
-// find in L2 again next round are loaded evict_last, the rest evict_first.
-__device__ __forceinline__ float4
-ld_stream(const float4* p, unsigned long long pol)
-{
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float
-ld_stream(const float* p, unsigned long long pol)
-{
-  float v;
-  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ unsigned long long
-l2_policy_evict_last()
-{
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ unsigned long long
-l2_policy_evict_first()
-{
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 
 // L2-coherent loads/stores for data other CTAs (or other GPUs) write during the kernel.
 __device__ __forceinline__ float
@@ -292,15 +208,6 @@ struct bf16_t
   unsigned short bits;
 };
 
-__device__ __forceinline__ uint4
-ld_stream(const uint4* p)
-{
-  uint4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-      : "l"(p));
-  return v;
-}
 
 // little-endian: the element at the lower address is the low half of the 32-bit word
 __device__ __forceinline__ float
@@ -496,11 +403,6 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
 //             waits for theirs, then releases the local CTAs through the generation word.
 // All waits are bounded by timeout_ns (checked every 1024 polls) so that a missing rank turns
 // into an error code instead of a hung GPU.  Returns false on timeout.
-__device__ __forceinline__ void
-red_release_gpu_add(unsigned int* p, unsigned int v)
-{
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 struct SpinClock
 {
@@ -1002,14 +904,6 @@ __global__ void __launch_bounds__(256) hilbert_kernel(float* __restrict__ out, u
   }
 }
 
-// fp32 -> bf16, round to nearest even (cvt.rn.bf16.f32), for the bf16-storage solves.
-__device__ __forceinline__ unsigned short
-f32_to_bf16_rn(float x)
-{
-  unsigned short h;
-  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
-  return h;
-}
 
 __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src,
                                                            unsigned short* __restrict__ dst, size_t n)

@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     mbar_init(my_bar, 1u);
   for (uint32_t c = tid; c < N; c += THREADS)
     e_s[c] = 1.f; // initialise_eigen_vector, reference :267-284
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_mbarrier_init();
+  fence_proxy_async();
   __syncthreads();
 
   if (blockIdx.x == 0 && tid == 0)
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         const uint32_t ch = u - rl * nch;
         const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
         const uint32_t bytes = min(kPfFloats >> 2, seg_nv) * 16u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_proxy_async();
         mbar_arrive_expect_tx(my_bar, bytes);
         bulk_load(my_pf, p.A + (size_t)rl * N + (size_t)ch * kChunkCols, bytes, my_bar);
       }

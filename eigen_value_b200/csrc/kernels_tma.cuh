@@ -22,37 +22,9 @@
 
 namespace st {
 
-__device__ __forceinline__ uint32_t
-smem_u32(const void* p)
-{
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
 
-__device__ __forceinline__ void
-mbar_init(uint64_t* bar, uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
 
-__device__ __forceinline__ void
-mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
 
-__device__ __forceinline__ bool
-mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-               "selp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok)
-               : "r"(smem_u32(bar)), "r"(parity)
-               : "memory");
-  return ok != 0;
-}
 
 // Bounded wait: a wrong byte count would otherwise hang the GPU.
 __device__ __forceinline__ bool
@@ -69,24 +41,7 @@ mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns)
   return true;
 }
 
-__device__ __forceinline__ void
-bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                 smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
-__device__ __forceinline__ void
-bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar,
-               unsigned long long pol)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-               "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-               : "memory");
-}
 
 // Position of one warp in its tile sequence: round k, column chunk c0, ordinal ii of the row
 // among the warp's rows, column offset t0 inside the chunk.
@@ -132,8 +87,8 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
   if (lane == 0)
     for (int s = 0; s < STAGES; s++)
       mbar_init(my_bar + s, 1u);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_mbarrier_init();
+  fence_proxy_async();
   __syncthreads();
 
   if (blockIdx.x == 0 && tid == 0)
@@ -155,7 +110,7 @@ __global__ void __launch_bounds__(THREADS, 1) round_loop_tma_kernel(const RoundP
     const float* src = p.A + (size_t)(rb + rl) * N + pc.c0 + pc.t0;
     const uint32_t stage = issued % STAGES;
     float* dst = my_ring + (size_t)stage * TILE_F;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_proxy_async();
     mbar_arrive_expect_tx(my_bar + stage, len * 4u);
     if (p.keep_rows_pct == 0u)
       bulk_load(dst, src, len * 4u, my_bar + stage);
