@@ -17,8 +17,12 @@
 #include "kernels_tma.cuh"
 #include "kernels_sc.cuh"
 #include "kernels_cluster.cuh"
+#include "launch_plan.hpp"
 
 namespace st {
+
+static_assert(kPlanClusterMaxCtas == kClusterMaxCtas && kPlanClusterSmemBudget == kClusterSmemBudget,
+              "launch_plan.hpp must agree with kernels_cluster.cuh");
 
 // ---- error plumbing -----------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -226,48 +230,7 @@ launch_by_stop(int stop, int threads, const RoundParams& p, int grid, size_t sme
   return launch_by_threads<VEC, FORM, kStopAbsolute>(threads, p, grid, smem, stream);
 }
 
-// Warp count for a CTA that owns `nrows` rows, one warp per row at a time: the count in
-// [lo, hi] that leaves the fewest warps idle in the last sweep (e.g. 55 rows: 14 warps x 4
-// sweeps = 56 slots instead of 16 x 4 = 64); ties go to the larger count.
-static int
-balanced_warps(uint32_t nrows, int lo, int hi)
-{
-  int best = hi;
-  double best_eff = -1.0;
-  for (int w = hi; w >= lo; w--) {
-    const uint32_t sweeps = (nrows + (uint32_t)w - 1u) / (uint32_t)w;
-    const double eff = (double)nrows / ((double)sweeps * w);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = w;
-    }
-  }
-  return best;
-}
-
 // ---- TMA-streamed variant ---------------------------------------------------------------------
-struct TmaConfig
-{
-  int id, threads, stages, tile_f;
-};
-// id 2 is the default; the others are tuning variants reachable through st_options.kernel
-static const TmaConfig kTmaConfigs[] = {
-  { 2, 512, 3, 1024 }, { 3, 256, 6, 1024 }, { 4, 256, 3, 2048 }, { 5, 512, 2, 1024 },
-  { 6, 256, 4, 1024 }, { 7, 1024, 1, 1024 }, { 8, 512, 1, 2048 }, { 9, 256, 2, 2048 },
-};
-constexpr size_t kSmemLimit = 227 * 1024 - 1024; // opt-in maximum minus the kernel's static shared
-
-static size_t
-tma_smem_bytes(const TmaConfig& c, uint32_t chunk_cols, uint32_t rows_cap, uint32_t* mbar_offset)
-{
-  size_t off = (size_t)(c.threads / 32) * c.stages * c.tile_f * sizeof(float);
-  off += (size_t)chunk_cols * sizeof(float);
-  off += (size_t)rows_cap * sizeof(float);
-  off = (off + 15) & ~(size_t)15;
-  *mbar_offset = (uint32_t)off;
-  return off + (size_t)(c.threads / 32) * c.stages * sizeof(uint64_t);
-}
-
 template<int THREADS, int STAGES, int TILE_F>
 static void
 launch_tma_one(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
@@ -296,29 +259,6 @@ launch_tma(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t str
 }
 
 // ---- resident-e variant (N <= 32768): e in smem, fused tail, cross-barrier prefetch ----------
-struct ScConfig
-{
-  int id, max_threads, pf_batches;
-};
-// the automatic choice takes the first entry that fits (one 4 KB batch prefetched per warp --
-// measured best or tied at N = 1024..8192, profiles/r1_sweep_kernels_sc*.txt); the others are
-// tuning variants reachable through st_options.kernel
-static const ScConfig kScConfigs[] = {
-  { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 }, { 14, 1024, 1 }, { 15, 1024, 0 },
-  { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
-};
-
-static size_t
-sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t rows_cap, uint32_t* mbar_offset)
-{
-  size_t off = (size_t)(threads / 32) * pf_batches * 1024 * sizeof(float);
-  off += (size_t)cols * sizeof(float);
-  off += (size_t)rows_cap * sizeof(float);
-  off = (off + 15) & ~(size_t)15;
-  *mbar_offset = (uint32_t)off;
-  return off + (size_t)(threads / 32) * sizeof(uint64_t);
-}
-
 template<int MAX_THREADS, int PF, int LD = kUnroll, int STOP = kStopAbsolute>
 static void
 launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
@@ -398,26 +338,6 @@ launch_general_bf16(int threads, const RoundParams& p, int grid, size_t smem, cu
 // ---- on-chip variant (N <= 512): matrix resident in the shared memory of one cluster -----------
 constexpr int kClusterKernelId = 20;
 constexpr int kClusterThreads = 512;
-
-// Cluster size (1, 2, 4, 8 CTAs): the largest that still leaves every CTA >= 16 rows (one per
-// warp) -- the loop is latency-bound, so more SMs means shorter per-warp row chains -- and never
-// smaller than what it takes to hold rows + e + both s buffers in each CTA's shared memory.
-static int
-cluster_ctas_for(uint32_t dim, size_t* smem_bytes)
-{
-  int best = 0;
-  for (int c = 1; c <= kClusterMaxCtas; c *= 2) {
-    const size_t rows_cap = (dim + (uint32_t)c - 1u) / (uint32_t)c;
-    const size_t need = sizeof(float) * (rows_cap * dim + 3 * (size_t)dim);
-    const bool fits = need <= kClusterSmemBudget;
-    const bool useful = c == 1 || dim / (uint32_t)c >= 16u;
-    if (fits && (useful || !best)) {
-      best = c;
-      *smem_bytes = need;
-    }
-  }
-  return best;
-}
 
 template<int STOP>
 static void

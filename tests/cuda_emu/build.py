@@ -1,0 +1,67 @@
+"""Builds the CPU emulation harness: the round kernels of eigen_value_b200/csrc compiled for the
+host against tests/cuda_emu/cuda_emu.h (TEST INFRASTRUCTURE; see that header).
+
+The kernel sources are used as they are, with one mechanical rewrite: CUDA's
+`extern __shared__ T name[];` (dynamic shared memory) has no C++ spelling, so each such line becomes
+`T* name = reinterpret_cast<T*>(emu::dynamic_smem());` in a scratch copy under _build/.
+"""
+from __future__ import annotations
+
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "eigen_value_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+SO = os.path.join(HERE, "libcuda_emu.so")
+KERNEL_SOURCES = ["kernels.cuh", "kernels_sc.cuh", "kernels_tma.cuh", "kernels_cluster.cuh", "launch_plan.hpp"]
+OWN_SOURCES = ["cuda_emu.h", "ptx_emu.h", "emu_driver.cpp", os.path.join("fake_include", "cuda_runtime.h"),
+               os.path.join("fake_include", "cooperative_groups.h")]
+
+DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
+
+
+def rewrite(text: str) -> str:
+    return DYN_SMEM.sub(lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(emu::dynamic_smem());", text)
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in KERNEL_SOURCES] + [os.path.join(HERE, f) for f in OWN_SOURCES] + [__file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False) -> str:
+    if not force and not stale():
+        return SO
+    os.makedirs(BUILD, exist_ok=True)
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(CSRC, f)) as src:
+            text = src.read()
+        new = rewrite(text)
+        if "extern __shared__" in new:
+            raise RuntimeError(f"{f}: an `extern __shared__` declaration was not rewritten")
+        with open(os.path.join(BUILD, f), "w") as dst:
+            dst.write(new)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [cxx, "-std=c++17", "-O2", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+           "-pthread", "-Wall", "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-unknown-pragmas",
+           "-Wno-unused-function", "-Wno-sign-compare",
+           '-DST_PTX_HEADER="ptx_emu.h"',
+           "-I", os.path.join(HERE, "fake_include"), "-I", BUILD, "-I", HERE,
+           "-o", SO, os.path.join(HERE, "emu_driver.cpp")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout[-6000:])
+        raise RuntimeError("building the CUDA emulation harness failed")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True))

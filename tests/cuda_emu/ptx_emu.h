@@ -1,0 +1,124 @@
+// ptx_emu.h -- host implementation of eigen_value_b200/csrc/ptx.cuh for the CPU emulation harness
+// (TEST INFRASTRUCTURE; selected through -DST_PTX_HEADER).  Same names and signatures; scoped
+// loads/stores become GCC atomics, bulk copies complete at issue, an mbarrier is a counter of
+// completed phases.
+#pragma once
+
+#include "cuda_emu.h"
+
+namespace st {
+
+inline unsigned long long
+globaltimer_ns()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+
+// polling loads give the other OS threads (CTAs, emulated GPUs) a chance to run
+inline unsigned int
+ld_acquire_gpu(const unsigned int* p)
+{
+  sched_yield();
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+inline void
+st_release_gpu(unsigned int* p, unsigned int v)
+{
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+inline unsigned long long
+ld_acquire_sys(const unsigned long long* p)
+{
+  sched_yield();
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+inline void
+st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+inline unsigned long long
+ld_relaxed_sys(const unsigned long long* p)
+{
+  sched_yield();
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
+inline void
+st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+}
+inline void
+red_release_gpu_add(unsigned int* p, unsigned int v)
+{
+  __atomic_fetch_add(p, v, __ATOMIC_RELEASE);
+}
+
+inline float4 ld_stream(const float4* p) { return *p; }
+inline float ld_stream(const float* p) { return *p; }
+inline float4 ld_stream(const float4* p, unsigned long long) { return *p; }
+inline float ld_stream(const float* p, unsigned long long) { return *p; }
+inline uint4 ld_stream(const uint4* p) { return *p; }
+inline unsigned long long l2_policy_evict_last() { return 0ull; }
+inline unsigned long long l2_policy_evict_first() { return 0ull; }
+
+// cvt.rn.bf16.f32: round to nearest even; NaN -> canonical 0x7fff
+inline unsigned short
+f32_to_bf16_rn(float x)
+{
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u)
+    return 0x7fffu;
+  return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+inline uint32_t
+smem_u32(const void* p)
+{
+  return (uint32_t)reinterpret_cast<uintptr_t>(p);
+}
+// an mbarrier is the number of phases completed so far
+inline void
+mbar_init(uint64_t* bar, uint32_t)
+{
+  *bar = 0;
+}
+inline void
+mbar_arrive_expect_tx(uint64_t*, uint32_t)
+{
+}
+inline bool
+mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+  return ((uint32_t)(*bar) & 1u) != parity; // the phase of that parity has completed
+}
+inline void
+bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+  if (bytes % 16u != 0u || (reinterpret_cast<uintptr_t>(dst_smem) & 15u) || (reinterpret_cast<uintptr_t>(src_gmem) & 15u)) {
+    fprintf(stderr, "cuda_emu: bulk copy with misaligned address or size (%u bytes)\n", bytes);
+    abort(); // the hardware would fault
+  }
+  memcpy(dst_smem, src_gmem, bytes);
+  *bar += 1;
+}
+inline void
+bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar, unsigned long long)
+{
+  bulk_load(dst_smem, src_gmem, bytes, bar);
+}
+inline void
+fence_mbarrier_init()
+{
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+inline void
+fence_proxy_async()
+{
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+
+} // namespace st
