@@ -63,5 +63,51 @@ def build(force: bool = False) -> str:
     return SO
 
 
+TSAN_EXE = os.path.join(HERE, "emu_tsan.bin")
+
+
+def _compile_tsan(include_dir: str, exe: str) -> str:
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-pthread",
+           "-fsanitize=thread", "-fno-omit-frame-pointer", "-w",
+           '-DST_PTX_HEADER="ptx_emu.h"',
+           "-I", os.path.join(HERE, "fake_include"), "-I", include_dir, "-I", HERE,
+           "-o", exe, os.path.join(HERE, "emu_driver.cpp"), os.path.join(HERE, "tsan_main.cpp")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout[-6000:])
+        raise RuntimeError("building the ThreadSanitizer runner failed")
+    return exe
+
+
+def build_tsan(force: bool = False) -> str:
+    """The same sources as an executable under ThreadSanitizer (cuda_emu.h, TSan mode): a CPU racecheck."""
+    build(force=False)                       # refreshes the rewritten kernel copies when needed
+    if not force and os.path.exists(TSAN_EXE) and os.path.getmtime(TSAN_EXE) >= max(
+            os.path.getmtime(SO), os.path.getmtime(os.path.join(HERE, "tsan_main.cpp"))):
+        return TSAN_EXE
+    return _compile_tsan(BUILD, TSAN_EXE)
+
+
+def build_tsan_mutant(tag: str, filename: str, old: str, new: str) -> str:
+    """A TSan runner whose copy of `filename` has `old` replaced by `new` (exactly one occurrence): used
+    to show that the racecheck notices when a synchronisation the kernels rely on is taken away."""
+    build(force=False)
+    mdir = os.path.join(BUILD, "mutant_" + tag)
+    os.makedirs(mdir, exist_ok=True)
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(BUILD, f)) as src:
+            text = src.read()
+        if f == filename:
+            if text.count(old) != 1:
+                raise RuntimeError(f"mutation {tag}: expected exactly one occurrence in {filename}, found {text.count(old)}")
+            text = text.replace(old, new)
+        with open(os.path.join(mdir, f), "w") as dst:
+            dst.write(text)
+    return _compile_tsan(mdir, os.path.join(mdir, "emu_tsan_mutant.bin"))
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    if "--tsan" in sys.argv:
+        print(build_tsan(force=True))

@@ -34,6 +34,33 @@
 #include <thread>
 #include <vector>
 
+// ---- ThreadSanitizer mode (tests/cuda_emu/build.py --tsan): a CPU "racecheck" ---------------------------
+// Every fiber is announced to TSan as a thread of its own and fiber switches do NOT synchronise, so two
+// CUDA threads touching the same shared or global address are a reported race unless the kernel ordered
+// them through __syncthreads / __syncwarp / a shuffle / an mbarrier (annotated below as release +
+// acquire) or through the atomics of the grid barrier.  __ldcg / __stcg become plain accesses so that the
+// row-sum exchange itself is checked.  TSan does not model stand-alone fences, so in this mode relaxed
+// atomics are strengthened to acq_rel: what is verified is that a synchronisation chain EXISTS between
+// conflicting accesses (barrier placement, double buffering, slot reuse), not the choice of fence.
+#if defined(__SANITIZE_THREAD__)
+#include <sanitizer/tsan_interface.h>
+#define EMU_TSAN 1
+#define EMU_NO_TSAN __attribute__((no_sanitize("thread")))
+#define EMU_RELEASE(addr) __tsan_release((void*)(addr))
+#define EMU_ACQUIRE(addr) __tsan_acquire((void*)(addr))
+#define EMU_RELAXED __ATOMIC_ACQ_REL
+#define EMU_RELAXED_LOAD __ATOMIC_ACQUIRE
+#define EMU_RELAXED_STORE __ATOMIC_RELEASE
+#else
+#define EMU_TSAN 0
+#define EMU_NO_TSAN
+#define EMU_RELEASE(addr) ((void)0)
+#define EMU_ACQUIRE(addr) ((void)0)
+#define EMU_RELAXED __ATOMIC_RELAXED
+#define EMU_RELAXED_LOAD __ATOMIC_RELAXED
+#define EMU_RELAXED_STORE __ATOMIC_RELAXED
+#endif
+
 // ---- language keywords ---------------------------------------------------------------------------
 #define __global__
 #define __device__
@@ -89,6 +116,8 @@ struct Cta
   int sync_and = 1, sync_and_result = 1;
   std::vector<WarpState> warps;
   std::function<void()> body;
+  std::vector<void*> tsan_fiber; // TSan mode: one announced fiber per CUDA thread
+  void* tsan_sched = nullptr;
 };
 
 struct Grid
@@ -104,11 +133,19 @@ struct Grid
 
 inline thread_local Cta* g_cta = nullptr;
 
-inline void
+EMU_NO_TSAN inline void
+to_scheduler(Cta* c)
+{
+#if EMU_TSAN
+  __tsan_switch_to_fiber(c->tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
+  swapcontext(&c->ctx[c->current], &c->sched);
+}
+
+EMU_NO_TSAN inline void
 yield()
 {
-  Cta* c = g_cta;
-  swapcontext(&c->ctx[c->current], &c->sched);
+  to_scheduler(g_cta);
 }
 
 inline unsigned char*
@@ -117,17 +154,25 @@ dynamic_smem()
   return g_cta->smem;
 }
 
+EMU_NO_TSAN inline void
+fiber_exit(Cta* c)
+{
+  c->done[c->current] = 1;
+  c->live--;
+  EMU_RELEASE(&c->live); // kernel completion: this thread's writes happen-before the host's reads after join
+  to_scheduler(c);
+}
+
 inline void
 fiber_entry()
 {
   Cta* c = g_cta;
+  EMU_ACQUIRE(&c->threads); // kernel launch: the host's writes happen-before this thread
   c->body();
-  c->done[c->current] = 1;
-  c->live--;
-  swapcontext(&c->ctx[c->current], &c->sched);
+  fiber_exit(c);
 }
 
-inline void
+EMU_NO_TSAN inline void
 run_cta(Cta* c)
 {
   g_cta = c;
@@ -146,15 +191,30 @@ run_cta(Cta* c)
     c->ctx[t].uc_link = &c->sched;
     makecontext(&c->ctx[t], (void (*)())fiber_entry, 0);
   }
+#if EMU_TSAN
+  c->tsan_sched = __tsan_get_current_fiber();
+  c->tsan_fiber.resize(c->threads);
+  for (unsigned t = 0; t < c->threads; t++)
+    c->tsan_fiber[t] = __tsan_create_fiber(0);
+#endif
+  EMU_RELEASE(&c->threads);
   while (c->live) {
     for (unsigned t = 0; t < c->threads; t++) {
       if (c->done[t])
         continue;
       c->current = t;
       threadIdx = uint3{ t, 0, 0 };
+#if EMU_TSAN
+      __tsan_switch_to_fiber(c->tsan_fiber[t], __tsan_switch_to_fiber_no_sync);
+#endif
       swapcontext(&c->sched, &c->ctx[t]);
     }
   }
+  EMU_ACQUIRE(&c->live);
+#if EMU_TSAN
+  for (unsigned t = 0; t < c->threads; t++)
+    __tsan_destroy_fiber(c->tsan_fiber[t]);
+#endif
   g_cta = nullptr;
 }
 
@@ -197,11 +257,12 @@ join(Grid& g)
 // All rendezvous are generation-counted: a fiber that arrives bumps the counter, the last one opens the
 // next generation, the others yield until the generation changes.  Fibers of one CTA never run
 // concurrently (one OS thread), so no locking is needed.
-inline int
+EMU_NO_TSAN inline int
 emu_block_rendezvous(int pred)
 {
   emu::Cta* c = emu::g_cta;
   const unsigned g = c->sync_gen;
+  EMU_RELEASE(&c->sync_gen); // everything this thread did so far happens-before every departure
   c->sync_and &= (pred != 0);
   if (++c->sync_arrived == c->live) {
     c->sync_and_result = c->sync_and;
@@ -212,6 +273,7 @@ emu_block_rendezvous(int pred)
     while (c->sync_gen == g)
       emu::yield();
   }
+  EMU_ACQUIRE(&c->sync_gen);
   return c->sync_and_result;
 }
 inline void
@@ -229,7 +291,7 @@ __syncthreads_and(int pred)
   return r;
 }
 
-inline uint32_t
+EMU_NO_TSAN inline uint32_t
 emu_warp_exchange(uint32_t mine, unsigned src_lane)
 {
   emu::Cta* c = emu::g_cta;
@@ -237,6 +299,7 @@ emu_warp_exchange(uint32_t mine, unsigned src_lane)
   const unsigned lane = threadIdx.x & 31u;
   const unsigned width = std::min(32u, c->threads - (threadIdx.x & ~31u));
   const uint32_t g = w.gen;
+  EMU_RELEASE(&w.gen); // a *_sync shuffle / __syncwarp orders the warp's memory accesses
   w.vals[g & 1u][lane] = mine;
   if (++w.arrived == width) {
     w.arrived = 0;
@@ -245,6 +308,7 @@ emu_warp_exchange(uint32_t mine, unsigned src_lane)
     while (w.gen == g)
       emu::yield();
   }
+  EMU_ACQUIRE(&w.gen);
   return src_lane < width ? w.vals[g & 1u][src_lane] : mine;
 }
 inline void
@@ -286,21 +350,26 @@ __shfl_sync(unsigned, T v, int src_lane)
 }
 
 // ---- memory ------------------------------------------------------------------------------------------
+#if EMU_TSAN
+inline float __ldcg(const float* p) { return *p; }       // plain: TSan checks the exchange is ordered
+inline void __stcg(float* p, float v) { *p = v; }
+#else
 inline float __ldcg(const float* p) { float v; uint32_t b = __atomic_load_n(reinterpret_cast<const uint32_t*>(p), __ATOMIC_RELAXED); memcpy(&v, &b, 4); return v; }
+inline void __stcg(float* p, float v) { uint32_t b; memcpy(&b, &v, 4); __atomic_store_n(reinterpret_cast<uint32_t*>(p), b, __ATOMIC_RELAXED); }
+#endif
 inline float4 __ldcg(const float4* p)
 {
   float4 v;
   v.x = __ldcg(&p->x); v.y = __ldcg(&p->y); v.z = __ldcg(&p->z); v.w = __ldcg(&p->w);
   return v;
 }
-inline void __stcg(float* p, float v) { uint32_t b; memcpy(&b, &v, 4); __atomic_store_n(reinterpret_cast<uint32_t*>(p), b, __ATOMIC_RELAXED); }
 inline void __stcg(float4* p, float4 v) { __stcg(&p->x, v.x); __stcg(&p->y, v.y); __stcg(&p->z, v.z); __stcg(&p->w, v.w); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
-inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
-inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, EMU_RELAXED); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, EMU_RELAXED); }
+inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, EMU_RELAXED); }
 inline int atomicMax(int* p, int v)
 {
   int old = __atomic_load_n(p, __ATOMIC_RELAXED);

@@ -43,12 +43,12 @@ inline unsigned long long
 ld_relaxed_sys(const unsigned long long* p)
 {
   sched_yield();
-  return __atomic_load_n(p, __ATOMIC_RELAXED);
+  return __atomic_load_n(p, EMU_RELAXED_LOAD);
 }
 inline void
 st_relaxed_sys(unsigned long long* p, unsigned long long v)
 {
-  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+  __atomic_store_n(p, v, EMU_RELAXED_STORE);
 }
 inline void
 red_release_gpu_add(unsigned int* p, unsigned int v)
@@ -81,19 +81,27 @@ smem_u32(const void* p)
   return (uint32_t)reinterpret_cast<uintptr_t>(p);
 }
 // an mbarrier is the number of phases completed so far
-inline void
+EMU_NO_TSAN inline void
 mbar_init(uint64_t* bar, uint32_t)
 {
   *bar = 0;
+}
+EMU_NO_TSAN inline void
+emu_bump(uint64_t* bar)
+{
+  *bar += 1;
 }
 inline void
 mbar_arrive_expect_tx(uint64_t*, uint32_t)
 {
 }
-inline bool
+EMU_NO_TSAN inline bool
 mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
-  return ((uint32_t)(*bar) & 1u) != parity; // the phase of that parity has completed
+  const bool done = ((uint32_t)(*bar) & 1u) != parity; // the phase of that parity has completed
+  if (done)
+    EMU_ACQUIRE(bar); // the copied bytes are visible to the waiter
+  return done;
 }
 inline void
 bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
@@ -103,7 +111,8 @@ bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
     abort(); // the hardware would fault
   }
   memcpy(dst_smem, src_gmem, bytes);
-  *bar += 1;
+  EMU_RELEASE(bar);
+  emu_bump(bar);
 }
 inline void
 bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar, unsigned long long)
