@@ -19,6 +19,15 @@
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
 
+// Triple-chevron launches go through two macros so that the host code of this file can also be built
+// for the CPU emulation harness (tests/cuda_emu), whose stand-in <cuda_runtime.h> defines them first:
+//   ST_LAUNCH              kernels whose threads cooperate (barriers, shuffles, shared memory)
+//   ST_LAUNCH_ELEMENTWISE  kernels whose threads are independent of each other
+#ifndef ST_LAUNCH
+#define ST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define ST_LAUNCH_ELEMENTWISE(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace st {
 
 static_assert(kPlanClusterMaxCtas == kClusterMaxCtas && kPlanClusterSmemBudget == kClusterSmemBudget,
@@ -722,9 +731,9 @@ launch_row_pass(st::Context& q, const float* d_rows, const float* d_e, float* d_
   const uint32_t chunk = std::min<uint32_t>((uint32_t)kChunkCols, dim);
   const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((rows + 7u) / 8u, 8u * q.sm_count()));
   if (vec4)
-    sum_across_rows_kernel<4><<<grid, 256, chunk * sizeof(float), q.stream()>>>(d_rows, d_e, d_vec, dim, row0, rows);
+    ST_LAUNCH(sum_across_rows_kernel<4>, grid, 256, chunk * sizeof(float), q.stream(), d_rows, d_e, d_vec, dim, row0, rows);
   else
-    sum_across_rows_kernel<1><<<grid, 256, chunk * sizeof(float), q.stream()>>>(d_rows, d_e, d_vec, dim, row0, rows);
+    ST_LAUNCH(sum_across_rows_kernel<1>, grid, 256, chunk * sizeof(float), q.stream(), d_rows, d_e, d_vec, dim, row0, rows);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -747,7 +756,7 @@ find_max(st::Context& q, const float* d_vec, float* d_max, const uint dim, const
 {
   q.activate();
   ST_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), q.stream())); // the zero-filled cell, reference :162-170
-  find_max_kernel<<<blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream()>>>(d_vec, d_max, dim);
+  ST_LAUNCH(find_max_kernel, blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream(), d_vec, d_max, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -757,8 +766,7 @@ compute_eigen_vector(st::Context& q, const float* d_vec, const float* d_max, flo
                      const uint dim, const uint)
 {
   q.activate();
-  compute_eigen_vector_kernel<<<blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream()>>>(
-    d_vec, d_max, d_eigen_vec, dim);
+  ST_LAUNCH_ELEMENTWISE(compute_eigen_vector_kernel, blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream(), d_vec, d_max, d_eigen_vec, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -767,7 +775,7 @@ int
 initialise_eigen_vector(st::Context& q, float* d_eigen_vec, const uint dim)
 {
   q.activate();
-  fill_kernel<<<blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream()>>>(d_eigen_vec, 1.f, dim);
+  ST_LAUNCH_ELEMENTWISE(fill_kernel, blocks_for(dim, 256, 4 * q.sm_count()), 256, 0, q.stream(), d_eigen_vec, 1.f, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -780,9 +788,9 @@ compute_next_matrix(st::Context& q, float* d_mat, const float* d_vec, const uint
   const dim3 grid(blocks_for(vec4 ? dim / 4 : dim, 256, 64),
                   (unsigned)std::min<uint32_t>(dim, 16384u));
   if (vec4)
-    compute_next_matrix_kernel<4><<<grid, 256, 0, q.stream()>>>(d_mat, d_vec, dim);
+    ST_LAUNCH_ELEMENTWISE(compute_next_matrix_kernel<4>, grid, 256, 0, q.stream(), d_mat, d_vec, dim);
   else
-    compute_next_matrix_kernel<1><<<grid, 256, 0, q.stream()>>>(d_mat, d_vec, dim);
+    ST_LAUNCH_ELEMENTWISE(compute_next_matrix_kernel<1>, grid, 256, 0, q.stream(), d_mat, d_vec, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -791,8 +799,8 @@ int
 stop(st::Context& q, const float* d_vec, uint* d_ret, const uint dim, const uint, float eps)
 {
   q.activate();
-  fill_u32_kernel<<<1, 32, 0, q.stream()>>>(d_ret, 1u, 1u); // the flag starts at 1, reference :351-359
-  stop_kernel<<<blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream()>>>(d_vec, d_ret, dim, eps);
+  ST_LAUNCH_ELEMENTWISE(fill_u32_kernel, 1, 32, 0, q.stream(), d_ret, 1u, 1u); // the flag starts at 1, reference :351-359
+  ST_LAUNCH(stop_kernel, blocks_for(dim, 1024, 4 * q.sm_count()), 1024, 0, q.stream(), d_vec, d_ret, dim, eps);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -803,7 +811,7 @@ generate_hilbert_matrix(st::Context& q, float* d_rows, const uint dim, const uin
   q.activate();
   const uint rows = rows_ ? rows_ : dim - row0;
   const dim3 grid(blocks_for(dim, 256, 32), (unsigned)std::min<uint32_t>(rows, 32768u));
-  hilbert_kernel<<<grid, 256, 0, q.stream()>>>(d_rows, dim, row0, rows);
+  ST_LAUNCH_ELEMENTWISE(hilbert_kernel, grid, 256, 0, q.stream(), d_rows, dim, row0, rows);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -814,7 +822,7 @@ convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t coun
   q.activate();
   const size_t work = (count + 3) / 4;
   const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)q.sm_count() * 16);
-  convert_bf16_kernel<<<std::max(1, grid), 256, 0, q.stream()>>>(d_src, d_dst, count);
+  ST_LAUNCH_ELEMENTWISE(convert_bf16_kernel, std::max(1, grid), 256, 0, q.stream(), d_src, d_dst, count);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -827,7 +835,7 @@ generate_uniform_matrix(st::Context& q, float* d_rows, const uint dim, uint64_t 
   const uint rows = rows_ ? rows_ : dim - row0;
   const size_t blocks4 = ((size_t)rows * dim + 3) / 4 + 1;
   const int grid = (int)std::min<size_t>((blocks4 + 255) / 256, (size_t)q.sm_count() * 16);
-  uniform_kernel<<<std::max(1, grid), 256, 0, q.stream()>>>(d_rows, dim, row0, rows, seed);
+  ST_LAUNCH_ELEMENTWISE(uniform_kernel, std::max(1, grid), 256, 0, q.stream(), d_rows, dim, row0, rows, seed);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }

@@ -63,6 +63,46 @@ def build(force: bool = False) -> str:
     return SO
 
 
+LIB_EMU = os.path.join(HERE, "libsimilarity_transform_emu.so")
+LIB_SOURCES = ["solver.cu", "abi.cu", "similarity_transform.hpp"]
+RT_SOURCES = ["cuda_runtime_emu.h", "emu_rt.cpp", os.path.join("fake_include_rt", "cuda_runtime.h")]
+
+
+def build_library(force: bool = False) -> str:
+    """The WHOLE library (C ABI + Context::solve + kernels) for the host, on the pretend CUDA runtime of
+    cuda_runtime_emu.h -> libsimilarity_transform_emu.so.  Used by tests/conftest.py under ST_EMULATED_LIB=1."""
+    build(force=False)
+    deps = ([os.path.join(CSRC, f) for f in LIB_SOURCES] + [os.path.join(HERE, f) for f in RT_SOURCES + OWN_SOURCES]
+            + [os.path.join(ROOT, "include", "similarity_transform.h"), SO, __file__])
+    if not force and os.path.exists(LIB_EMU) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_EMU) for d in deps):
+        return LIB_EMU
+    rt_dir = os.path.join(BUILD, "library")
+    os.makedirs(rt_dir, exist_ok=True)
+    for f in KERNEL_SOURCES:
+        shutil.copyfile(os.path.join(BUILD, f), os.path.join(rt_dir, f))
+    units = []
+    for f in LIB_SOURCES:
+        with open(os.path.join(CSRC, f)) as src:
+            text = src.read()
+        text = text.replace('"../../include/similarity_transform.h"',
+                            '"' + os.path.join(ROOT, "include", "similarity_transform.h") + '"')
+        out = os.path.join(rt_dir, f.replace(".cu", ".cpp"))
+        with open(out, "w") as dst:
+            dst.write(text)
+        if f.endswith(".cu"):
+            units.append(out)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [cxx, "-std=c++17", "-O2", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+           "-pthread", "-w", '-DST_PTX_HEADER="ptx_emu.h"',
+           "-I", os.path.join(HERE, "fake_include_rt"), "-I", rt_dir, "-I", HERE,
+           "-o", LIB_EMU, *units, os.path.join(HERE, "emu_rt.cpp")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout[-8000:])
+        raise RuntimeError("building the emulated library failed")
+    return LIB_EMU
+
+
 TSAN_EXE = os.path.join(HERE, "emu_tsan.bin")
 
 
@@ -111,3 +151,5 @@ if __name__ == "__main__":
     print(build(force=True))
     if "--tsan" in sys.argv:
         print(build_tsan(force=True))
+    if "--library" in sys.argv:
+        print(build_library(force=True))

@@ -62,7 +62,7 @@
 #endif
 
 // ---- language keywords ---------------------------------------------------------------------------
-#define __global__
+#define __global__ inline
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -173,12 +173,12 @@ fiber_entry()
 }
 
 EMU_NO_TSAN inline void
-run_cta(Cta* c)
+run_cta(Cta* c, uint3 block_index, dim3 grid_dim)
 {
   g_cta = c;
-  blockIdx = uint3{ c->index, 0, 0 };
+  blockIdx = block_index;
   blockDim = dim3(c->threads);
-  gridDim = dim3(c->grid->ctas);
+  gridDim = grid_dim;
   c->ctx.resize(c->threads);
   c->done.assign(c->threads, 0);
   c->warps.assign((c->threads + 31) / 32, WarpState{});
@@ -238,7 +238,7 @@ launch_async(void (*kernel)(const P), unsigned ctas, unsigned threads, size_t sm
     g->cta.push_back(std::move(c));
   }
   for (unsigned b = 0; b < ctas; b++)
-    g->workers.emplace_back(run_cta, g->cta[b].get());
+    g->workers.emplace_back(run_cta, g->cta[b].get(), uint3{ b, 0, 0 }, dim3(ctas));
   return g;
 }
 
