@@ -57,3 +57,60 @@ def test_fused_exchange_multi_gpu(world):
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0, proc.stdout[-4000:]
     assert "SHARDED_OK" in proc.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_in_process_sharded_solve_with_local_link(world):
+    """One process, one host thread per GPU, shards wired with st_shard_link_local (plain peer access
+    instead of IPC handles).  Every rank must return the bits of the single-GPU solve, which in turn are
+    the bits of the oracle in the kernels' summation order.  (On the emulated library this runs with
+    ST_EMU_DEVICES pretend GPUs and exercises the fused exchange through the real C ABI.)"""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs in one process")
+    import ctypes
+    import threading
+    from eigen_value_b200 import Solver, STOP_RELATIVE
+    from eigen_value_b200._lib import StResult, check
+    from eigen_value_b200.similarity_transform import make_options
+
+    dim, seed = 1000, 0x5EED0001
+    solvers = [Solver(g) for g in range(world)]
+    lib = solvers[0].lib
+    shards = []
+    for g in range(world):
+        sh = ctypes.c_void_p()
+        check(lib.st_shard_create(solvers[g].ctx, dim, g, world, ctypes.byref(sh)), "st_shard_create")
+        shards.append(sh)
+    table = (ctypes.c_void_p * world)(*[s.value for s in shards])
+    check(lib.st_shard_link_local(table, world), "st_shard_link_local")
+    rows = []
+    for g in range(world):
+        r0, n = ctypes.c_uint32(), ctypes.c_uint32()
+        check(lib.st_shard_rows(shards[g], ctypes.byref(r0), ctypes.byref(n)), "st_shard_rows")
+        rows.append(solvers[g].uniform(dim, seed, r0.value, n.value))
+        solvers[g].synchronize()
+
+    mat = oracle.uniform(dim, seed)
+    for opts, okw in ((dict(), dict()), (dict(eps=1e-6, stop=STOP_RELATIVE, max_iter=60), dict(eps=1e-6, stop=oracle.STOP_RELATIVE, max_itr=60))):
+        out = [None] * world
+
+        def work(g):
+            o = make_options(lib, **opts)
+            res = StResult()
+            vec = solvers[g].alloc(4 * dim)
+            rc = lib.st_shard_solve(shards[g], rows[g].ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res))
+            out[g] = (rc, res.eigen_val, res.iter_count, vec.download(np.float32, dim) if rc == 0 else None)
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=600)
+        assert all(o is not None and o[0] == 0 for o in out), out
+        o_val, o_vec, _, o_it = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA, **okw)
+        for rc, val, it, vec in out:
+            assert it == o_it and np.float32(val) == o_val and np.array_equal(vec, o_vec)
+    for sh in shards:
+        lib.st_shard_destroy(sh)
+    for s in solvers:
+        s.close()

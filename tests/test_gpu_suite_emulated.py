@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def run_emulated(args, max_dim=1100, timeout=1500):
-    env = dict(os.environ, ST_EMULATED_LIB="1", ST_EMU_MAX_DIM=str(max_dim))
+    env = dict(os.environ, ST_EMULATED_LIB="1", ST_EMU_MAX_DIM=str(max_dim), ST_EMU_DEVICES="4")
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", *args]
     return subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
 
@@ -26,12 +26,12 @@ def test_gpu_test_files_pass_on_the_emulated_library():
     """tests/test_zz_gpu_bitexact.py and tests/test_zzz_gpu_bf16_storage.py in full (bit-exact parity through
     max_eigen_value, both forms, relative stop, bf16 storage, refusals), and from the older files the drop-in
     boundary (golden, 4-byte iter_cnt slot, bad arguments), the per-kernel entry points against the reference's
-    unit fixtures, the device generators, the options and the world == 1 shard path -- every case up to
-    N = 1100.  (The 1000-round NaN cases take a minute each when emulated; their logic is covered with a
+    unit fixtures, the device generators, the options, the world == 1 shard path and the in-process sharded
+    solve on 2 and 4 pretend GPUs (st_shard_link_local, one host thread per GPU) -- every case up to N = 1100.  (The 1000-round NaN cases take a minute each when emulated; their logic is covered with a
     30-round cap in tests/test_kernel_logic_emulated.py.)"""
     keep = ("bitexact or bf16 or three_by_three or iter_count_slot or bad_arguments or test_kernel_ or test_device_ "
             "or forms_agree or eps_option or max_iter_cap or ragged_and_tiny or on_chip_cluster or world_one "
-            "or shard_argument or launch_shape")
+            "or shard_argument or launch_shape or in_process")
     proc = run_emulated(["tests/test_gpu_parity.py", "tests/test_gpu_sharded.py", "tests/test_zz_gpu_bitexact.py",
                          "tests/test_zzz_gpu_bf16_storage.py", "-k", keep])
     assert proc.returncode == 0, proc.stdout[-4000:]
