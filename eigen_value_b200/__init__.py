@@ -5,8 +5,8 @@ Only the hot path of itzmeanjan/eigen_value lives here: the CUDA round loop (csr
 reference's Python interface.  Importing the package does not touch the GPU; the shared
 library is loaded on first use and there is no CPU fallback.
 """
-from .similarity_transform import (EPS, MAX_ITR, FORM_INPLACE, FORM_READONLY, STOP_ABSOLUTE, STOP_RELATIVE,
+from .similarity_transform import (EPS, MAX_ITR, FORM_INPLACE, FORM_READONLY, STOP_ABSOLUTE, STOP_RELATIVE, ACC_F32, ACC_F64,
                                    EigenValue, Solver, SolveInfo, DeviceBuffer)
 
-__all__ = ["EPS", "MAX_ITR", "FORM_INPLACE", "FORM_READONLY", "STOP_ABSOLUTE", "STOP_RELATIVE", "EigenValue",
+__all__ = ["EPS", "MAX_ITR", "FORM_INPLACE", "FORM_READONLY", "STOP_ABSOLUTE", "STOP_RELATIVE", "ACC_F32", "ACC_F64", "EigenValue",
            "Solver", "SolveInfo", "DeviceBuffer"]

@@ -26,6 +26,7 @@ class StOptions(ctypes.Structure):
         ("kernel", ctypes.c_int32),
         ("l2_keep_pct", ctypes.c_int32),
         ("stop", ctypes.c_int32),
+        ("accumulate", ctypes.c_int32),
     ]
 
 

@@ -196,6 +196,32 @@ dot_acc(float a, float e, float acc)
   return fmaf(a, e, acc);
 }
 
+// fp64 ACCUMULATION (opt-in): the same lane / accumulator / fold / tree order with
+// double accumulators.  The product of two floats is exact in double, so each step rounds once (in
+// double) and the row sum is rounded to float once at the end (oracle: ORACLE_SUM_CUDA_F64).
+__device__ __forceinline__ double
+dot_acc(float4 a, float4 e, double acc)
+{
+  acc = fma((double)a.x, (double)e.x, acc);
+  acc = fma((double)a.y, (double)e.y, acc);
+  acc = fma((double)a.z, (double)e.z, acc);
+  acc = fma((double)a.w, (double)e.w, acc);
+  return acc;
+}
+__device__ __forceinline__ double
+dot_acc(float a, float e, double acc)
+{
+  return fma((double)a, (double)e, acc);
+}
+__device__ __forceinline__ double
+warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---- bf16 STORAGE of the matrix (opt-in, outside reference parity) ----------
 // The matrix is held as bfloat16 (2 bytes per element: half the HBM bytes per round); everything
 // else -- the eigenvector, the row sums, every accumulation -- stays fp32.  bf16 -> fp32 is exact
@@ -277,7 +303,7 @@ row_dot_bf16(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lan
 // Fixed evaluation order (depends on the segment length only): lane l owns vectors
 // l, l+32, ...; vector j of a batch goes to accumulator j; accumulators are folded pairwise,
 // then the 32 lanes by an xor-shuffle tree.  All lanes return the sum.
-template<int VEC, bool HINT = false>
+template<int VEC, bool HINT = false, typename ACC = float>
 __device__ __forceinline__ float
 row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, int lane,
                  unsigned long long pol = 0ull)
@@ -286,10 +312,10 @@ row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, 
   const V* __restrict__ a = reinterpret_cast<const V*>(row);
   const V* es = reinterpret_cast<const V*>(e_s);
   const uint32_t nv = len / VEC;
-  float acc[kUnroll];
+  ACC acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
-    acc[u] = 0.f;
+    acc[u] = ACC(0);
   uint32_t i = (uint32_t)lane;
   for (; i + 32u * (kUnroll - 1) < nv; i += 32u * kUnroll) {
     V v[kUnroll];
@@ -311,7 +337,7 @@ row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, 
 #pragma unroll
     for (int u = 0; u < s; u++)
       acc[u] += acc[u + s];
-  return warp_sum(acc[0]);
+  return (float)warp_sum(acc[0]);
 }
 
 __device__ __forceinline__ float4
@@ -489,9 +515,10 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
 // ---------------------------------------------------------------------------------------
 // the round loop
 // ---------------------------------------------------------------------------------------
-template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute, typename T = float>
+template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute, typename T = float, typename ACC = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundParams p)
 {
+  static_assert(sizeof(ACC) == 4 || (sizeof(T) == 4 && FORM == kFormReadOnly), "fp64 accumulation: fp32 storage, read-only form");
   constexpr bool kBf16 = sizeof(T) == 2; // p.A then points to bf16 storage (read-only form, N % 8 == 0)
   static_assert(!kBf16 || (VEC == 4 && FORM == kFormReadOnly), "bf16 storage: read-only form, vector loads");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
@@ -599,7 +626,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
           const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
           t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(scale_s), clen >> 3, lane);
         } else if (FORM == kFormReadOnly) {
-          if (p.keep_rows_pct == 0u)
+          if (sizeof(ACC) == 8)
+            t = row_dot_readonly<VEC, false, ACC>(p.A + off, scale_s, clen, lane);
+          else if (p.keep_rows_pct == 0u)
             t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
           else
             t = row_dot_readonly<VEC, true>(p.A + off, scale_s, clen, lane,

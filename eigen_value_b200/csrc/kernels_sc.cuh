@@ -42,16 +42,16 @@ constexpr int kRegVec = 5;           // float4 of s a thread keeps in registers 
 // accumulator (j / 32) % 8, the accumulators are folded pairwise and the lanes by an
 // xor-shuffle tree; the chunk sums of a row are added left to right by whoever finishes the
 // row.  LD = independent 128-bit loads in flight per lane (8 or 16); it does not affect the order.
-template<int LD>
+template<int LD, typename ACC = float>
 __device__ __forceinline__ float
 chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane,
                      const float4* pf, uint32_t npre)
 {
   static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
-  float acc[kUnroll];
+  ACC acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
-    acc[u] = 0.f;
+    acc[u] = ACC(0);
   for (uint32_t b0 = 0; b0 < npre; b0 += 32u * kUnroll) {
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) {
@@ -81,12 +81,14 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
 #pragma unroll
     for (int u = 0; u < s; u++)
       acc[u] += acc[u + s];
-  return warp_sum(acc[0]);
+  return (float)warp_sum(acc[0]);
 }
 
-template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float>
+template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float,
+         typename ACC = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
+  static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
   // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
                                  ch * (kChunkVec >> 1);
             t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
           } else {
-            t = chunk_dot_prefetched<LD>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
-                                         reinterpret_cast<const float4*>(my_pf), npre);
+            t = chunk_dot_prefetched<LD, ACC>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
+                                              reinterpret_cast<const float4*>(my_pf), npre);
           }
           if (lane == 0) {
             if (pending)

@@ -344,6 +344,39 @@ launch_general_bf16(int threads, const RoundParams& p, int grid, size_t smem, cu
   return launch_general_bf16_one<1024, STOP>(p, grid, threads, smem, stream);
 }
 
+// ---- fp64 accumulation (fp32 storage, read-only form): the automatic resident-e configurations
+// (13 / 10 / 12) and the general loop ----------------------------------------------------------------
+template<typename K>
+static void
+launch_cooperative(K kernel, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
+{
+  if (smem > 48 * 1024)
+    ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = { (void*)&p };
+  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, smem, stream));
+}
+
+template<int STOP>
+static void
+launch_sc_acc64(int id, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
+{
+  switch (id) {
+    case 10: return launch_cooperative(round_loop_sc_kernel<512, 2, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
+    case 12: return launch_cooperative(round_loop_sc_kernel<512, 3, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
+    case 13: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
+    default: throw std::invalid_argument("fp64 accumulation is built for resident-e configurations 13, 10 and 12");
+  }
+}
+
+template<int VEC, int STOP>
+static void
+launch_general_acc64(int threads, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
+{
+  if (threads <= 512)
+    return launch_cooperative(round_loop_kernel<VEC, kFormReadOnly, 512, STOP, float, double>, p, grid, threads, smem, stream);
+  return launch_cooperative(round_loop_kernel<VEC, kFormReadOnly, 1024, STOP, float, double>, p, grid, threads, smem, stream);
+}
+
 // ---- on-chip variant (N <= 512): matrix resident in the shared memory of one cluster -----------
 constexpr int kClusterKernelId = 20;
 constexpr int kClusterThreads = 512;
@@ -396,6 +429,15 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   if (opt.stop != ST_STOP_ABSOLUTE && opt.stop != ST_STOP_RELATIVE)
     throw std::invalid_argument("solve: unknown st_options.stop");
   const int stop = opt.stop == ST_STOP_RELATIVE ? kStopRelative : kStopAbsolute;
+  if (opt.accumulate != ST_ACC_F32 && opt.accumulate != ST_ACC_F64)
+    throw std::invalid_argument("solve: unknown st_options.accumulate");
+  const bool acc64 = opt.accumulate == ST_ACC_F64;
+  if (acc64) {
+    if (bf16 || form != kFormReadOnly)
+      throw std::invalid_argument("solve: fp64 accumulation needs fp32 storage and the read-only form");
+    if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != 10 && opt.kernel != 12 && opt.kernel != 13)
+      throw std::invalid_argument("solve: fp64 accumulation is built for kernel 0 (automatic), 1, 10, 12 and 13");
+  }
   if (bf16) {
     // d_rows points to bfloat16 storage: 128-bit loads of 8 elements, fp32 everywhere else
     if (form != kFormReadOnly || dim % 8u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
@@ -483,7 +525,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const ScConfig* sc = nullptr;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
-  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !bf16 && dim <= (uint32_t)kClusterCols)) {
+  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !bf16 && !acc64 && dim <= (uint32_t)kClusterCols)) {
     if (!readonly4 || shard || dim > (uint32_t)kClusterCols)
       throw std::invalid_argument("solve: on-chip kernel needs one GPU, the read-only form, dim % 4 == 0, dim <= 512");
     cluster_ctas = cluster_ctas_for(dim, &smem);
@@ -511,8 +553,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         continue;
       if (bf16 && c.id != kScBf16Id)
         continue; // bf16 storage is built for configuration 11 only
-      if (opt.kernel == 0 && !bf16 && stop == kStopRelative && c.id != 13 && c.id != 10 && c.id != 12)
-        continue; // only the automatic configurations are built with the relative stop test
+      if (opt.kernel == 0 && !bf16 && (stop == kStopRelative || acc64) && c.id != 13 && c.id != 10 && c.id != 12)
+        continue; // only the automatic configurations are built with the relative stop test / fp64 accumulation
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
@@ -576,7 +618,23 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   ST_CUDA(cudaMemsetAsync(d_bar_, 0, sizeof(BarrierState), stream_));
   ST_CUDA(cudaMemsetAsync(d_scalars_, 0, 64, stream_));
   ST_CUDA(cudaEventRecord(ev0_, stream_));
-  if (bf16 && sc) {
+  if (acc64 && sc) {
+    if (stop == kStopRelative)
+      launch_sc_acc64<kStopRelative>(sc->id, p, grid, threads, smem, stream_);
+    else
+      launch_sc_acc64<kStopAbsolute>(sc->id, p, grid, threads, smem, stream_);
+  } else if (acc64) {
+    if (tma || cluster_ctas)
+      throw std::invalid_argument("solve: fp64 accumulation is not built for this kernel");
+    if (vec4 && stop == kStopRelative)
+      launch_general_acc64<4, kStopRelative>(threads, p, grid, smem, stream_);
+    else if (vec4)
+      launch_general_acc64<4, kStopAbsolute>(threads, p, grid, smem, stream_);
+    else if (stop == kStopRelative)
+      launch_general_acc64<1, kStopRelative>(threads, p, grid, smem, stream_);
+    else
+      launch_general_acc64<1, kStopAbsolute>(threads, p, grid, smem, stream_);
+  } else if (bf16 && sc) {
     if (sc->id != kScBf16Id)
       throw std::invalid_argument("solve: bf16 storage needs resident-e configuration 11");
     if (stop == kStopRelative)

@@ -23,6 +23,7 @@ EPS = 1e-3       # reference include/similarity_transform.hpp:4
 MAX_ITR = 1000   # reference include/similarity_transform.hpp:5
 FORM_READONLY, FORM_INPLACE = 0, 1
 STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # st_options.stop: the reference's test | max diff < eps * max(s)
+ACC_F32, ACC_F64 = 0, 1               # st_options.accumulate: fp32 like the reference | fp64 accumulators
 
 
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
@@ -130,10 +131,11 @@ class DeviceBuffer:
 
 def make_options(lib, eps: float = EPS, max_iter: int = MAX_ITR, form: int = FORM_READONLY,
                  sweep: Optional[int] = None, threads: int = 0, ctas: int = 0, kernel: int = 0,
-                 l2_keep_pct: Optional[int] = None, stop: int = STOP_ABSOLUTE) -> StOptions:
+                 l2_keep_pct: Optional[int] = None, stop: int = STOP_ABSOLUTE,
+                 accumulate: int = ACC_F32) -> StOptions:
     o = StOptions()
     lib.st_default_options(ctypes.byref(o))
-    o.eps, o.max_iter, o.form, o.stop = eps, max_iter, form, stop
+    o.eps, o.max_iter, o.form, o.stop, o.accumulate = eps, max_iter, form, stop, accumulate
     o.threads, o.ctas, o.kernel = threads, ctas, kernel
     if sweep is not None:
         o.sweep = sweep

@@ -89,6 +89,14 @@ enum
                            Changes WHEN the loop stops, never the arithmetic of a round.        */
 };
 
+enum
+{
+  ST_ACC_F32 = 0, /* row sums accumulated in fp32, like the reference (default)                    */
+  ST_ACC_F64 = 1  /* opt-in: the same evaluation order with fp64 accumulators, each row sum rounded
+                     to fp32 once at the end (fp32 storage, read-only form; kernels 0, 1, 10, 12, 13).
+                     Lowers the rounding noise of the row sums; changes results within the tolerance. */
+};
+
 typedef struct st_options
 {
   float eps;         /* stop threshold, reference EPS                               */
@@ -106,6 +114,7 @@ typedef struct st_options
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
   int32_t stop;        /* ST_STOP_*; tuning kernels 2-9, 11, 14-19 support ST_STOP_ABSOLUTE only */
+  int32_t accumulate;  /* ST_ACC_*                                                                */
 } st_options;
 
 typedef struct st_result

@@ -24,6 +24,7 @@ MAX_ITR = 1000    # reference include/similarity_transform.hpp:5
 FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
 SUM_CUDA = 4   # the CUDA kernels' evaluation order: bit-identical to the GPU (tests/test_zz_gpu_bitexact.py)
+SUM_CUDA_F64 = 6    # SUM_CUDA's order with fp64 accumulators (st_options.accumulate = ST_ACC_F64)
 SUM_CUDA_BF16 = 5   # the same with 8-element units: the kernels' order on bf16 storage (feed to_bf16(mat)[0])
 STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # the reference's stop test | extension: threshold eps * max(s)
 

@@ -63,6 +63,9 @@ enum
   ORACLE_SUM_CUDA = 4,       /* the evaluation order of the CUDA round kernels (lane / accumulator /
                                 fold / shuffle tree, FMA): with ORACLE_FORM_READONLY the oracle
                                 then matches the GPU bit for bit (row_dot_cuda_order below) */
+  ORACLE_SUM_CUDA_F64 = 6,   /* ORACLE_SUM_CUDA's order with fp64 accumulators (ST_ACC_F64): products are
+                                exact in double, every add rounds once in double, the chunk sum is
+                                rounded to fp32 once; chunk sums of a row are added in fp32 */
   ORACLE_SUM_CUDA_BF16 = 5   /* the same order with 8-element units: what the CUDA kernels do on
                                 bf16 STORAGE of the matrix (one 128-bit load = 8 elements).  Feed
                                 the oracle the bf16-rounded matrix (as fp32): bf16 -> fp32 is
@@ -161,6 +164,46 @@ row_dot_cuda_order(const float* row, const float* scale, size_t n, size_t unit)
   return total;
 }
 
+/* ORACLE_SUM_CUDA_F64: row_dot_cuda_order with double accumulators (fp32 storage: float4 / scalar units) */
+static float
+row_dot_cuda_order_f64(const float* row, const float* scale, size_t n)
+{
+  const size_t vec = (n % 4 == 0) ? 4 : 1;
+  float total = 0.f;
+  for (size_t c0 = 0; c0 < n; c0 += ORACLE_CUDA_CHUNK) {
+    const size_t clen = n - c0 < ORACLE_CUDA_CHUNK ? n - c0 : ORACLE_CUDA_CHUNK;
+    const size_t nv = clen / vec;
+    double acc[32][8];
+    for (int l = 0; l < 32; l++)
+      for (int u = 0; u < 8; u++)
+        acc[l][u] = 0.0;
+    for (size_t j = 0; j < nv; j++) {
+      const int l = (int)(j % 32), u = (int)((j / 32) % 8);
+      for (size_t k = 0; k < vec; k++) {
+        const size_t c = c0 + j * vec + k;
+        acc[l][u] = fma((double)row[c], scale ? (double)scale[c] : 1.0, acc[l][u]);
+      }
+    }
+    double lane[32];
+    for (int l = 0; l < 32; l++) {
+      for (int s = 4; s >= 1; s >>= 1)
+        for (int u = 0; u < s; u++)
+          acc[l][u] += acc[l][u + s];
+      lane[l] = acc[l][0];
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+      double next[32];
+      for (int l = 0; l < 32; l++)
+        next[l] = lane[l] + lane[l ^ o];
+      for (int l = 0; l < 32; l++)
+        lane[l] = next[l];
+    }
+    const float chunk_sum = (float)lane[0];
+    total = c0 == 0 ? chunk_sum : total + chunk_sum;
+  }
+  return total;
+}
+
 /* sum_c row[c] * (scale ? scale[c] : 1)   -- scale == NULL is the plain row sum */
 static float
 row_dot(const float* row, const float* scale, size_t n, int sum_mode)
@@ -177,6 +220,8 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
   }
   if (sum_mode == ORACLE_SUM_CUDA)
     return row_dot_cuda_order(row, scale, n, 0);
+  if (sum_mode == ORACLE_SUM_CUDA_F64)
+    return row_dot_cuda_order_f64(row, scale, n);
   if (sum_mode == ORACLE_SUM_CUDA_BF16)
     return row_dot_cuda_order(row, scale, n, 8); /* n % 8 == 0 required, like the kernels */
   if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {

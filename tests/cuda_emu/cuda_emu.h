@@ -321,12 +321,14 @@ template<typename T>
 inline T
 emu_shfl(T v, unsigned src_lane)
 {
-  static_assert(sizeof(T) == 4, "32-bit shuffles only");
-  uint32_t bits;
-  memcpy(&bits, &v, 4);
-  bits = emu_warp_exchange(bits, src_lane);
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only");
+  uint32_t bits[2] = { 0u, 0u };
+  memcpy(bits, &v, sizeof(T));
+  bits[0] = emu_warp_exchange(bits[0], src_lane);
+  if (sizeof(T) == 8)
+    bits[1] = emu_warp_exchange(bits[1], src_lane); // a 64-bit shuffle is two 32-bit ones, as on the hardware
   T out;
-  memcpy(&out, &bits, 4);
+  memcpy(&out, bits, sizeof(T));
   return out;
 }
 template<typename T>

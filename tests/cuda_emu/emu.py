@@ -17,7 +17,7 @@ class Opts(ctypes.Structure):
     _fields_ = [("eps", ctypes.c_float), ("max_iter", ctypes.c_uint32), ("form", ctypes.c_int32),
                 ("sweep", ctypes.c_int32), ("dynamic", ctypes.c_int32), ("threads", ctypes.c_int32),
                 ("ctas", ctypes.c_int32), ("kernel", ctypes.c_int32), ("stop", ctypes.c_int32),
-                ("bf16", ctypes.c_int32), ("world", ctypes.c_int32)]
+                ("bf16", ctypes.c_int32), ("world", ctypes.c_int32), ("acc64", ctypes.c_int32)]
 
 
 _lib = None
@@ -40,12 +40,12 @@ def lib() -> ctypes.CDLL:
 
 def solve(mat: np.ndarray, dim: int, kernel: int = 1, threads: int = 64, ctas: int = 3, world: int = 1,
           eps: float = 1e-3, max_iter: int = 1000, form: int = 0, sweep: int = 1, dynamic: int = -1,
-          stop: int = 0, bf16: bool = False):
+          stop: int = 0, bf16: bool = False, acc64: bool = False):
     """One solve on `world` emulated GPUs of `ctas` CTAs x `threads` threads each.
     Returns (lambda, eigen_vec, iter_count, passes, all_ranks_agree)."""
     assert mat.flags["C_CONTIGUOUS"] and mat.dtype == (np.uint16 if bf16 else np.float32)
     o = Opts(eps=eps, max_iter=max_iter, form=form, sweep=sweep, dynamic=dynamic, threads=threads, ctas=ctas,
-             kernel=kernel, stop=stop, bf16=int(bf16), world=world)
+             kernel=kernel, stop=stop, bf16=int(bf16), world=world, acc64=int(acc64))
     val, it, ps, agree = ctypes.c_float(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(1)
     vec = np.empty(dim, dtype=np.float32)
     rc = lib().emu_solve(mat.ctypes.data, dim, ctypes.byref(o), ctypes.byref(val), vec.ctypes.data,

@@ -33,6 +33,7 @@ struct emu_opts
   int32_t stop;    // 0 absolute, 1 relative
   int32_t bf16;    // matrix is bf16 storage
   int32_t world;   // emulated GPUs (row-block sharded)
+  int32_t acc64;   // fp64 accumulation (read-only form, fp32 storage; kernels 1, 10, 12, 13)
 };
 
 static thread_local std::string g_err;
@@ -63,8 +64,11 @@ struct Rank
 };
 
 template<int STOP>
-void (*general_kernel(bool vec4, int form, bool bf16))(const RoundParams)
+void (*general_kernel(bool vec4, int form, bool bf16, bool acc64))(const RoundParams)
 {
+  if (acc64)
+    return vec4 ? round_loop_kernel<4, kFormReadOnly, 512, STOP, float, double>
+                : round_loop_kernel<1, kFormReadOnly, 512, STOP, float, double>;
   if (bf16)
     return round_loop_kernel<4, kFormReadOnly, 512, STOP, bf16_t>;
   if (vec4)
@@ -75,8 +79,15 @@ void (*general_kernel(bool vec4, int form, bool bf16))(const RoundParams)
 }
 
 template<int STOP>
-void (*sc_kernel(int pf, bool bf16))(const RoundParams)
+void (*sc_kernel(int pf, bool bf16, bool acc64))(const RoundParams)
 {
+  if (acc64) {
+    switch (pf) {
+      case 1: return round_loop_sc_kernel<512, 1, kUnroll, STOP, float, double>;
+      case 2: return round_loop_sc_kernel<512, 2, kUnroll, STOP, float, double>;
+      default: return round_loop_sc_kernel<512, 3, kUnroll, STOP, float, double>;
+    }
+  }
   if (bf16)
     return round_loop_sc_kernel<512, 0, kUnroll, STOP, bf16_t>;
   switch (pf) {
@@ -99,7 +110,10 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
       throw std::string("bad argument");
     const int form = o->form ? kFormInPlace : kFormReadOnly;
     const bool bf16 = o->bf16 != 0;
+    const bool acc64 = o->acc64 != 0;
     const bool vec4 = dim % 4u == 0u;
+    if (acc64 && (bf16 || form != kFormReadOnly || !(o->kernel == 1 || o->kernel == 10 || o->kernel == 12 || o->kernel == 13)))
+      throw std::string("fp64 accumulation: fp32 storage, read-only form, kernels 1, 10, 12, 13");
     if (bf16 && (dim % 8u != 0u || form != kFormReadOnly))
       throw std::string("bf16 storage needs dim % 8 == 0 and the read-only form");
     const size_t elem = bf16 ? 2 : 4;
@@ -171,7 +185,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         r.grid = std::max(1u, std::min(want, (rows + warps - 1) / warps));
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
         r.smem = sizeof(float) * ((size_t)p.chunk_cols + cap);
-        kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16) : general_kernel<kStopAbsolute>(vec4, form, bf16);
+        kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64);
       } else if (kid >= 10 && kid <= 13) {
         if (!vec4 || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
           throw std::string("resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
@@ -196,7 +210,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.partial = r.partial.data();
           p.row_done = r.row_done.data();
         }
-        kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16) : sc_kernel<kStopAbsolute>(pf, bf16);
+        kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
       } else if (kid == 6 || kid == 9) {
         if (!vec4 || form != kFormReadOnly || bf16 || o->stop)
           throw std::string("TMA variants: read-only form, fp32, absolute stop test");

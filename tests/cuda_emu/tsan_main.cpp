@@ -13,7 +13,7 @@ struct emu_opts
 {
   float eps;
   uint32_t max_iter;
-  int32_t form, sweep, dynamic, threads, ctas, kernel, stop, bf16, world;
+  int32_t form, sweep, dynamic, threads, ctas, kernel, stop, bf16, world, acc64;
 };
 int emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, float* eigen_vec,
               uint32_t* iter_count, uint32_t* passes, uint32_t* ranks_agree);
@@ -76,7 +76,7 @@ main(int argc, char** argv)
     printf("racy kernel done\n");
     return 0;
   }
-  const emu_opts base{ 1e-3f, 1000u, 0, 1, -1, 64, 3, 1, 0, 0, 1 };
+  const emu_opts base{ 1e-3f, 1000u, 0, 1, -1, 64, 3, 1, 0, 0, 1, 0 };
   auto with = [&](int kernel, int threads, int ctas, int world = 1, int form = 0, int stop = 0, int dynamic = -1,
                   int bf16 = 0, uint32_t max_iter = 1000u) {
     emu_opts o = base;

@@ -39,7 +39,7 @@ def test_python_binding_table_matches_header():
 
 
 def test_struct_layouts():
-    assert ctypes.sizeof(_lib.StOptions) == 36
+    assert ctypes.sizeof(_lib.StOptions) == 40
     assert ctypes.sizeof(_lib.StResult) == 56
 
 

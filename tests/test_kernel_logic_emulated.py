@@ -204,3 +204,21 @@ def test_standalone_row_sum_kernel(dim):
     full = np.zeros((dim, dim), dtype=np.float32)
     full[: m.shape[0]] = m
     assert np.array_equal(emu.sum_across_rows(m), oracle.sum_across_rows(full, oracle.SUM_CUDA)[: m.shape[0]])
+
+
+# ---- fp64 accumulation (st_options.accumulate = ST_ACC_F64) ------------------------------------------------
+@pytest.mark.parametrize("kernel,dim,threads,ctas", [(1, 5, 32, 1), (1, 100, 64, 3), (1, 1023, 64, 3), (13, 1000, 64, 4),
+                                                     (10, 640, 64, 3), (12, 2048, 128, 4)])
+def test_fp64_accumulation(kernel, dim, threads, ctas):
+    mat = U(dim)
+    for kw in (dict(), dict(stop=1, eps=1e-6, max_iter=60)):
+        same_bits(emu.solve(mat, dim, kernel=kernel, threads=threads, ctas=ctas, acc64=True, **kw),
+                  expect(mat, sum_mode=oracle.SUM_CUDA_F64, **kw))
+
+
+def test_fp64_accumulation_rows_of_several_units_and_sharded():
+    mat = U(8200)
+    same_bits(emu.solve(mat, 8200, kernel=13, threads=128, ctas=6, acc64=True, max_iter=3),
+              expect(mat, sum_mode=oracle.SUM_CUDA_F64, max_iter=3))
+    mat = U(1000)
+    same_bits(emu.solve(mat, 1000, kernel=13, threads=64, ctas=2, world=3, acc64=True), expect(mat, sum_mode=oracle.SUM_CUDA_F64))

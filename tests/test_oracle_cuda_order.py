@@ -214,3 +214,57 @@ def test_bf16_storage_solve_is_an_fp32_solve_of_the_rounded_matrix():
     assert low[3] == same_matrix_fp32_order[3]
     assert abs(float(low[0]) - float(same_matrix_fp32_order[0])) <= 1e-5 * float(low[0])
     assert np.max(np.abs(low[1] / low[1].max() - same_matrix_fp32_order[1] / same_matrix_fp32_order[1].max())) <= 1e-4
+
+
+# ---- fp64 accumulation (opt-in extension; ST_ACC_F64 / SUM_CUDA_F64) -------------------------------------------
+def row_dot_cuda_order_f64_numpy(row, scale):
+    """SUM_CUDA's order with double accumulators: the product of two floats is exact in double, every add
+    rounds once in double, a chunk's sum is rounded to float once, chunk sums are added in float."""
+    n = row.shape[0]
+    vec = 4 if n % 4 == 0 else 1
+    total = None
+    for c0 in range(0, n, 8192):
+        clen = min(8192, n - c0)
+        nv = clen // vec
+        acc = np.zeros((32, 8), dtype=np.float64)
+        for b0 in range(0, nv, 256):
+            j = np.arange(b0, min(b0 + 256, nv))
+            lane, u = j % 32, (j // 32) % 8
+            for k in range(vec):
+                c = c0 + j * vec + k
+                acc[lane, u] = row[c].astype(np.float64) * scale[c].astype(np.float64) + acc[lane, u]
+        for s in (4, 2, 1):
+            acc[:, :s] = acc[:, :s] + acc[:, s:2 * s]
+        lanes = acc[:, 0].copy()
+        for o in (16, 8, 4, 2, 1):
+            lanes = lanes + lanes[np.arange(32) ^ o]
+        chunk = np.float32(lanes[0])
+        total = chunk if total is None else np.float32(total + chunk)
+    return np.float32(total)
+
+
+@pytest.mark.parametrize("dim", [1, 5, 100, 257, 1024, 8200, 16385])
+def test_fp64_accumulation_order_matches_the_numpy_restatement(dim):
+    rng = np.random.default_rng(dim)
+    rows = min(3, dim)
+    mat = np.zeros((dim, dim), dtype=np.float32)
+    mat[:rows] = (rng.random((rows, dim)) + 0.25).astype(np.float32)
+    got = oracle.sum_across_rows(mat, oracle.SUM_CUDA_F64)[:rows]
+    ones = np.ones(dim, dtype=np.float32)
+    want = np.array([row_dot_cuda_order_f64_numpy(mat[r], ones) for r in range(rows)], dtype=np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_fp64_accumulation_is_closer_to_the_exact_row_sums():
+    dim = 4096
+    mat = oracle.uniform(dim, 77)
+    exact = mat.astype(np.float64).sum(axis=1)
+    err32 = np.abs(oracle.sum_across_rows(mat, oracle.SUM_CUDA).astype(np.float64) - exact)
+    err64 = np.abs(oracle.sum_across_rows(mat, oracle.SUM_CUDA_F64).astype(np.float64) - exact)
+    assert err64.max() <= np.spacing(np.float32(exact.max())) / 2 * 1.0001      # correctly rounded row sums
+    assert err64.mean() < err32.mean()
+    # and the solve stays inside the reference tolerance of the fp32 one
+    H = oracle.hilbert(1024)
+    a = oracle.similarity_transform(H, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    b = oracle.similarity_transform(H, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_F64)
+    assert a[3] == b[3] == 13 and abs(float(a[0]) - float(b[0])) <= 1e-5 * float(a[0])

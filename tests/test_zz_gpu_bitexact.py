@@ -165,3 +165,35 @@ def test_relative_stop_with_nan_hits_the_cap_and_tuning_kernels_refuse_it(solver
         solver.solve_device(d, 1024, stop=7)                           # unknown mode
     info, _ = solver.solve_device(d, 1024)                             # the handle stays usable
     assert info.iter_count == 13
+
+
+# ---- ST_ACC_F64 (extension): fp64 accumulators, same order; same bits as the oracle's SUM_CUDA_F64 -----------
+from eigen_value_b200 import ACC_F64  # noqa: E402
+
+
+@pytest.mark.parametrize("dim", [3, 100, 512, 1000, 1023, 2048, 8192, 8200])
+def test_fp64_accumulation_is_bit_identical_to_the_oracle(solver, dim):
+    # resident-e kernel (N % 4 == 0; the on-chip cluster kernel is not built for it), general loop otherwise
+    mat = _matrix("uniform", dim) if dim > 3 else A3
+    d = solver.upload(mat)
+    info, vec = solver.solve_device(d, dim, accumulate=ACC_F64)
+    want = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_F64)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), (want[0], want[1], want[3]), f"fp64 accumulation {dim}")
+    base, _ = solver.solve_device(d, dim)
+    assert abs(float(info.eigen_val) - float(base.eigen_val)) <= 1e-5 * float(base.eigen_val)
+    if dim % 4 == 0 and dim <= 2048:
+        info, vec = solver.solve_device(d, dim, accumulate=ACC_F64, kernel=1, eps=1e-6, stop=STOP_RELATIVE, max_iter=60)
+        want = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_F64, eps=1e-6,
+                                           stop=oracle.STOP_RELATIVE, max_itr=60)
+        _assert_same_bits((info.eigen_val, vec, info.iter_count), (want[0], want[1], want[3]), f"fp64 + relative {dim}")
+
+
+def test_fp64_accumulation_refusals(solver):
+    d = solver.hilbert(256)
+    for bad in (dict(form=FORM_INPLACE), dict(kernel=2), dict(kernel=20), dict(kernel=11), dict(accumulate=5)):
+        kw = dict(accumulate=ACC_F64)
+        kw.update(bad)
+        with pytest.raises(Exception):
+            solver.solve_device(d, 256, **kw)
+    info, _ = solver.solve_device(d, 256, accumulate=ACC_F64)
+    assert info.iter_count == 10 and info.kernel_id == 13          # README.md:71; resident-e instead of the cluster kernel
