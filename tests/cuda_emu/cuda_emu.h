@@ -87,6 +87,39 @@ inline thread_local uint3 blockIdx{ 0, 0, 0 };
 inline thread_local dim3 blockDim;
 inline thread_local dim3 gridDim;
 
+// ---- fiber switch -------------------------------------------------------------------------------------------
+// Outside ThreadSanitizer builds a fiber switch is a dozen instructions (callee-saved registers + stack
+// pointer); ucontext's swapcontext costs two signal-mask system calls per switch, which dominated the
+// emulation.  TSan builds keep ucontext (TSan knows it).
+#if !EMU_TSAN && defined(__x86_64__)
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_switch(void** save_sp, void* next_sp);
+asm(R"(
+.text
+.weak emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#define EMU_FAST_SWITCH 0
+#endif
+
 namespace emu {
 
 constexpr size_t kStackBytes = 96 * 1024;
@@ -106,6 +139,8 @@ struct Cta
   unsigned index = 0, threads = 0;
   unsigned char* smem = nullptr; // dynamic shared memory
   std::vector<ucontext_t> ctx;
+  std::vector<void*> sp;  // fast switch: saved stack pointer per fiber
+  void* sched_sp = nullptr;
   std::vector<std::unique_ptr<unsigned char[]>> stacks;
   std::vector<char> done;
   ucontext_t sched;
@@ -139,7 +174,11 @@ to_scheduler(Cta* c)
 #if EMU_TSAN
   __tsan_switch_to_fiber(c->tsan_sched, __tsan_switch_to_fiber_no_sync);
 #endif
+#if EMU_FAST_SWITCH
+  emu_switch(&c->sp[c->current], c->sched_sp);
+#else
   swapcontext(&c->ctx[c->current], &c->sched);
+#endif
 }
 
 EMU_NO_TSAN inline void
@@ -170,6 +209,7 @@ fiber_entry()
   EMU_ACQUIRE(&c->threads); // kernel launch: the host's writes happen-before this thread
   c->body();
   fiber_exit(c);
+  abort(); // a finished fiber is never resumed
 }
 
 EMU_NO_TSAN inline void
@@ -179,10 +219,27 @@ run_cta(Cta* c, uint3 block_index, dim3 grid_dim)
   blockIdx = block_index;
   blockDim = dim3(c->threads);
   gridDim = grid_dim;
+#if !EMU_FAST_SWITCH
   c->ctx.resize(c->threads);
+#endif
   c->done.assign(c->threads, 0);
   c->warps.assign((c->threads + 31) / 32, WarpState{});
   c->live = c->threads;
+#if EMU_FAST_SWITCH
+  c->sp.resize(c->threads);
+  for (unsigned t = 0; t < c->threads; t++) {
+    c->stacks.emplace_back(new unsigned char[kStackBytes]);
+    // initial frame: six callee-saved register slots, then the "return address" emu_switch's ret jumps to;
+    // fiber_entry then starts with the stack alignment a call would have left (rsp % 16 == 8)
+    uintptr_t top = (reinterpret_cast<uintptr_t>(c->stacks.back().get()) + kStackBytes) & ~(uintptr_t)15;
+    void** frame = reinterpret_cast<void**>(top - 64);
+    for (int i = 0; i < 6; i++)
+      frame[i] = nullptr;
+    frame[6] = reinterpret_cast<void*>(&fiber_entry);
+    frame[7] = nullptr;
+    c->sp[t] = frame;
+  }
+#else
   for (unsigned t = 0; t < c->threads; t++) {
     c->stacks.emplace_back(new unsigned char[kStackBytes]);
     getcontext(&c->ctx[t]);
@@ -191,6 +248,7 @@ run_cta(Cta* c, uint3 block_index, dim3 grid_dim)
     c->ctx[t].uc_link = &c->sched;
     makecontext(&c->ctx[t], (void (*)())fiber_entry, 0);
   }
+#endif
 #if EMU_TSAN
   c->tsan_sched = __tsan_get_current_fiber();
   c->tsan_fiber.resize(c->threads);
@@ -207,7 +265,11 @@ run_cta(Cta* c, uint3 block_index, dim3 grid_dim)
 #if EMU_TSAN
       __tsan_switch_to_fiber(c->tsan_fiber[t], __tsan_switch_to_fiber_no_sync);
 #endif
+#if EMU_FAST_SWITCH
+      emu_switch(&c->sched_sp, c->sp[t]);
+#else
       swapcontext(&c->sched, &c->ctx[t]);
+#endif
     }
   }
   EMU_ACQUIRE(&c->live);
