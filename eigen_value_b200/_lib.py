@@ -68,6 +68,8 @@ SYMBOLS = {
     "st_memcpy_h2d": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "st_memcpy_d2h": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "st_synchronize": (ctypes.c_int, [_VP]),
+    "st_pin_host": (ctypes.c_int, [_VP, _VP, ctypes.c_size_t]),
+    "st_unpin_host": (ctypes.c_int, [_VP, _VP]),
     "st_generate_hilbert": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "st_generate_uniform": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                            ctypes.c_uint64]),

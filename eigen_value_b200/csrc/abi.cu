@@ -218,6 +218,30 @@ st_memcpy_d2h(void* ctx, void* hptr, const void* dptr, size_t bytes)
 }
 
 int
+st_pin_host(void* ctx, void* hptr, size_t bytes)
+{
+  return guarded([&] {
+    if (!hptr || bytes == 0)
+      throw std::invalid_argument("st_pin_host: bad argument");
+    as_ctx(ctx)->activate();
+    ABI_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterDefault));
+    return ST_OK;
+  });
+}
+
+int
+st_unpin_host(void* ctx, void* hptr)
+{
+  return guarded([&] {
+    if (!hptr)
+      throw std::invalid_argument("st_unpin_host: bad argument");
+    as_ctx(ctx)->activate();
+    ABI_CUDA(cudaHostUnregister(hptr));
+    return ST_OK;
+  });
+}
+
+int
 st_synchronize(void* ctx)
 {
   return guarded([&] {

@@ -44,6 +44,26 @@ class EigenValue:
             raise Exception("failed to get default CUDA device queue: "
                             + (err.decode() if err else "no GPU"))
 
+    def pinned(self, mat: np.ndarray):
+        """Context manager (extension): page-locks `mat` for the duration of the block, so that repeated
+        similarity_transform(mat) calls move it at full PCIe rate instead of through the driver's staging
+        buffers (st_pin_host / st_unpin_host).
+
+            with ev.pinned(mat):
+                lam, vec, ms, rounds = ev.similarity_transform(mat)
+        """
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            assert mat.flags["C_CONTIGUOUS"]
+            check(self.so_lib.st_pin_host(self.sycl_q, _ptr(mat), mat.nbytes), "st_pin_host")
+            try:
+                yield mat
+            finally:
+                check(self.so_lib.st_unpin_host(self.sycl_q, _ptr(mat)), "st_unpin_host")
+        return scope()
+
     def similarity_transform(self, mat: np.ndarray) -> Tuple[np.float32, np.ndarray, int, int]:
         """(max eigen value, eigen vector, loop milliseconds, iteration count) of a positive
         square float32 matrix; A v = lambda v holds to the reference's tolerance

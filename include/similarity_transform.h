@@ -151,6 +151,12 @@ int st_memcpy_h2d(void* ctx, void* dptr, const void* hptr, size_t bytes);
 int st_memcpy_d2h(void* ctx, void* hptr, const void* dptr, size_t bytes);
 int st_synchronize(void* ctx);
 
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so that max_eigen_value / st_solve_host /
+ * st_memcpy_* move it at full PCIe rate: a pageable 8192^2 matrix is staged by the driver at a fraction
+ * of the ~55 GB/s a pinned one reaches.  Pin once, solve many times, unpin before freeing the buffer. */
+int st_pin_host(void* ctx, void* hptr, size_t bytes);
+int st_unpin_host(void* ctx, void* hptr);
+
 /* Input generation on the device, rows [row0, row0+rows) of the dim x dim matrix written
  * to d_rows (rows x dim, row-major).
  * Hilbert: reference utils.cpp:136-154, A[r][c] = 1.f / (float)(r + c + 1).

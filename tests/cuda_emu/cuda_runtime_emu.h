@@ -178,6 +178,9 @@ cudaHostAlloc(T** p, size_t bytes, unsigned)
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+enum { cudaHostRegisterDefault = 0 };
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }

@@ -361,3 +361,19 @@ def test_cuda_matches_the_reference_own_outputs(ev, case):
     r_val, r_vec, r_it = _golden_expected(case)
     val, vec, ms, it = ev.similarity_transform(mat)
     assert_parity((val, vec, it), (r_val, r_vec, r_it), same_rounds=case["kind"] != "uniform")
+
+
+def test_pinning_the_callers_matrix_changes_nothing_but_the_transfer(ev):
+    # st_pin_host / st_unpin_host (extension): same result, the matrix is left untouched, and usable again after unpinning
+    mat = oracle.hilbert(1024)
+    keep = mat.copy()
+    base = ev.similarity_transform(mat)
+    with ev.pinned(mat):
+        for _ in range(2):
+            got = ev.similarity_transform(mat)
+            assert got[0] == base[0] and got[3] == base[3] == 13 and np.array_equal(got[1], base[1])
+    assert np.array_equal(mat, keep)
+    got = ev.similarity_transform(mat)
+    assert got[0] == base[0]
+    lib = ev.so_lib
+    assert lib.st_pin_host(ev.sycl_q, None, 16) != 0 and lib.st_unpin_host(ev.sycl_q, None) != 0
