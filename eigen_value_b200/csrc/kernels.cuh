@@ -16,6 +16,10 @@
 //   kernels_sc.cuh       N <= 32768  eigenvector resident in shared memory (the default)
 //   kernels_tma.cuh      tuning variant streaming the matrix through per-warp TMA rings
 //
+// Opt-in variants are template parameters, so the default instantiations stay exactly the measured
+// code: STOP (the reference's absolute stop test | relative), T (fp32 | bf16 STORAGE of the matrix),
+// ACC (fp32 | fp64 accumulators).  None of them changes the evaluation order.
+//
 // The small standalone kernels at the bottom are the per-kernel entry points mirroring the
 // reference's L1 functions (similarity_transform.cpp:77-460) and the input generators
 // (utils.cpp:136-154, :124-134).
