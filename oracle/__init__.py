@@ -107,13 +107,22 @@ def uniform(dim: int, seed: int, row0: int = 0, rows: int | None = None) -> np.n
 
 
 def to_bf16(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """fp32 -> bfloat16, round to nearest even (what cvt.rn.bf16.f32 / st_convert_f32_to_bf16 does for
-    finite inputs).  Returns (the rounded values widened back to fp32 -- exact --, the uint16 bit patterns)."""
+    """fp32 -> bfloat16, round to nearest even (what cvt.rn.bf16.f32 / st_convert_f32_to_bf16 does; NaN ->
+    0x7fff).  Returns (the rounded values widened back to fp32 -- exact --, the uint16 bit patterns).
+    Works in row blocks with 32-bit arithmetic so that a 40960^2 matrix costs its two outputs and little more."""
     a = np.ascontiguousarray(mat, dtype=np.float32)
-    u = a.view(np.uint32).astype(np.uint64)
-    rounded = (u + 0x7FFF + ((u >> 16) & 1)) >> 16            # ties to even on the kept bit
-    bits = rounded.astype(np.uint16)
-    back = (bits.astype(np.uint32) << 16).view(np.float32)
+    flat = a.reshape(-1)
+    bits = np.empty(flat.shape, dtype=np.uint16)
+    back = np.empty(flat.shape, dtype=np.float32)
+    step = 1 << 24
+    for i in range(0, flat.shape[0], step):
+        u = flat[i:i + step].view(np.uint32)
+        nan = (u & np.uint32(0x7FFFFFFF)) > np.uint32(0x7F800000)
+        # for every non-NaN value u + 0x8000 cannot wrap 32 bits; NaNs are patched afterwards
+        r = ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) >> np.uint32(16)).astype(np.uint16)
+        r[nan] = 0x7FFF
+        bits[i:i + step] = r
+        back[i:i + step] = (r.astype(np.uint32) << np.uint32(16)).view(np.float32)
     return back.reshape(a.shape), bits.reshape(a.shape)
 
 
