@@ -21,6 +21,12 @@ test:           ## CPU suite: oracle vs golden vectors / real reference, ABI, gl
 test-gpu:       ## parity through the C ABI on a B200
 	$(PY) -m pytest tests -x -q -m gpu
 
+test-emulated:  ## the -m gpu test files on the CPU, against the whole library built on the emulation harness
+	ST_EMULATED_LIB=1 ST_EMU_DEVICES=4 $(PY) -m pytest tests -q -m gpu
+
+racecheck:      ## the emulated round kernels under ThreadSanitizer (+ mutants that must be reported)
+	$(PY) -m pytest tests/test_kernel_racecheck_emulated.py -q
+
 run: bench      ## reference `make run` prints its benchmark table; here: one JSON line
 bench:
 	$(PY) bench.py
@@ -31,6 +37,7 @@ golden:         ## regenerate tests/golden/ from the reference (build container 
 
 clean:
 	rm -f eigen_value_b200/libsimilarity_transform.so tests/cpp/*.bin tools/stream_probe
+	rm -rf tests/cuda_emu/_build tests/cuda_emu/*.so tests/cuda_emu/*.bin
 	$(MAKE) -C oracle clean
 
-.PHONY: lib oracle ref build test test-gpu run bench golden clean
+.PHONY: lib oracle ref build test test-gpu test-emulated racecheck run bench golden clean
