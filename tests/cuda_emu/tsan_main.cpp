@@ -99,6 +99,7 @@ main(int argc, char** argv)
     { "TMA ring 6, 512", 512, with(6, 256, 2) },
     { "2 GPUs, general 200", 200, with(1, 64, 2, 2) },
     { "3 GPUs, resident-e 13 dynamic 320", 320, with(13, 64, 2, 3, 0, 0, 1) },
+    { "resident-e 13, fp64 accumulation, 320", 320, [&] { emu_opts o = with(13, 64, 3); o.acc64 = 1; return o; }() },
   };
   int failures = 0;
   for (const Case& c : cases) {
