@@ -54,9 +54,21 @@ DIMS = [1, 2, 3, 4, 5, 31, 33, 100, 128, 257, 512, 640, 1000, 1023, 1024, 2048, 
 @pytest.mark.parametrize("kind", ["hilbert", "uniform"])
 @pytest.mark.parametrize("dim", DIMS)
 def test_drop_in_boundary_is_bit_identical_to_the_oracle(ev, kind, dim):
+    if kind == "uniform" and dim > 4100:
+        # uniform matrices of this size never satisfy the reference's absolute stop test in fp32:
+        # 1000 rounds cost the CPU oracle minutes; they go through st_solve_device with a round cap below
+        pytest.skip("covered with a round cap by test_large_uniform_matrices_with_a_round_cap")
     mat = _matrix(kind, dim)
     val, vec, ms, it = ev.similarity_transform(mat)                     # make_queue + max_eigen_value
     _assert_same_bits((val, vec, it), _oracle(mat), f"{kind}-{dim}")
+
+
+@pytest.mark.parametrize("dim", [8192, 8196, 12288])
+def test_large_uniform_matrices_with_a_round_cap(solver, dim):
+    mat = _matrix("uniform", dim)
+    info, vec = solver.solve_device(solver.upload(mat), dim, max_iter=12)
+    assert info.iter_count == 12                                          # the absolute test cannot hold here
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=12), f"uniform-{dim} capped")
 
 
 def test_three_by_three_golden_bit_identical(ev):
@@ -176,10 +188,11 @@ def test_fp64_accumulation_is_bit_identical_to_the_oracle(solver, dim):
     # resident-e kernel (N % 4 == 0; the on-chip cluster kernel is not built for it), general loop otherwise
     mat = _matrix("uniform", dim) if dim > 3 else A3
     d = solver.upload(mat)
-    info, vec = solver.solve_device(d, dim, accumulate=ACC_F64)
-    want = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_F64)
+    cap = 12 if dim > 4100 else 1000                     # large uniform matrices never meet the absolute test
+    info, vec = solver.solve_device(d, dim, accumulate=ACC_F64, max_iter=cap)
+    want = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_F64, max_itr=cap)
     _assert_same_bits((info.eigen_val, vec, info.iter_count), (want[0], want[1], want[3]), f"fp64 accumulation {dim}")
-    base, _ = solver.solve_device(d, dim)
+    base, _ = solver.solve_device(d, dim, max_iter=cap)
     assert abs(float(info.eigen_val) - float(base.eigen_val)) <= 1e-5 * float(base.eigen_val)
     if dim % 4 == 0 and dim <= 2048:
         info, vec = solver.solve_device(d, dim, accumulate=ACC_F64, kernel=1, eps=1e-6, stop=STOP_RELATIVE, max_iter=60)

@@ -48,11 +48,14 @@ def test_bf16_storage_solve_is_bit_identical_to_the_oracle(solver, kind, dim):
     # resident-e kernel (configuration 11: no prefetch slots); 8200 / 16384: rows of two work units
     mat, rounded, bits = _case(kind, dim)
     d16 = solver.upload(bits)
-    info, vec = solver.solve_device(d16, dim, bf16=True)
+    # large uniform matrices never meet the reference's absolute stop test in fp32: cap the rounds
+    cap = 12 if (kind == "uniform" and dim > 4100) else 1000
+    info, vec = solver.solve_device(d16, dim, bf16=True, max_iter=cap)
     assert info.kernel_id == 11 and info.bytes_per_round == 2 * dim * dim
-    _same_bits(info, vec, oracle.similarity_transform(rounded, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_BF16))
+    _same_bits(info, vec, oracle.similarity_transform(rounded, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_BF16,
+                                                      max_itr=cap))
     # and close to the fp32-storage answer: the entries moved by <= 2^-9 relative
-    full, _ = solver.solve_device(solver.upload(mat), dim)
+    full, _ = solver.solve_device(solver.upload(mat), dim, max_iter=cap)
     assert abs(float(info.eigen_val) - float(full.eigen_val)) <= 2.0 ** -8 * float(full.eigen_val)
 
 
