@@ -9,7 +9,7 @@ if ROOT not in sys.path:
 
 
 EMULATED = os.environ.get("ST_EMULATED_LIB") == "1"
-EMU_MAX_DIM = int(os.environ.get("ST_EMU_MAX_DIM", "2100"))
+EMU_MAX_DIM = int(os.environ.get("ST_EMU_MAX_DIM", "4200"))
 
 
 def pytest_configure(config):
