@@ -65,7 +65,7 @@ env_int(const char* name, int fallback)
   return v && *v ? atoi(v) : fallback;
 }
 inline int devices() { return std::max(1, std::min(8, env_int("ST_EMU_DEVICES", 1))); }
-inline int sms() { return std::max(1, std::min(64, env_int("ST_EMU_SMS", 4))); }
+inline int sms() { return std::max(1, std::min(148, env_int("ST_EMU_SMS", 4))); }
 inline thread_local int current_device = 0;
 inline double
 now_ms()

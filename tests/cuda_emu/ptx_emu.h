@@ -101,6 +101,9 @@ mbar_try_wait(uint64_t* bar, uint32_t parity)
   const bool done = ((uint32_t)(*bar) & 1u) != parity; // the phase of that parity has completed
   if (done)
     EMU_ACQUIRE(bar); // the copied bytes are visible to the waiter
+  else
+    emu::yield(); // a polling lane must let the lane that issues the copy run (the hardware's independent
+                  // thread scheduling guarantees that progress; a cooperative fiber has to hand over)
   return done;
 }
 inline void

@@ -1,8 +1,8 @@
 """The `-m gpu` test files, run on the CPU against the WHOLE library built on the emulation harness.
 
 tests/cuda_emu/build.py::build_library compiles solver.cu + abi.cu + the kernels for the host on a
-pretend CUDA runtime (cuda_runtime_emu.h: device memory is host memory, launches are synchronous, a
-4-SM "device") into tests/cuda_emu/libsimilarity_transform_emu.so; with ST_EMULATED_LIB=1 tests/conftest.py
+pretend CUDA runtime (cuda_runtime_emu.h: device memory is host memory, launches are synchronous; the
+pretend device gets 148 SMs here, so Context::solve plans exactly the launch shapes it plans on a B200) into tests/cuda_emu/libsimilarity_transform_emu.so; with ST_EMULATED_LIB=1 tests/conftest.py
 points the Python binding at it for the test session.  So the C ABI, Context::solve's launch planning,
 the Python mirror and the GPU tests' own code are exercised where no GPU exists -- the same assertions
 the B200 box runs, on the small and medium cases (the emulated device is orders of magnitude slower).  TEST INFRASTRUCTURE: the
@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def run_emulated(args, max_dim=4200, timeout=1500):
-    env = dict(os.environ, ST_EMULATED_LIB="1", ST_EMU_MAX_DIM=str(max_dim), ST_EMU_DEVICES="4")
+    env = dict(os.environ, ST_EMULATED_LIB="1", ST_EMU_MAX_DIM=str(max_dim), ST_EMU_DEVICES="4", ST_EMU_SMS="148")
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", *args]
     return subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
 

@@ -88,6 +88,11 @@ def test_resident_rows_stay_in_the_prefetch_slot():
     same_bits(emu.solve(mat, 2048, kernel=10, threads=512, ctas=4), expect(mat))   # 64 warps >= ... not resident
     mat = oracle.hilbert(64)
     same_bits(emu.solve(mat, 64, kernel=13, threads=128, ctas=16), expect(mat))     # 64 warps, 64 one-unit rows: resident
+    # the shapes the B200 launch plan produces (512 threads; one row per warp): N = 128 on 8 CTAs, N = 1024 on 64 --
+    # lanes that reach the mbarrier wait before lane 0 has issued the copy must not starve it
+    for dim, ctas, kernel in ((128, 8, 13), (1024, 64, 13), (2048, 128, 10)):
+        mat = oracle.hilbert(dim)
+        same_bits(emu.solve(mat, dim, kernel=kernel, threads=512, ctas=ctas), expect(mat))
 
 
 @pytest.mark.parametrize("kernel,dynamic", [(13, 1), (13, 0), (11, 1), (1, -1), (9, -1)])
