@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--stop", default="absolute", choices=["absolute", "relative"],
                     help="absolute = the reference's stop test (default; the only one the headline is quoted on); "
                          "relative = extension, max adjacent diff < eps * max(s)")
+    ap.add_argument("--accumulate", default="f32", choices=["f32", "f64"],
+                    help="f32 = like the reference (default); f64 = opt-in fp64 accumulators, same evaluation order")
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
                     help="f32 = the reference's matrix format (default, the headline); bf16 = opt-in bfloat16 storage "
                          "of the matrix with fp32 accumulation (changes results; bytes counted at 2 per element)")
@@ -276,7 +278,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     solver = Solver(local_rank)
     opts = dict(max_iter=args.max_iter, form=args.form, sweep=args.sweep, threads=args.threads, ctas=args.ctas,
-                kernel=args.kernel, eps=args.eps, stop=1 if args.stop == "relative" else 0)
+                kernel=args.kernel, eps=args.eps, stop=1 if args.stop == "relative" else 0,
+                accumulate=1 if args.accumulate == "f64" else 0)
 
     def barrier():
         if world > 1:
@@ -451,7 +454,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "N": dim, "rows_per_gpu": rows, "form": "read-only" if args.form == 0 else "in-place",
-                       "eps": args.eps, "stop": args.stop, "max_iter": args.max_iter, "storage": args.storage,
+                       "eps": args.eps, "stop": args.stop, "max_iter": args.max_iter, "storage": args.storage, "accumulate": args.accumulate,
                        "sweep": 1 if args.sweep is None else args.sweep, "kernel": args.kernel,
                        "grid": last.grid,
                        "sharding": f"row-block x{world}, fused peer-store exchange" if world > 1 else "none",

@@ -28,4 +28,7 @@ for w in hilbert-8192 hilbert-32768; do
   timeout 600 python bench.py --workload $w --storage bf16 --steps 10 --no-cpu-baseline --no-sweep-table \
     > $O/first_call_bench_${w}_bf16.json 2>> $O/first_call_bench_n1.err
 done
+# fp64 accumulation: same bytes, two conversions and one DFMA per element -- does it still sit under the stream?
+timeout 600 python bench.py --workload hilbert-8192 --accumulate f64 --steps 10 --no-e2e --no-cpu-baseline --no-sweep-table \
+  > $O/first_call_bench_hilbert-8192_acc64.json 2>> $O/first_call_bench_n1.err
 tail -5 $O/first_call_tests.txt
