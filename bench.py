@@ -421,17 +421,19 @@ def main():
     table = None
     if world == 1 and not args.no_sweep_table:
         table = []
+        d_sweep_vec = solver.alloc(4 * 8192)      # not d_vec: the workload may be smaller than the sweep's sizes
         for n in (128, 256, 512, 1024, 2048, 4096, 8192):
             d = solver.hilbert(n)
             best = None
             for _ in range(4):
-                info, _ = solver.solve_device(d, n, d_eigen_vec=d_vec, **opts)
+                info, _ = solver.solve_device(d, n, d_eigen_vec=d_sweep_vec, **opts)
                 if best is None or info.loop_ms < best.loop_ms:
                     best = info
             table.append({"N": n, "rounds": best.iter_count, "ms_to_converge": round(best.loop_ms, 4),
                           "us_per_round": round(best.round_us_median, 2),
                           "l2_resident": 4 * n * n <= solver.l2_bytes})
             d.free()
+        d_sweep_vec.free()
 
     # ---- CPU baseline beside it (rank 0, N=1) ----
     cpu = None

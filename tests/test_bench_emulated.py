@@ -1,0 +1,47 @@
+"""bench.py's B200 arm, executed end to end on the emulated library (tests/cuda_emu/run_bench_emulated.py):
+the contract keys of the JSON line, the e2e leg through max_eigen_value, the Hilbert sweep table, the CPU
+baseline and the opt-in switches are exercised where no GPU exists.  Values are meaningless here."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNNER = os.path.join(ROOT, "tests", "cuda_emu", "run_bench_emulated.py")
+
+
+def run(*args, timeout=900):
+    proc = subprocess.run([sys.executable, RUNNER, *args], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                          text=True, timeout=timeout)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, proc.stdout[-2000:]                       # ONE JSON line
+    return json.loads(lines[0])
+
+
+def test_default_shape_of_the_line_with_e2e_sweep_table_and_cpu_baseline():
+    # a workload smaller than the sweep's largest size: the sweep must not reuse the workload's output vector
+    line = run("--workload", "hilbert-256", "--steps", "2", "--warmup", "1")
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["gpu_launches"] == 2
+    assert line["rounds"] == 10 and line["config"]["workload"] == "hilbert-256"           # reference README.md:71
+    assert line["config"]["stop"] == "absolute" and line["config"]["storage"] == "f32" and line["config"]["accumulate"] == "f32"
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 4 * 256 * 256 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert [r["rounds"] for r in line["hilbert_sweep"]] == [9, 10, 12, 13, 14, 15, 17]      # reference README.md:70-76
+
+
+@pytest.mark.parametrize("extra,rounds", [(("--stop", "relative", "--eps", "1e-6"), None), (("--storage", "bf16"), 13),
+                                          (("--accumulate", "f64"), 13)])
+def test_opt_in_switches(extra, rounds):
+    line = run("--workload", "hilbert-1024", "--steps", "2", "--no-cpu-baseline", "--no-sweep-table", *extra)
+    if rounds is not None:
+        assert line["rounds"] == rounds
+    if "--storage" in extra:
+        assert line["e2e"] is None and line["roofline"]["bytes_per_launch"] == line["passes_per_step"] * 2 * 1024 * 1024
+        assert "bf16 storage" in line["metric"]
