@@ -210,3 +210,20 @@ def test_fp64_accumulation_refusals(solver):
             solver.solve_device(d, 256, **kw)
     info, _ = solver.solve_device(d, 256, accumulate=ACC_F64)
     assert info.iter_count == 10 and info.kernel_id == 13          # README.md:71; resident-e instead of the cluster kernel
+
+
+def test_eigenvalues_printed_by_the_b200_in_round_1_are_reproduced(ev):
+    """profiles/r1_reference_format_table.txt was produced on a B200 in round 1 (tools/bench_table.py).  Seven decimals
+    identify one float32 in [2, 4): whatever runs this test -- the B200 again, or the emulated library on the CPU --
+    must print the same eigenvalues and round counts."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_reference_format_table.txt")
+    rows = re.findall(r"^(\d+)\s*x\s*\d+\s+[\d.]+ ms\s+(\d+) round\(s\)\s+max_eigen_value\(\):.*lambda = ([\d.]+)", open(path).read(), re.M)
+    assert len(rows) == 7
+    for n, rounds, lam in rows:
+        n = int(n)
+        if n > 2048:
+            continue                                          # kept cheap: the larger sizes are covered above
+        val, vec, ms, it = ev.similarity_transform(oracle.hilbert(n))
+        assert it == int(rounds) and "%.7f" % float(val) == lam, (n, it, float(val), lam)
