@@ -201,9 +201,52 @@ cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // ---- kernels ---------------------------------------------------------------------------------------------
+// The launch limits the planner has to respect on a B200 are enforced here too: dynamic shared memory
+// above 48 KB needs the opt-in attribute and can never exceed 227 KB, a CTA has at most 1024 threads, and a
+// cooperative grid must be co-resident (these kernels occupy a whole SM each).
+enum : int { cudaErrorCooperativeLaunchTooLarge = 720, cudaErrorInvalidConfiguration = 9 };
+namespace emu_rt {
+constexpr size_t kDefaultDynamicSmem = 48 * 1024, kMaxDynamicSmem = 227 * 1024;
+inline std::mutex& attr_mutex() { static std::mutex m; return m; }
+inline std::vector<std::pair<const void*, size_t>>& smem_optin() { static std::vector<std::pair<const void*, size_t>> v; return v; }
+inline size_t
+allowed_smem(const void* func)
+{
+  std::lock_guard<std::mutex> lock(attr_mutex());
+  for (auto& e : smem_optin())
+    if (e.first == func)
+      return e.second;
+  return kDefaultDynamicSmem;
+}
+inline cudaError_t
+check_launch(const void* func, dim3 grid, dim3 block, size_t smem, bool cooperative)
+{
+  if (block.x == 0 || block.x > 1024 || grid.x == 0)
+    return cudaErrorInvalidConfiguration;
+  if (smem > allowed_smem(func))
+    return cudaErrorInvalidValue;
+  if (cooperative && grid.x * grid.y * grid.z > (unsigned)sms())
+    return cudaErrorCooperativeLaunchTooLarge;
+  return cudaSuccess;
+}
+} // namespace emu_rt
 inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, const void*) { a->numRegs = 0; a->sharedSizeBytes = 0; return cudaSuccess; }
 template<typename K>
-inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t
+cudaFuncSetAttribute(K func, cudaFuncAttribute, int value)
+{
+  if (value < 0 || (size_t)value > emu_rt::kMaxDynamicSmem)
+    return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lock(emu_rt::attr_mutex());
+  const void* key = reinterpret_cast<const void*>(func);
+  for (auto& e : emu_rt::smem_optin())
+    if (e.first == key) {
+      e.second = (size_t)value;
+      return cudaSuccess;
+    }
+  emu_rt::smem_optin().emplace_back(key, (size_t)value);
+  return cudaSuccess;
+}
 
 namespace st { struct RoundParams; }
 // every cooperative kernel of this library takes one `const RoundParams` argument
@@ -211,12 +254,16 @@ cudaError_t emu_launch_round_kernel(const void* func, dim3 grid, dim3 block, voi
 inline cudaError_t
 cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t)
 {
-  return emu_launch_round_kernel(func, grid, block, args, smem);
+  const cudaError_t e = emu_rt::check_launch(func, grid, block, smem, true);
+  return e != cudaSuccess ? e : emu_launch_round_kernel(func, grid, block, args, smem);
 }
 template<typename P>
 inline cudaError_t
 cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(const P), P params)
 {
+  const cudaError_t e = emu_rt::check_launch(reinterpret_cast<const void*>(kernel), cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, false);
+  if (e != cudaSuccess || cfg->gridDim.x > 8) // portable cluster size
+    return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
   auto g = emu::launch_async<P>(kernel, cfg->gridDim.x, cfg->blockDim.x, cfg->dynamicSmemBytes, params); // cluster == grid
   emu::join(*g);
   return cudaSuccess;
