@@ -27,6 +27,13 @@ def pytest_configure(config):
         _lib._build.stale = lambda: False
 
 
+def pytest_report_header(config):
+    if EMULATED:
+        return ("*** ST_EMULATED_LIB=1: the `-m gpu` tests of this session run on the CPU EMULATION of the library "
+                "(tests/cuda_emu), NOT on a GPU -- results say nothing about hardware ***")
+    return None
+
+
 def _have_gpu() -> bool:
     try:
         from eigen_value_b200 import _lib
