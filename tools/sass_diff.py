@@ -35,14 +35,30 @@ def split(path):
     return funcs
 
 
+def digest(funcs):
+    import hashlib
+    return {name: {"instructions": len(body), "sha256": hashlib.sha256("\n".join(body).encode()).hexdigest()}
+            for name, body in funcs.items()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("before")
-    ap.add_argument("after")
+    ap.add_argument("after", nargs="?")
+    ap.add_argument("--write-digest", default=None,
+                    help="write {kernel: sha256 of its instruction stream} of `before` to this JSON file and exit "
+                         "(refreshes profiles/r1_measured_kernels_sass_digest.json after a re-measurement)")
     ap.add_argument("--append-arg", default=None,
                     help="mangled template argument(s) appended to kernels taking RoundParams, e.g. Li0E; "
                          "several alternatives separated by commas (Li0E,Li0Ef)")
     args = ap.parse_args()
+    if args.write_digest:
+        import json
+        with open(args.write_digest, "w") as f:
+            json.dump({"kernels": digest(split(args.before))}, f, indent=1, sort_keys=True)
+        return 0
+    if not args.after:
+        ap.error("two SASS dumps are needed for a comparison")
     b, a = split(args.before), split(args.after)
     bad = 0
     for name, body in b.items():
