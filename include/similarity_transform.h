@@ -217,7 +217,9 @@ int st_stop(void* ctx, const float* d_vec, uint32_t* d_ret, uint32_t dim, float 
  *   st_shard_export  writes its 64-byte CUDA IPC handle (ship it to the peers with any
  *                    host-side transport, e.g. torch.distributed all_gather)
  *   st_shard_import  opens the world x 64-byte handle table, in rank order
- *   st_shard_solve   collective: every rank calls it with its own rows */
+ *   st_shard_solve   collective: every rank calls it with its own rows.  If a rank does not show up, the others
+ *                    return ST_ERR_TIMEOUT after the device-side timeout (10 s) instead of hanging; the group's
+ *                    solve counters have then diverged, so destroy the shards of every rank and create new ones. */
 #define ST_IPC_HANDLE_BYTES 64
 #define ST_MAX_WORLD 8
 int st_shard_create(void* ctx, uint32_t dim, uint32_t rank, uint32_t world, void** shard);

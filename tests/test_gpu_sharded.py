@@ -114,3 +114,61 @@ def test_in_process_sharded_solve_with_local_link(world):
         lib.st_shard_destroy(sh)
     for s in solvers:
         s.close()
+
+
+def test_missing_peer_turns_into_a_timeout_error_not_a_hang():
+    """Two linked shards, only rank 0 calls the collective solve: its round barrier waits for rank 1's flag, gives up
+    after the device-side timeout (10 s) and the call returns ST_ERR_TIMEOUT -- no hang, no crash.  The shard group is
+    desynchronised afterwards (its epochs differ) and has to be recreated; a fresh group on the same contexts works."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs in one process")
+    import ctypes
+    import threading
+    import time
+    from eigen_value_b200 import Solver
+    from eigen_value_b200._lib import StResult, check
+
+    dim = 256
+    solvers = [Solver(0), Solver(1)]
+    lib = solvers[0].lib
+
+    def make_group():
+        shards = []
+        for g in range(2):
+            sh = ctypes.c_void_p()
+            check(lib.st_shard_create(solvers[g].ctx, dim, g, 2, ctypes.byref(sh)), "st_shard_create")
+            shards.append(sh)
+        check(lib.st_shard_link_local((ctypes.c_void_p * 2)(*[s.value for s in shards]), 2), "st_shard_link_local")
+        return shards
+
+    rows = [solvers[g].hilbert(dim, g * 128, 128) for g in range(2)]
+    shards = make_group()
+    res, vec = StResult(), solvers[0].alloc(4 * dim)
+    t0 = time.time()
+    rc = lib.st_shard_solve(shards[0], rows[0].ptr, None, vec.ptr, ctypes.byref(res))      # rank 1 never shows up
+    waited = time.time() - t0
+    assert rc == -4 and b"timed out" in lib.st_last_error(), (rc, lib.st_last_error())          # ST_ERR_TIMEOUT
+    assert 5 < waited < 60, waited
+    for sh in shards:
+        lib.st_shard_destroy(sh)
+
+    shards = make_group()                                                                   # recreate: works again
+    out = [None, None]
+
+    def work(g):
+        r, v = StResult(), solvers[g].alloc(4 * dim)
+        rc = lib.st_shard_solve(shards[g], rows[g].ptr, None, v.ptr, ctypes.byref(r))
+        out[g] = (rc, r.iter_count, v.download(np.float32, dim) if rc == 0 else None)
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    o_val, o_vec, _, o_it = oracle.similarity_transform(oracle.hilbert(dim), form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    assert out[0][0] == 0 and out[1][0] == 0 and out[0][1] == out[1][1] == o_it == 10       # README.md:71
+    assert np.array_equal(out[0][2], o_vec) and np.array_equal(out[1][2], o_vec)
+    for sh in shards:
+        lib.st_shard_destroy(sh)
+    for s in solvers:
+        s.close()
