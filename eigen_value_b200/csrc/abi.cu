@@ -25,6 +25,9 @@ guarded(F&& f) noexcept
   } catch (const std::invalid_argument& e) {
     st::set_last_error(e.what());
     return ST_ERR_ARG;
+  } catch (const st::OutOfDeviceMemory& e) {
+    st::set_last_error(e.what());
+    return ST_ERR_NOMEM;
   } catch (const std::bad_alloc&) {
     st::set_last_error("host allocation failed");
     return ST_ERR_NOMEM;
@@ -43,6 +46,10 @@ guarded(F&& f) noexcept
     if (e_ != cudaSuccess) {                                                                       \
       char buf_[512];                                                                              \
       snprintf(buf_, sizeof buf_, "%s failed: %s", #call, cudaGetErrorString(e_));                 \
+      if (e_ == cudaErrorMemoryAllocation) {                                                       \
+        (void)cudaGetLastError();                                                                  \
+        throw st::OutOfDeviceMemory(buf_);                                                         \
+      }                                                                                            \
       throw std::runtime_error(buf_);                                                              \
     }                                                                                              \
   } while (0)
@@ -474,6 +481,9 @@ st_shard_create(void* ctx, uint32_t dim, uint32_t rank, uint32_t world, void** s
     cudaError_t e = cudaMalloc(&s->block, s->block_bytes);
     if (e != cudaSuccess) {
       delete s;
+      (void)cudaGetLastError();
+      if (e == cudaErrorMemoryAllocation)
+        throw st::OutOfDeviceMemory(std::string("cudaMalloc(exchange block): ") + cudaGetErrorString(e));
       throw std::runtime_error(std::string("cudaMalloc(exchange block): ") + cudaGetErrorString(e));
     }
     ABI_CUDA(cudaMemset(s->block, 0, s->block_bytes));

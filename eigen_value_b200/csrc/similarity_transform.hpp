@@ -11,6 +11,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -147,4 +148,9 @@ int convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t 
 namespace st {
 void set_last_error(const std::string& msg);
 const char* last_error();
+// thrown when a device allocation fails; the C ABI turns it into ST_ERR_NOMEM
+struct OutOfDeviceMemory : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
 } // namespace st

@@ -59,6 +59,10 @@ struct CudaError : std::runtime_error
       char buf_[512];                                                                              \
       snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),          \
                __FILE__, __LINE__);                                                                \
+      if (e_ == cudaErrorMemoryAllocation) {                                                       \
+        (void)cudaGetLastError(); /* not sticky: the context stays usable */                        \
+        throw ::st::OutOfDeviceMemory(buf_);                                                       \
+      }                                                                                            \
       throw ::st::CudaError(buf_);                                                                 \
     }                                                                                              \
   } while (0)

@@ -163,6 +163,11 @@ template<typename T>
 inline cudaError_t
 cudaMalloc(T** p, size_t bytes)
 {
+  // the pretend device has ST_EMU_HBM_MIB of memory per allocation: larger requests fail like a full GPU would
+  if (bytes > ((size_t)emu_rt::env_int("ST_EMU_HBM_MIB", 4096) << 20)) {
+    *p = nullptr;
+    return cudaErrorMemoryAllocation;
+  }
   *p = static_cast<T*>(aligned_alloc(256, (bytes + 255) / 256 * 256 + 256));
   if (!*p)
     return cudaErrorMemoryAllocation;

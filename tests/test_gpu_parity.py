@@ -377,3 +377,15 @@ def test_pinning_the_callers_matrix_changes_nothing_but_the_transfer(ev):
     assert got[0] == base[0]
     lib = ev.so_lib
     assert lib.st_pin_host(ev.sycl_q, None, 16) != 0 and lib.st_unpin_host(ev.sycl_q, None) != 0
+
+
+def test_device_out_of_memory_is_reported_as_nomem_and_the_handle_survives(solver):
+    # a matrix far beyond the device's memory (dim^2 * 4 B = 4 TiB): st_malloc must fail with ST_ERR_NOMEM, not crash,
+    # and the context must stay usable (an allocation failure is not a sticky CUDA error)
+    import ctypes
+    lib = solver.lib
+    p = ctypes.c_void_p()
+    rc = lib.st_malloc(solver.ctx, 4 << 40, ctypes.byref(p))
+    assert rc == -5 and b"memory" in lib.st_last_error().lower(), (rc, lib.st_last_error())      # ST_ERR_NOMEM
+    info, _ = solver.solve_device(solver.hilbert(256), 256)
+    assert info.iter_count == 10
