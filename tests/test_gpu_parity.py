@@ -389,3 +389,25 @@ def test_device_out_of_memory_is_reported_as_nomem_and_the_handle_survives(solve
     assert rc == -5 and b"memory" in lib.st_last_error().lower(), (rc, lib.st_last_error())      # ST_ERR_NOMEM
     info, _ = solver.solve_device(solver.hilbert(256), 256)
     assert info.iter_count == 10
+
+
+def test_concurrent_callers_on_one_handle_are_serialised(ev):
+    """ctypes releases the GIL, so Python threads can enter max_eigen_value on ONE handle at the same time (the
+    reference is re-entrant by accident, SURVEY 8(b) "Threading").  The handle serialises them; every caller gets
+    its own correct result."""
+    import threading
+    mats = [oracle.hilbert(n) for n in (128, 256, 384, 512, 640, 1000)]
+    want = [oracle.similarity_transform(m, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA) for m in mats]
+    out = [None] * len(mats)
+
+    def work(i):
+        for _ in range(3):
+            out[i] = ev.similarity_transform(mats[i])
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(mats))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for got, w in zip(out, want):
+        assert got is not None and got[3] == w[3] and got[0] == w[0] and np.array_equal(got[1], w[1])
