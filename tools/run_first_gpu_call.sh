@@ -13,7 +13,7 @@ O=gpurun_out
   timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
   echo "== bit-exact + relative-stop tests (new)"
   timeout 900 python -m pytest tests/test_zz_gpu_bitexact.py -q -x 2>&1 | tail -15
-  echo "== bf16 storage tests (new; xfail(strict=False) until green: look for XPASS)"
+  echo "== bf16 storage tests (new; passed on hardware at the end of round 1)"
   timeout 900 python -m pytest tests/test_zzz_gpu_bf16_storage.py -q -rxX 2>&1 | tail -30
   echo "== full gpu suite"
   timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8
