@@ -49,6 +49,20 @@ class StResult(ctypes.Structure):
     ]
 
 
+class StStreamPlan(ctypes.Structure):
+    """st_stream_plan (include/similarity_transform.h)."""
+    _fields_ = [
+        ("block_rows", ctypes.c_uint32),
+        ("blocks", ctypes.c_uint32),
+        ("slots", ctypes.c_uint32),
+        ("streamed", ctypes.c_uint32),
+        ("cache_bytes", ctypes.c_uint64),
+        ("h2d_bytes_first", ctypes.c_uint64),
+        ("h2d_bytes_per_round", ctypes.c_uint64),
+        ("h2d_bytes_total", ctypes.c_uint64),
+    ]
+
+
 # every symbol include/similarity_transform.h declares: name -> (restype, argtypes)
 _VP = ctypes.c_void_p
 SYMBOLS = {
@@ -77,6 +91,12 @@ SYMBOLS = {
                                        ctypes.POINTER(StResult)]),
     "st_solve_host": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP, _VP,
                                      ctypes.POINTER(StResult)]),
+    "st_solve_streamed": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), ctypes.c_size_t,
+                                         ctypes.c_uint32, _VP, _VP, ctypes.POINTER(StResult),
+                                         ctypes.POINTER(StStreamPlan)]),
+    "st_solve_file": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(StOptions),
+                                     ctypes.c_size_t, ctypes.c_uint32, _VP, _VP, ctypes.POINTER(StResult),
+                                     ctypes.POINTER(StStreamPlan)]),
     "st_convert_f32_to_bf16": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "st_solve_device_bf16": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP,
                                             ctypes.POINTER(StResult)]),

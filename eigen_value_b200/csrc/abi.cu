@@ -4,10 +4,17 @@
 // of the CUDA solver; Part 2 is the additive st_* surface.  Nothing throws across this file.
 #include "similarity_transform.hpp"
 
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <stdexcept>
+#include <string>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cuda_runtime.h>
 
@@ -309,6 +316,72 @@ st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt
       st_default_options(&o);
     std::lock_guard<std::mutex> lock(c->mutex());
     return c->solve_host(h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
+  });
+}
+
+int
+st_solve_streamed(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt, size_t device_budget,
+                  uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec, st_result* res, st_stream_plan* plan)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve_streamed(h_mat, dim, o, device_budget, block_rows, h_eigen_val, h_eigen_vec, res, plan);
+  });
+}
+
+namespace {
+// read-only mapping of a file range, released on every path out of st_solve_file
+struct FileMapping
+{
+  int fd = -1;
+  void* base = MAP_FAILED;
+  size_t length = 0;
+  ~FileMapping()
+  {
+    if (base != MAP_FAILED)
+      munmap(base, length);
+    if (fd >= 0)
+      close(fd);
+  }
+};
+} // namespace
+
+int
+st_solve_file(void* ctx, const char* path, uint64_t offset, uint32_t dim, const st_options* opt, size_t device_budget,
+              uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec, st_result* res, st_stream_plan* plan)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    if (!path || dim == 0 || offset % sizeof(float) != 0)
+      throw std::invalid_argument("st_solve_file: null path, dim == 0 or an offset that is not a multiple of 4");
+    const uint64_t need = (uint64_t)dim * dim * sizeof(float);
+    FileMapping m;
+    m.fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (m.fd < 0)
+      throw std::invalid_argument(std::string("st_solve_file: cannot open ") + path + ": " + strerror(errno));
+    struct stat sb{};
+    if (fstat(m.fd, &sb) != 0 || (uint64_t)sb.st_size < offset + need)
+      throw std::invalid_argument(std::string("st_solve_file: ") + path + " is shorter than offset + 4 * dim * dim bytes");
+    const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+    const uint64_t start = offset / page * page;
+    m.length = (size_t)(offset - start + need);
+    m.base = mmap(nullptr, m.length, PROT_READ, MAP_PRIVATE, m.fd, (off_t)start);
+    if (m.base == MAP_FAILED)
+      throw std::runtime_error(std::string("st_solve_file: mmap failed: ") + strerror(errno));
+    const float* mat = reinterpret_cast<const float*>(static_cast<const char*>(m.base) + (offset - start));
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve_streamed(mat, dim, o, device_budget, block_rows, h_eigen_val, h_eigen_vec, res, plan);
   });
 }
 

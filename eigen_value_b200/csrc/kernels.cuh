@@ -903,6 +903,73 @@ fill_u32_kernel(uint32_t* __restrict__ v, uint32_t value, uint32_t n)
     v[r] = value;
 }
 
+// Vector tail of one HOST-DRIVEN round (the streamed solve, Context::solve_streamed: the matrix does
+// not fit the device, so the round loop cannot live in one kernel).  Two small grid-wide kernels do what
+// the fused kernels' tail does, with the same order-independent reductions:
+//   tail_scan_kernel    cells[0] <- bits of m = max(0, max_r s[r])                    reference :154-227
+//                       cells[1] <- absolute stop: 1 iff every circular pair differs by < eps (:413-421)
+//                                   relative stop: bits of the largest circular adjacent difference
+//   tail_update_kernel  e[r] *= s[r] / m (:260); block 0 publishes out[0] = converged, out[1] = bits of s[0]
+// The host presets cells[0] = 0 and cells[1] = (absolute ? 1 : 0) before the scan.  Non-negative floats
+// (and the NaN of a difference) order like their bit patterns, so integer atomicMax combines the blocks.
+__global__ void __launch_bounds__(1024) tail_scan_kernel(const float* __restrict__ vec, uint32_t dim, float eps,
+                                                         int stop_kind, uint32_t* __restrict__ cells)
+{
+  __shared__ float red_max[32];
+  __shared__ uint32_t red_bits[32];
+  float mx = 0.f;
+  int ok = 1;
+  uint32_t dbits = 0u;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x) {
+    const float self = vec[c];
+    const float next = vec[c + 1u == dim ? 0u : c + 1u];
+    mx = fmaxf(mx, self);
+    if (stop_kind == kStopRelative)
+      dbits = max(dbits, diff_bits(self, next));
+    else
+      ok &= (fabsf(self - next) < eps) ? 1 : 0;
+  }
+  uint32_t word = stop_kind == kStopRelative ? dbits : (uint32_t)(ok ? 0 : 1); // max-combinable: 1 = a pair failed
+  for (int o = 16; o >= 1; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    word = max(word, (uint32_t)__shfl_xor_sync(0xffffffffu, word, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_max[threadIdx.x >> 5] = mx;
+    red_bits[threadIdx.x >> 5] = word;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool live = threadIdx.x < (blockDim.x >> 5);
+    mx = live ? red_max[threadIdx.x] : 0.f;
+    word = live ? red_bits[threadIdx.x] : 0u;
+    for (int o = 16; o >= 1; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      word = max(word, (uint32_t)__shfl_xor_sync(0xffffffffu, word, o));
+    }
+    if (threadIdx.x == 0) {
+      atomicMax(reinterpret_cast<int*>(cells), __float_as_int(mx));
+      if (stop_kind == kStopRelative)
+        atomicMax(reinterpret_cast<int*>(cells + 1), (int)word);
+      else if (word)
+        atomicAnd(cells + 1, 0u);
+    }
+  }
+}
+
+__global__ void
+tail_update_kernel(const float* __restrict__ vec, float* __restrict__ eigen_vec, uint32_t dim, float eps,
+                   int stop_kind, const uint32_t* __restrict__ cells, uint32_t* __restrict__ out)
+{
+  const float m = __uint_as_float(cells[0]);
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < dim; r += gridDim.x * blockDim.x)
+    eigen_vec[r] *= (vec[r] / m);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = stop_kind == kStopRelative ? (__uint_as_float(cells[1]) < eps * m ? 1u : 0u) : cells[1];
+    out[1] = __float_as_uint(vec[0]);
+  }
+}
+
 // compute_next_matrix()  reference :286-330: W[r][c] *= (1.f / s[r]) * s[c]
 template<int VEC>
 __global__ void __launch_bounds__(256) compute_next_matrix_kernel(float* __restrict__ mat,

@@ -53,6 +53,11 @@ public:
             float* d_eigen_vec, st_result* res, bool bf16 = false);
   int solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
                  float* h_eigen_vec, st_result* res);
+  // Host matrix larger than the device (or than `device_budget`): block cache + alternating sweep,
+  // host-driven rounds (include/similarity_transform.h, st_solve_streamed).
+  int solve_streamed(const float* h_mat, uint32_t dim, const st_options& opt, size_t device_budget,
+                     uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec, st_result* res,
+                     st_stream_plan* plan);
   const std::vector<uint64_t>& round_timestamps() const { return last_ts_; }
   const std::vector<uint64_t>& phase_timestamps() const { return last_phase_ts_; }
 
@@ -93,6 +98,9 @@ private:
   float* d_work_ = nullptr; // in-place working copy
   size_t work_cap_ = 0;
   void* h_pinned_ = nullptr; // small pinned read-back block
+  // streamed solve: copy stream and two events per cache slot (block landed / block consumed)
+  CUstream_st* copy_stream_ = nullptr;
+  std::vector<CUevent_st*> slot_ready_, slot_free_;
   std::vector<uint64_t> last_ts_;
   std::vector<uint64_t> last_phase_ts_;
 };

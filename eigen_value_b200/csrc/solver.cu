@@ -127,6 +127,12 @@ Context::~Context()
   cudaFree(d_mat_);
   cudaFree(d_work_);
   cudaFreeHost(h_pinned_);
+  for (cudaEvent_t e : slot_ready_)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : slot_free_)
+    cudaEventDestroy(e);
+  if (copy_stream_)
+    cudaStreamDestroy(copy_stream_);
   cudaEventDestroy(ev0_);
   cudaEventDestroy(ev1_);
   cudaEventDestroy(ev_timer_[0]);
@@ -899,5 +905,223 @@ generate_uniform_matrix(st::Context& q, float* d_rows, const uint dim, uint64_t 
   const int grid = (int)std::min<size_t>((blocks4 + 255) / 256, (size_t)q.sm_count() * 16);
   ST_LAUNCH_ELEMENTWISE(uniform_kernel, std::max(1, grid), 256, 0, q.stream(), d_rows, dim, row0, rows, seed);
   ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+// =============================================================================================
+// streamed solve: host matrix larger than the device cache (include/similarity_transform.h)
+// =============================================================================================
+// The reference copies the whole matrix to the device before its loop (similarity_transform.cpp:14-19);
+// when it does not fit, this keeps `slots` row blocks in a direct-mapped device cache (block b <-> slot
+// b % slots) and sweeps the blocks in alternating direction, so each round starts on the blocks the last
+// one ended on.  Per round: the cached blocks are reduced from HBM in contiguous runs, the others are
+// copied on copy_stream_ (each copy waits for the pass that last read its slot) and reduced as they land.
+// One round = row passes (sum_across_rows_kernel, the fused kernels' evaluation order) + tail_scan_kernel
+// + tail_update_kernel + an 8-byte read-back; the host decides about the next round like the reference's
+// host loop does (:44-50).
+namespace {
+constexpr uint32_t kStreamedKernelId = 30;
+constexpr size_t kStreamBlockBytes = 64ull << 20;   // automatic block size
+constexpr size_t kStreamHitRunBytes = 1024ull << 20; // cached blocks are reduced in runs of at most this
+constexpr size_t kStreamReserveBytes = 1024ull << 20; // left free when the budget is taken from cudaMemGetInfo
+} // namespace
+
+int
+st::Context::solve_streamed(const float* h_mat, uint32_t dim, const st_options& opt, size_t device_budget,
+                            uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec, st_result* res,
+                            st_stream_plan* plan)
+{
+  if (!h_mat || dim == 0 || opt.max_iter == 0 || !(opt.eps >= 0.f))
+    throw std::invalid_argument("solve_streamed: bad argument");
+  if (opt.form != ST_FORM_READONLY || opt.accumulate != ST_ACC_F32)
+    throw std::invalid_argument("solve_streamed: read-only form and fp32 accumulation only");
+  if (opt.stop != ST_STOP_ABSOLUTE && opt.stop != ST_STOP_RELATIVE)
+    throw std::invalid_argument("solve_streamed: unknown st_options.stop");
+  const int stop_kind = opt.stop == ST_STOP_RELATIVE ? kStopRelative : kStopAbsolute;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  activate();
+  const size_t row_bytes = sizeof(float) * (size_t)dim;
+  const uint64_t mat_bytes = (uint64_t)row_bytes * dim;
+  if (plan)
+    memset(plan, 0, sizeof *plan);
+
+  size_t budget = device_budget;
+  if (budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    ST_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = free_b + sizeof(float) * mat_cap_; // the staging buffer is reused for the cache
+    budget = avail > kStreamReserveBytes ? avail - kStreamReserveBytes : 0;
+    if (mat_bytes <= budget) { // it fits: the fused device-side loop is the better path
+      const int rc = solve_host(h_mat, dim, opt, h_eigen_val, h_eigen_vec, res);
+      if (plan && rc == ST_OK) {
+        plan->block_rows = dim;
+        plan->blocks = plan->slots = 1;
+        plan->cache_bytes = plan->h2d_bytes_first = plan->h2d_bytes_total = mat_bytes;
+      }
+      return rc;
+    }
+  }
+
+  // ---- plan: rows per block, blocks, cache slots ----
+  uint32_t B = block_rows ? std::min(block_rows, dim)
+                          : (uint32_t)std::max<size_t>(1, std::min<size_t>(dim, kStreamBlockBytes / row_bytes));
+  if (!block_rows)
+    while (B > 1 && budget / (row_bytes * B) < 2)
+      B = (B + 1) / 2;
+  const uint32_t nb = (dim + B - 1) / B;
+  const size_t block_bytes = row_bytes * B;
+  const uint64_t fit = budget / block_bytes;
+  if (fit < 2 && nb > 1)
+    throw std::invalid_argument("solve_streamed: the device budget holds fewer than two row blocks");
+  const uint32_t C = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(fit, 1));
+  reserve_matrix((size_t)C * B * dim);
+  reserve_vectors(dim, opt.max_iter);
+  if (!copy_stream_)
+    ST_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  while (slot_ready_.size() < C) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ST_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    slot_ready_.push_back(a);
+    ST_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    slot_free_.push_back(b);
+  }
+
+  float* S = d_vec_;
+  float* E = d_vec_ + 2 * (size_t)vec_cap_;
+  uint32_t* cells = reinterpret_cast<uint32_t*>(d_scalars_) + 8; // [0] max bits, [1] stop evidence
+  uint32_t* d_out = cells + 2;                                   // [0] converged, [1] bits of s[0]
+  volatile uint32_t* h_out = reinterpret_cast<volatile uint32_t*>(h_pinned_) + 8;
+  const int tail_scan_grid = blocks_for(dim, 1024, 4 * sm_count_);
+  const int tail_update_grid = blocks_for(dim, 256, 4 * sm_count_);
+
+  auto block_rows_of = [&](uint32_t b) { return std::min(B, dim - b * B); };
+  auto slot_ptr = [&](uint32_t slot) { return d_mat_ + (size_t)slot * B * dim; };
+
+  std::vector<int64_t> slot_block(C, -1);
+  std::vector<char> slot_used(C, 0);
+  uint64_t h2d_first = 0, h2d_last = 0, h2d_total = 0;
+  uint32_t launches = 0, passes = 0, it = opt.max_iter;
+  float lambda = 0.f;
+  std::vector<float> round_us;
+
+  ST_CUDA(cudaEventRecord(ev0_, stream_));
+  initialise_eigen_vector(*this, E, dim); // reference :34 -> :280
+  launches++;
+  for (uint32_t k = 0; k < opt.max_iter; ++k) {
+    const auto r0 = std::chrono::steady_clock::now();
+    const bool backward = (k & 1u) != 0;
+    uint64_t copied = 0;
+    // cached blocks adjacent in the sweep form one run = one launch over rows that are contiguous
+    // both in the matrix and in the cache
+    bool run_open = false;
+    uint32_t run_lo = 0, run_hi = 0;
+    auto flush_run = [&] {
+      if (!run_open)
+        return;
+      const uint32_t row0 = run_lo * B;
+      const uint32_t rows = std::min(dim, (run_hi + 1) * B) - row0;
+      launch_row_pass(*this, slot_ptr(run_lo % C), E, S, dim, row0, rows);
+      launches++;
+      for (uint32_t b = run_lo; b <= run_hi; b++)
+        ST_CUDA(cudaEventRecord(slot_free_[b % C], stream_));
+      run_open = false;
+    };
+    for (uint32_t j = 0; j < nb; j++) {
+      const uint32_t b = backward ? nb - 1 - j : j;
+      const uint32_t slot = b % C;
+      if (slot_block[slot] == (int64_t)b) { // cached
+        if (run_open) {
+          const bool up = b == run_hi + 1 && b % C != 0;
+          const bool down = b + 1 == run_lo && run_lo % C != 0;
+          const bool room = (size_t)(run_hi - run_lo + 2) * block_bytes <= kStreamHitRunBytes;
+          if ((up || down) && room) {
+            run_lo = std::min(run_lo, b);
+            run_hi = std::max(run_hi, b);
+            continue;
+          }
+          flush_run();
+        }
+        run_open = true;
+        run_lo = run_hi = b;
+        continue;
+      }
+      flush_run();
+      const uint32_t rows = block_rows_of(b);
+      if (slot_used[slot]) // the pass that last read this slot must be done before it is overwritten
+        ST_CUDA(cudaStreamWaitEvent(copy_stream_, slot_free_[slot], 0));
+      ST_CUDA(cudaMemcpyAsync(slot_ptr(slot), h_mat + (size_t)b * B * dim, row_bytes * rows, cudaMemcpyHostToDevice,
+                              copy_stream_));
+      ST_CUDA(cudaEventRecord(slot_ready_[slot], copy_stream_));
+      ST_CUDA(cudaStreamWaitEvent(stream_, slot_ready_[slot], 0));
+      launch_row_pass(*this, slot_ptr(slot), E, S, dim, b * B, rows);
+      launches++;
+      ST_CUDA(cudaEventRecord(slot_free_[slot], stream_));
+      slot_used[slot] = 1;
+      slot_block[slot] = b;
+      copied += (uint64_t)row_bytes * rows;
+    }
+    flush_run();
+
+    // ---- vector tail + the host's decision (reference :41-50) ----
+    ST_CUDA(cudaMemsetAsync(cells, 0, sizeof(uint32_t), stream_));
+    ST_LAUNCH_ELEMENTWISE(fill_u32_kernel, 1, 32, 0, stream_, cells + 1, stop_kind == kStopRelative ? 0u : 1u, 1u);
+    ST_LAUNCH(tail_scan_kernel, tail_scan_grid, 1024, 0, stream_, (const float*)S, dim, opt.eps, stop_kind, cells);
+    ST_LAUNCH_ELEMENTWISE(tail_update_kernel, tail_update_grid, 256, 0, stream_, (const float*)S, E, dim, opt.eps,
+                          stop_kind, (const uint32_t*)cells, d_out);
+    ST_CUDA(cudaGetLastError());
+    launches += 3;
+    ST_CUDA(cudaMemcpyAsync(const_cast<uint32_t*>(h_out), d_out, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    ST_CUDA(cudaStreamSynchronize(stream_));
+    passes++;
+    h2d_total += copied;
+    if (k == 0)
+      h2d_first = copied;
+    else
+      h2d_last = copied;
+    const uint32_t bits = h_out[1];
+    memcpy(&lambda, &bits, sizeof lambda); // :60-65
+    round_us.push_back(std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - r0).count());
+    if (h_out[0] != 0u) {
+      it = k; // :54
+      break;
+    }
+  }
+  ST_CUDA(cudaEventRecord(ev1_, stream_));
+  ST_CUDA(cudaEventSynchronize(ev1_));
+  float loop_ms = 0.f;
+  ST_CUDA(cudaEventElapsedTime(&loop_ms, ev0_, ev1_));
+  if (h_eigen_vec)
+    ST_CUDA(cudaMemcpy(h_eigen_vec, E, sizeof(float) * dim, cudaMemcpyDeviceToHost));
+  if (h_eigen_val)
+    *h_eigen_val = lambda;
+  last_ts_.clear();
+  last_phase_ts_.clear();
+
+  if (plan) {
+    plan->block_rows = B;
+    plan->blocks = nb;
+    plan->slots = C;
+    plan->streamed = 1;
+    plan->cache_bytes = (uint64_t)C * block_bytes;
+    plan->h2d_bytes_first = h2d_first;
+    plan->h2d_bytes_per_round = h2d_last;
+    plan->h2d_bytes_total = h2d_total;
+  }
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->eigen_val = lambda;
+    res->iter_count = it;
+    res->passes = passes;
+    res->launches = launches;
+    res->loop_ms = loop_ms;
+    res->bytes_per_round = mat_bytes;
+    res->kernel_id = kStreamedKernelId;
+    res->threads = 256;
+    std::sort(round_us.begin(), round_us.end());
+    res->round_us_min = round_us.front();
+    res->round_us_median = round_us[round_us.size() / 2];
+    res->status = ST_OK;
+    res->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  }
   return ST_OK;
 }

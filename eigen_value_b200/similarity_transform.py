@@ -17,7 +17,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import StOptions, StResult, check
+from ._lib import StOptions, StResult, StStreamPlan, check
 
 EPS = 1e-3       # reference include/similarity_transform.hpp:4
 MAX_ITR = 1000   # reference include/similarity_transform.hpp:5
@@ -100,11 +100,13 @@ class SolveInfo:
     threads: int = 0
 
     KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_tma_kernel", 10: "st::round_loop_sc_kernel",
-                    20: "st::round_loop_cluster_kernel"}
+                    20: "st::round_loop_cluster_kernel",
+                    30: "st::sum_across_rows_kernel + tail kernels (streamed, host-driven rounds)"}
 
     @property
     def kernel_name(self) -> str:
-        key = 20 if self.kernel_id >= 20 else 10 if self.kernel_id >= 10 else 2 if self.kernel_id >= 2 else 1
+        key = 30 if self.kernel_id >= 30 else 20 if self.kernel_id >= 20 else 10 if self.kernel_id >= 10 else \
+            2 if self.kernel_id >= 2 else 1
         return self.KERNEL_NAMES[key]
 
     @classmethod
@@ -247,6 +249,32 @@ class Solver:
         check(self.lib.st_solve_host(self.ctx, _ptr(mat), n, ctypes.byref(o), _ptr(val), _ptr(vec),
                                      ctypes.byref(res)), "st_solve_host")
         return SolveInfo.from_c(res), vec
+
+    def solve_streamed(self, mat, device_budget: int = 0, block_rows: int = 0, offset: int = 0,
+                       dim: Optional[int] = None, **opts) -> Tuple[SolveInfo, np.ndarray, dict]:
+        """similarity_transform() on a host matrix that does not fit the device (or the `device_budget`
+        bytes granted): a device cache of row blocks + alternating sweeps, only the uncached blocks cross
+        PCIe per round (st_solve_streamed).  `mat` is a C-contiguous float32 array -- np.memmap works --
+        or a file path (then `dim`, and `offset` = bytes before the first element; st_solve_file).
+        Same bits as solve_host.  Returns (info, eigen_vec, plan)."""
+        o = make_options(self.lib, **opts)
+        res, plan = StResult(), StStreamPlan()
+        val = np.empty(1, dtype=np.float32)
+        if isinstance(mat, (str, bytes)):
+            assert dim is not None, "a file needs dim"
+            vec = np.empty(dim, dtype=np.float32)
+            path = mat.encode() if isinstance(mat, str) else mat
+            check(self.lib.st_solve_file(self.ctx, path, offset, dim, ctypes.byref(o), device_budget, block_rows,
+                                         _ptr(val), _ptr(vec), ctypes.byref(res), ctypes.byref(plan)), "st_solve_file")
+        else:
+            assert mat.ndim == 2 and mat.shape[0] == mat.shape[1] and mat.dtype == np.float32
+            assert mat.flags["C_CONTIGUOUS"]
+            n = mat.shape[0]
+            vec = np.empty(n, dtype=np.float32)
+            check(self.lib.st_solve_streamed(self.ctx, _ptr(mat), n, ctypes.byref(o), device_budget, block_rows,
+                                             _ptr(val), _ptr(vec), ctypes.byref(res), ctypes.byref(plan)),
+                  "st_solve_streamed")
+        return SolveInfo.from_c(res), vec, {name: int(getattr(plan, name)) for name, _ in StStreamPlan._fields_}
 
     def solve_tensor(self, mat, **opts):
         """Zero-copy solve of a square float32 CUDA tensor (torch, or anything exposing

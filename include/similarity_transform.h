@@ -182,6 +182,43 @@ int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options*
 int st_convert_f32_to_bf16(void* ctx, const float* d_src, uint16_t* d_dst, size_t count);
 int st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const st_options* opt,
                          float* d_eigen_vec, st_result* res);
+/* Streamed solve: the same round loop for a HOST matrix that does not fit the device (or the share of
+ * it the caller grants).  The step before the path in the reference is the host copy-in of the whole
+ * matrix (similarity_transform.cpp:14-19); here the device holds a direct-mapped cache of `slots` row
+ * blocks (block b lives in slot b % slots) and every round sweeps the blocks in alternating direction,
+ * so the blocks a round ends on are the ones the next round starts on: per round only
+ * (blocks - slots) blocks cross PCIe, the cached ones are read from HBM.  Copies run on their own
+ * stream ahead of the row passes; the round loop is host-driven (one 8-byte read-back per round),
+ * which costs microseconds against rounds that take milliseconds to seconds.  Same arithmetic and
+ * evaluation order as every other solve, so the result is bit-identical to st_solve_host; read-only
+ * form, fp32 accumulation, both stop tests.
+ *   h_mat           dim x dim fp32 row-major, pageable, pinned (st_pin_host: full PCIe rate) or a
+ *                   read-only file mapping; never modified
+ *   device_budget   bytes of device memory to use for the block cache; 0 = what is free now minus 1 GiB,
+ *                   and then a matrix that fits is simply handed to st_solve_host
+ *   block_rows      rows per block; 0 = about 64 MiB worth of rows
+ *   plan            optional: what was done (blocks, slots, bytes over PCIe in round 0 and per later round) */
+typedef struct st_stream_plan
+{
+  uint32_t block_rows;          /* rows per block (the last block may be shorter)          */
+  uint32_t blocks;              /* row blocks of the matrix                                */
+  uint32_t slots;               /* blocks the device cache holds                           */
+  uint32_t streamed;            /* 0: the matrix fitted and st_solve_host ran instead      */
+  uint64_t cache_bytes;         /* device memory taken by the cache                        */
+  uint64_t h2d_bytes_first;     /* bytes copied host -> device in round 0                  */
+  uint64_t h2d_bytes_per_round; /* bytes copied per later round                            */
+  uint64_t h2d_bytes_total;     /* bytes copied by this call                               */
+} st_stream_plan;
+int st_solve_streamed(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt, size_t device_budget,
+                      uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec, st_result* res,
+                      st_stream_plan* plan);
+/* The same on a file: `path` holds dim x dim fp32 row-major starting `offset` bytes into the file (a raw
+ * dump, or a .npy file with offset = its header length).  The file is mapped read-only and streamed;
+ * nothing but the cache and the vectors is ever resident. */
+int st_solve_file(void* ctx, const char* path, uint64_t offset, uint32_t dim, const st_options* opt,
+                  size_t device_budget, uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec,
+                  st_result* res, st_stream_plan* plan);
+
 /* Per-round device timestamps (ns, globaltimer) of the last solve on this context. */
 int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
 /* Three stamps per round of the last solve, taken by CTA 0: matrix pass done, round barrier

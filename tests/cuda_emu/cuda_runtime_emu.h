@@ -153,6 +153,9 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = n
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new CUevent_st{ 0.0 }; return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new CUevent_st{ 0.0 }; return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; } // everything already happened
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = emu_rt::now_ms(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
@@ -175,6 +178,12 @@ cudaMalloc(T** p, size_t bytes)
   return cudaSuccess;
 }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t
+cudaMemGetInfo(size_t* free_b, size_t* total_b)
+{
+  *free_b = *total_b = (size_t)emu_rt::env_int("ST_EMU_HBM_MIB", 4096) << 20;
+  return cudaSuccess;
+}
 template<typename T>
 inline cudaError_t
 cudaHostAlloc(T** p, size_t bytes, unsigned)

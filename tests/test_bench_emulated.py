@@ -45,3 +45,21 @@ def test_opt_in_switches(extra, rounds):
     if "--storage" in extra:
         assert line["e2e"] is None and line["roofline"]["bytes_per_launch"] == line["passes_per_step"] * 2 * 1024 * 1024
         assert "bf16 storage" in line["metric"]
+
+
+def test_streamed_bench_tool_on_the_emulated_library():
+    # tools/bench_streamed.py (streamed solve vs in-device solve of the same matrix), same trick as the runner above
+    code = ("import os, sys; sys.path.insert(0, 'tests/cuda_emu'); os.environ.setdefault('ST_EMU_SMS', '8');"
+            "import build as b; from eigen_value_b200 import _lib;"
+            "_lib._build.SO_PATH = b.build_library(); _lib._build.stale = lambda: False;"
+            "sys.path.insert(0, 'tools'); import bench_streamed;"
+            "sys.argv = ['bench_streamed.py', '--dim', '512', '--cached', '0.4', '--block-rows', '32', '--steps', '1'];"
+            "sys.exit(bench_streamed.main())")
+    proc = subprocess.run([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    line = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["bit_identical_to_in_device_solve"] is True and line["rounds"] == 12          # reference README.md:72
+    plan = line["plan"]
+    assert plan["streamed"] == 1 and plan["blocks"] == 16 and plan["slots"] == 6
+    assert plan["h2d_bytes_per_round"] == 10 * 32 * 512 * 4 and plan["h2d_bytes_first"] == 4 * 512 * 512

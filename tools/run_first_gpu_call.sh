@@ -31,4 +31,10 @@ done
 # fp64 accumulation: same bytes, two conversions and one DFMA per element -- does it still sit under the stream?
 timeout 600 python bench.py --workload hilbert-8192 --accumulate f64 --steps 10 --no-e2e --no-cpu-baseline --no-sweep-table \
   > $O/first_call_bench_hilbert-8192_acc64.json 2>> $O/first_call_bench_n1.err
+# streamed solve (written without hardware): half / 90 % of a 4 GiB matrix cached, pinned and pageable source
+timeout 300 python -m pytest tests/test_zzzz_gpu_streamed.py -q > $O/first_call_streamed_tests.txt 2>&1
+for c in 0.5 0.9; do
+  timeout 600 python tools/bench_streamed.py --dim 32768 --cached $c >> $O/first_call_bench_streamed.json 2>> $O/first_call_bench_n1.err
+done
+timeout 600 python tools/bench_streamed.py --dim 32768 --cached 0.5 --pinned 0 >> $O/first_call_bench_streamed.json 2>> $O/first_call_bench_n1.err
 tail -5 $O/first_call_tests.txt
