@@ -97,6 +97,9 @@ SYMBOLS = {
     "st_solve_file": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(StOptions),
                                      ctypes.c_size_t, ctypes.c_uint32, _VP, _VP, ctypes.POINTER(StResult),
                                      ctypes.POINTER(StStreamPlan)]),
+    "st_group_attach": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.c_uint32, ctypes.c_uint32]),
+    "st_group_detach": (ctypes.c_int, [_VP]),
+    "st_group_size": (ctypes.c_int, [_VP]),
     "st_convert_f32_to_bf16": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "st_solve_device_bf16": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP,
                                             ctypes.POINTER(StResult)]),

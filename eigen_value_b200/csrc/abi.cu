@@ -4,7 +4,15 @@
 // of the CUDA solver; Part 2 is the additive st_* surface.  Nothing throws across this file.
 #include "similarity_transform.hpp"
 
+#include <algorithm>
 #include <cerrno>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -79,6 +87,170 @@ as_shard(void* p)
 
 constexpr size_t kFlagBytes = 128; // ST_MAX_WORLD x 8-byte flags, padded to one line
 
+// ---- device group: several GPUs behind ONE handle --------------------------------------------------
+// st_group_attach (or ST_DEVICES in make_queue's environment) binds helper contexts on other GPUs to a
+// context.  max_eigen_value / st_solve_host on that context then run the row-block sharded solve for
+// matrices of min_dim and up: one host thread per GPU uploads its own row block from the caller's host
+// matrix (so the copy runs over every GPU's PCIe link at once) and enters the collective round kernel;
+// the shards are linked through plain peer access (st_shard_link_local).  Results are bit-identical to
+// the one-GPU solve; the reference's wrapper needs no change to use the whole box.
+struct Group
+{
+  std::vector<Context*> ctx; // [0] is the context the group is attached to (not owned)
+  std::vector<void*> shards; // built for one dimension at a time
+  uint32_t dim = 0, world = 0, min_dim = 0;
+  std::mutex mu;
+};
+constexpr uint32_t kGroupDefaultMinDim = 8192;
+
+std::mutex g_groups_mu;
+std::map<Context*, Group*> g_groups;
+
+Group*
+group_of(Context* c)
+{
+  std::lock_guard<std::mutex> lock(g_groups_mu);
+  auto it = g_groups.find(c);
+  return it == g_groups.end() ? nullptr : it->second;
+}
+
+void
+group_drop_shards(Group& g)
+{
+  for (void* sh : g.shards)
+    st_shard_destroy(sh);
+  g.shards.clear();
+  g.dim = g.world = 0;
+}
+
+void
+group_free(Group* g)
+{
+  group_drop_shards(*g);
+  for (size_t i = 1; i < g->ctx.size(); i++)
+    delete g->ctx[i];
+  delete g;
+}
+
+// throws; the caller holds no context mutex
+int
+group_solve_host(Group& g, const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val, float* h_eigen_vec,
+                 st_result* res)
+{
+  std::lock_guard<std::mutex> lock(g.mu);
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint32_t world = (uint32_t)std::min<size_t>(g.ctx.size(), dim);
+  if (g.dim != dim || g.world != world) { // exchange blocks are sized for one dimension
+    group_drop_shards(g);
+    for (uint32_t r = 0; r < world; r++) {
+      void* sh = nullptr;
+      const int rc = st_shard_create(g.ctx[r], dim, r, world, &sh);
+      if (rc != ST_OK) {
+        group_drop_shards(g);
+        return rc; // st_last_error is set on this thread
+      }
+      g.shards.push_back(sh);
+    }
+    const int rc = st_shard_link_local(g.shards.data(), world);
+    if (rc != ST_OK) {
+      group_drop_shards(g);
+      return rc;
+    }
+    g.dim = dim;
+    g.world = world;
+  }
+  std::vector<int> rcs(world, ST_OK);
+  std::vector<std::string> errs(world);
+  std::vector<st_result> results(world);
+  // Two phases with a host barrier between them: (1) every rank allocates and starts its upload, (2) every
+  // rank enters the collective kernel.  No allocation may happen on any GPU while a peer already spins in
+  // the round barrier, and if a rank fails in phase 1 nobody enters phase 2 (no 10 s timeout).
+  std::mutex bar_mu;
+  std::condition_variable bar_cv;
+  uint32_t arrived = 0, failed = 0;
+  auto work = [&](uint32_t r) {
+    Context* c = g.ctx[r];
+    Shard* sh = static_cast<Shard*>(g.shards[r]);
+    std::lock_guard<std::mutex> ctx_lock(c->mutex());
+    rcs[r] = guarded([&] {
+      c->upload_rows(h_mat, dim, opt, sh);
+      return ST_OK;
+    });
+    if (rcs[r] != ST_OK)
+      errs[r] = st::last_error(); // thread-local: carry it to the calling thread
+    {
+      std::unique_lock<std::mutex> lk(bar_mu);
+      failed += rcs[r] != ST_OK;
+      if (++arrived == world)
+        bar_cv.notify_all();
+      else
+        bar_cv.wait(lk, [&] { return arrived == world; });
+      if (failed)
+        return;
+    }
+    rcs[r] = guarded([&] {
+      return c->solve_uploaded(dim, opt, r == 0 ? h_eigen_val : nullptr, r == 0 ? h_eigen_vec : nullptr, &results[r], sh);
+    });
+    if (rcs[r] != ST_OK)
+      errs[r] = st::last_error();
+  };
+  std::vector<std::thread> threads;
+  for (uint32_t r = 1; r < world; r++)
+    threads.emplace_back(work, r);
+  work(0);
+  for (auto& t : threads)
+    t.join();
+  for (uint32_t r = 0; r < world; r++)
+    if (rcs[r] != ST_OK) {
+      // a rank that failed leaves the group's flag epochs diverged: rebuild the shards next time
+      group_drop_shards(g);
+      st::set_last_error("device group, rank " + std::to_string(r) + " (device " + std::to_string(g.ctx[r]->device()) +
+                         "): " + errs[r]);
+      return rcs[r];
+    }
+  if (res) {
+    *res = results[0];
+    res->launches = 0;
+    res->bytes_per_round = 0;
+    for (uint32_t r = 0; r < world; r++) {
+      res->loop_ms = std::max(res->loop_ms, results[r].loop_ms); // max over ranks
+      res->launches += results[r].launches;
+      res->bytes_per_round += results[r].bytes_per_round;
+    }
+    res->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return ST_OK;
+}
+
+// ST_DEVICES=all | "0,1,2,3": devices make_queue binds (the first one is the handle's own device)
+std::vector<int>
+devices_from_env()
+{
+  std::vector<int> out;
+  const char* v = getenv("ST_DEVICES");
+  if (!v || !*v)
+    return out;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess)
+    count = 0;
+  if (strcmp(v, "all") == 0) {
+    for (int d = 0; d < count; d++)
+      out.push_back(d);
+    return out;
+  }
+  for (const char* p = v; *p;) {
+    char* end = nullptr;
+    const long d = strtol(p, &end, 10);
+    if (end == p || d < 0 || d >= count || std::find(out.begin(), out.end(), (int)d) != out.end())
+      throw std::invalid_argument(std::string("ST_DEVICES: bad device list '") + v + "'");
+    out.push_back((int)d);
+    p = *end == ',' ? end + 1 : end;
+    if (*end && *end != ',')
+      throw std::invalid_argument(std::string("ST_DEVICES: bad device list '") + v + "'");
+  }
+  return out;
+}
+
 } // namespace
 
 extern "C" {
@@ -93,8 +265,21 @@ make_queue(void** wq)
   if (!wq)
     return;
   *wq = nullptr;
-  guarded([&] {
-    *wq = new Context(0);
+  guarded([&]() -> int {
+    // ST_DEVICES (extension): "all" or a list like "0,1,2,3" -- the handle lives on the first device and the
+    // others help with matrices of 8192 rows and up; unset = device 0 alone, like the reference's default device
+    const std::vector<int> devs = devices_from_env();
+    Context* c = new Context(devs.empty() ? 0 : devs[0]);
+    if (devs.size() > 1) {
+      const char* md = getenv("ST_GROUP_MIN_DIM"); // optional: smallest dim that is sharded (default 8192)
+      const long min_dim = md && *md ? strtol(md, nullptr, 10) : 0;
+      const int rc = st_group_attach(c, devs.data() + 1, (uint32_t)devs.size() - 1, min_dim > 0 ? (uint32_t)min_dim : 0u);
+      if (rc != ST_OK) {
+        delete c;
+        return rc;
+      }
+    }
+    *wq = c;
     return ST_OK;
   });
 }
@@ -104,10 +289,22 @@ max_eigen_value(void* wq, float* mat, float* eigen_val, float* eigen_vec, st_uin
                 st_uint* iter_cnt)
 {
   int64_t ms = -1;
-  const int rc = guarded([&] {
+  const int rc = guarded([&]() -> int {
     if (!mat || !eigen_val || !eigen_vec || !iter_cnt || dim == 0)
       throw std::invalid_argument("max_eigen_value: null pointer or dim == 0");
-    ms = similarity_transform(*as_ctx(wq), mat, eigen_val, eigen_vec, dim, dim >> 1, iter_cnt);
+    Context* c = as_ctx(wq);
+    if (Group* g = group_of(c); g && dim >= g->min_dim) { // several GPUs behind this handle
+      st_options o;
+      st_default_options(&o);
+      st_result r{};
+      const int rc = group_solve_host(*g, mat, dim, o, eigen_val, eigen_vec, &r);
+      if (rc != ST_OK)
+        return rc;
+      *iter_cnt = r.iter_count;  // exactly 4 bytes
+      ms = (int64_t)r.loop_ms;   // whole milliseconds of the loop, like reference :56-58
+      return ST_OK;
+    }
+    ms = similarity_transform(*c, mat, eigen_val, eigen_vec, dim, dim >> 1, iter_cnt);
     return ms < 0 ? (int)ms : ST_OK;
   });
   return rc == ST_OK ? ms : (int64_t)rc;
@@ -160,9 +357,84 @@ void
 st_destroy(void* ctx)
 {
   guarded([&] {
+    if (ctx)
+      st_group_detach(ctx);
     delete static_cast<Context*>(ctx);
     return ST_OK;
   });
+}
+
+int
+st_group_attach(void* ctx, const int* devices, uint32_t count, uint32_t min_dim)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    if (group_of(c))
+      throw std::invalid_argument("st_group_attach: a group is already attached to this context");
+    std::vector<int> devs;
+    if (!devices || count == 0) { // every other visible device
+      for (int d = 0; d < st_device_count(); d++)
+        if (d != c->device())
+          devs.push_back(d);
+    } else {
+      for (uint32_t i = 0; i < count; i++) {
+        if (devices[i] == c->device() || std::find(devs.begin(), devs.end(), devices[i]) != devs.end())
+          throw std::invalid_argument("st_group_attach: the list repeats a device or names the context's own");
+        devs.push_back(devices[i]);
+      }
+    }
+    if (devs.size() + 1 > ST_MAX_WORLD)
+      throw std::invalid_argument("st_group_attach: more than ST_MAX_WORLD devices");
+    Group* g = new Group();
+    g->ctx.push_back(c);
+    g->min_dim = min_dim ? min_dim : kGroupDefaultMinDim;
+    try {
+      for (int d : devs)
+        g->ctx.push_back(new Context(d));
+    } catch (...) {
+      group_free(g);
+      throw;
+    }
+    c->activate();
+    std::lock_guard<std::mutex> lock(g_groups_mu);
+    g_groups[c] = g;
+    return ST_OK;
+  });
+}
+
+int
+st_group_detach(void* ctx)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    Group* g = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_groups_mu);
+      auto it = g_groups.find(c);
+      if (it == g_groups.end())
+        return ST_OK;
+      g = it->second;
+      g_groups.erase(it);
+    }
+    {
+      std::lock_guard<std::mutex> busy(g->mu); // a solve in flight finishes first
+    }
+    group_free(g);
+    c->activate();
+    return ST_OK;
+  });
+}
+
+int
+st_group_size(void* ctx)
+{
+  int n = 0;
+  guarded([&] {
+    Group* g = group_of(as_ctx(ctx));
+    n = g ? (int)g->ctx.size() : 1;
+    return ST_OK;
+  });
+  return n;
 }
 
 int
@@ -314,6 +586,8 @@ st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt
       o = *opt;
     else
       st_default_options(&o);
+    if (Group* g = group_of(c); g && dim >= g->min_dim && h_mat)
+      return group_solve_host(*g, h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
     std::lock_guard<std::mutex> lock(c->mutex());
     return c->solve_host(h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
   });

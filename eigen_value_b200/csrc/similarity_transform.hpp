@@ -51,8 +51,14 @@ public:
   // bf16 == true: d_rows points to bfloat16 storage (read-only form, dim % 8 == 0); fp32 otherwise.
   int solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
             float* d_eigen_vec, st_result* res, bool bf16 = false);
+  // shard != nullptr (device group): h_mat is still the whole matrix; this context uploads and solves
+  // its own row block, collectively with the other ranks of the shard group.
   int solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
-                 float* h_eigen_vec, st_result* res);
+                 float* h_eigen_vec, st_result* res, Shard* shard = nullptr);
+  // the two halves of solve_host: every allocation + the (asynchronous) upload | the solve + read-back
+  void upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Shard* shard);
+  int solve_uploaded(uint32_t dim, const st_options& opt, float* h_eigen_val, float* h_eigen_vec, st_result* res,
+                     Shard* shard);
   // Host matrix larger than the device (or than `device_budget`): block cache + alternating sweep,
   // host-driven rounds (include/similarity_transform.h, st_solve_streamed).
   int solve_streamed(const float* h_mat, uint32_t dim, const st_options& opt, size_t device_budget,

@@ -731,21 +731,35 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   return ST_OK;
 }
 
-int
-Context::solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
-                    float* h_eigen_vec, st_result* res)
+// Host-matrix solve in two steps, so that a device group can finish every allocation on every GPU before
+// any GPU enters the collective round kernel (cudaMalloc / cudaFree on a device with peer mappings may wait
+// for its peers, and a peer that already spins in the round barrier would never become idle).
+void
+Context::upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Shard* shard)
 {
   if (!h_mat || dim == 0)
     throw std::invalid_argument("solve_host: bad argument");
-  const auto host_t0 = std::chrono::steady_clock::now();
+  if (shard && (shard->ctx != this || shard->dim != dim))
+    throw std::invalid_argument("solve_host: shard belongs to another context or dimension");
   activate();
-  const size_t elems = (size_t)dim * dim;
+  // sharded (device group): h_mat is the WHOLE matrix, this context copies and solves its own row block
+  const uint32_t row0 = shard ? shard->row0 : 0u;
+  const uint32_t rows = shard ? shard->rows : dim;
+  const size_t elems = (size_t)rows * dim;
   reserve_matrix(elems);
   reserve_vectors(dim, opt.max_iter);
+  if (opt.form == ST_FORM_INPLACE)
+    reserve_work(elems);
   // the caller's matrix is never modified (reference similarity_transform.cpp:14,19 copies it)
-  ST_CUDA(cudaMemcpyAsync(d_mat_, h_mat, sizeof(float) * elems, cudaMemcpyHostToDevice, stream_));
+  ST_CUDA(cudaMemcpyAsync(d_mat_, h_mat + (size_t)row0 * dim, sizeof(float) * elems, cudaMemcpyHostToDevice, stream_));
+}
+
+int
+Context::solve_uploaded(uint32_t dim, const st_options& opt, float* h_eigen_val, float* h_eigen_vec, st_result* res,
+                        Shard* shard)
+{
   st_result local{};
-  const int rc = solve(d_mat_, dim, opt, nullptr, nullptr, &local);
+  const int rc = solve(d_mat_, dim, opt, shard, nullptr, &local);
   if (rc == ST_OK) {
     if (h_eigen_vec)
       ST_CUDA(cudaMemcpy(h_eigen_vec, d_vec_ + 4 * (size_t)vec_cap_, sizeof(float) * dim,
@@ -753,8 +767,20 @@ Context::solve_host(const float* h_mat, uint32_t dim, const st_options& opt, flo
     if (h_eigen_val)
       *h_eigen_val = local.eigen_val;
   }
-  const auto host_t1 = std::chrono::steady_clock::now();
-  local.total_ms = std::chrono::duration<float, std::milli>(host_t1 - host_t0).count();
+  if (res)
+    *res = local;
+  return rc;
+}
+
+int
+Context::solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
+                    float* h_eigen_vec, st_result* res, Shard* shard)
+{
+  const auto host_t0 = std::chrono::steady_clock::now();
+  upload_rows(h_mat, dim, opt, shard);
+  st_result local{};
+  const int rc = solve_uploaded(dim, opt, h_eigen_val, h_eigen_vec, &local, shard);
+  local.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   if (res)
     *res = local;
   return rc;

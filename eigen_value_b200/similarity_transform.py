@@ -33,7 +33,7 @@ def _ptr(a: np.ndarray) -> ctypes.c_void_p:
 class EigenValue:
     """Drop-in for the reference's `EigenValue` (similarity_transform.py:18-78)."""
 
-    def __init__(self) -> None:
+    def __init__(self, devices=None, min_dim: int = 0) -> None:
         # reference :29-40 -- load the shared object, make the queue, fail on a NULL handle
         self.so_lib = _lib.load()
         self.so_path = _lib.so_path()
@@ -43,6 +43,15 @@ class EigenValue:
             err = self.so_lib.st_last_error()
             raise Exception("failed to get default CUDA device queue: "
                             + (err.decode() if err else "no GPU"))
+        # extension (st_group_attach): devices="all" or a list of helper GPUs -- matrices of min_dim rows and
+        # up (0 = 8192) are then row-block sharded over all of them behind the same similarity_transform() call.
+        # The unmodified reference wrapper gets the same from the ST_DEVICES environment variable.
+        if devices is not None:
+            attach_group(self.so_lib, self.sycl_q, devices, min_dim)
+
+    @property
+    def device_count(self) -> int:
+        return int(self.so_lib.st_group_size(self.sycl_q))
 
     def pinned(self, mat: np.ndarray):
         """Context manager (extension): page-locks `mat` for the duration of the block, so that repeated
@@ -82,6 +91,19 @@ class EigenValue:
             err = self.so_lib.st_last_error()
             raise RuntimeError(f"max_eigen_value failed ({ts}): {err.decode() if err else ''}")
         return eigen_val[0], eigen_vec, ts, int(iter_cnt[0])
+
+
+def attach_group(lib, ctx, devices="all", min_dim: int = 0) -> None:
+    """st_group_attach: bind helper GPUs ("all" = every other visible one, or a list of device ids that does
+    not name the context's own device) to a context / make_queue handle."""
+    if isinstance(devices, str):
+        assert devices == "all", devices
+        check(lib.st_group_attach(ctx, None, 0, min_dim), "st_group_attach")
+    else:
+        ids = (ctypes.c_int * len(devices))(*devices)
+        if len(devices) == 0:
+            return
+        check(lib.st_group_attach(ctx, ids, len(devices), min_dim), "st_group_attach")
 
 
 @dataclass
@@ -187,6 +209,15 @@ class Solver:
         if self.ctx is not None and self.ctx.value:
             self.lib.st_destroy(self.ctx)
             self.ctx = None
+
+    def attach_group(self, devices="all", min_dim: int = 0) -> int:
+        """Helper GPUs behind this solver (st_group_attach): solve_host() then shards matrices of min_dim rows
+        and up (0 = 8192) over all of them.  Returns the number of devices now behind the handle."""
+        attach_group(self.lib, self.ctx, devices, min_dim)
+        return int(self.lib.st_group_size(self.ctx))
+
+    def detach_group(self) -> None:
+        check(self.lib.st_group_detach(self.ctx), "st_group_detach")
 
     # ---- memory / inputs ------------------------------------------------------------------
     def alloc(self, nbytes: int) -> DeviceBuffer:

@@ -219,6 +219,20 @@ int st_solve_file(void* ctx, const char* path, uint64_t offset, uint32_t dim, co
                   size_t device_budget, uint32_t block_rows, float* h_eigen_val, float* h_eigen_vec,
                   st_result* res, st_stream_plan* plan);
 
+/* Device group: several GPUs behind ONE handle, so that the reference's unmodified wrapper uses the whole
+ * box.  st_group_attach binds helper contexts on `devices` (NULL / 0 = every other visible GPU; the list
+ * must not name the context's own device) to `ctx`.  From then on max_eigen_value / st_solve_host on `ctx`
+ * run the row-block sharded solve for matrices with dim >= min_dim (0 = 8192): one host thread per GPU copies
+ * its own row block from the caller's host matrix -- every GPU's PCIe link carries 1/G of the matrix -- and
+ * joins the collective round kernel; the shards are linked by peer access (st_shard_link_local).  Same bits
+ * as on one GPU.  Smaller matrices stay on the context's own GPU.  st_group_detach (also done by
+ * st_destroy) frees the helpers.  Setting ST_DEVICES=all or ST_DEVICES=0,1,2,3 in the environment makes
+ * make_queue attach the group itself: the handle lives on the first device listed (ST_GROUP_MIN_DIM
+ * optionally overrides min_dim). */
+int st_group_attach(void* ctx, const int* devices, uint32_t count, uint32_t min_dim);
+int st_group_detach(void* ctx);
+int st_group_size(void* ctx); /* devices behind this handle, 1 without a group */
+
 /* Per-round device timestamps (ns, globaltimer) of the last solve on this context. */
 int st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count);
 /* Three stamps per round of the last solve, taken by CTA 0: matrix pass done, round barrier

@@ -63,3 +63,19 @@ def test_streamed_bench_tool_on_the_emulated_library():
     plan = line["plan"]
     assert plan["streamed"] == 1 and plan["blocks"] == 16 and plan["slots"] == 6
     assert plan["h2d_bytes_per_round"] == 10 * 32 * 512 * 4 and plan["h2d_bytes_first"] == 4 * 512 * 512
+
+
+def test_group_bench_tool_on_the_emulated_library():
+    # tools/bench_group.py (drop-in call on one GPU vs a device group), 4 pretend GPUs
+    code = ("import os, sys; sys.path.insert(0, 'tests/cuda_emu'); os.environ.setdefault('ST_EMU_SMS', '8');"
+            "os.environ['ST_EMU_DEVICES'] = '4';"
+            "import build as b; from eigen_value_b200 import _lib;"
+            "_lib._build.SO_PATH = b.build_library(); _lib._build.stale = lambda: False;"
+            "sys.path.insert(0, 'tools'); import bench_group;"
+            "sys.argv = ['bench_group.py', '--dim', '512', '--steps', '1', '--min-dim', '256'];"
+            "sys.exit(bench_group.main())")
+    proc = subprocess.run([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    line = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["bit_identical"] is True and line["rounds"] == 12 and line["group"]["gpus"] == 4

@@ -16,3 +16,10 @@ timeout 600 $TR --nproc-per-node 8 --master-port 29651 bench.py --gpus 8 --workl
 cut -c1-1200 gpurun_out/scale_uniform131072_n8.json
 timeout 600 $TR --nproc-per-node 8 --master-port 29652 bench.py --gpus 8 --workload uniform-65536 --steps 1 --warmup 3 --no-e2e 2>/dev/null | grep '^{' > gpurun_out/scale_uniform65536_n8.json
 cut -c1-1200 gpurun_out/scale_uniform65536_n8.json
+# in-process device group behind the drop-in handle (written without hardware): tests first, then one GPU vs all GPUs, e2e
+timeout 600 python -m pytest tests/test_zzzz_gpu_group.py tests/test_gpu_sharded.py -q -k "group or in_process or missing_peer" > gpurun_out/group_tests.txt 2>&1
+tail -3 gpurun_out/group_tests.txt
+for n in 8192 32768; do
+  timeout 600 python tools/bench_group.py --dim $n >> gpurun_out/bench_group.json 2>> gpurun_out/bench_group.err
+done
+cat gpurun_out/bench_group.json
