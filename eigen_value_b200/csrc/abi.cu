@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -96,17 +97,31 @@ constexpr size_t kFlagBytes = 128; // ST_MAX_WORLD x 8-byte flags, padded to one
 // the one-GPU solve; the reference's wrapper needs no change to use the whole box.
 struct Group
 {
-  std::vector<Context*> ctx; // [0] is the context the group is attached to (not owned)
+  std::vector<Context*> ctx; // [0] is the context the group is attached to (not owned), the others are owned
   std::vector<void*> shards; // built for one dimension at a time
   uint32_t dim = 0, world = 0, min_dim = 0;
   std::mutex mu;
+  void drop_shards()
+  {
+    for (void* sh : shards)
+      st_shard_destroy(sh);
+    shards.clear();
+    dim = world = 0;
+  }
+  ~Group()
+  {
+    drop_shards();
+    for (size_t i = 1; i < ctx.size(); i++)
+      delete ctx[i];
+  }
 };
 constexpr uint32_t kGroupDefaultMinDim = 8192;
 
+// a caller that looked its group up keeps it alive until its solve returns, whatever st_group_detach does meanwhile
 std::mutex g_groups_mu;
-std::map<Context*, Group*> g_groups;
+std::map<Context*, std::shared_ptr<Group>> g_groups;
 
-Group*
+std::shared_ptr<Group>
 group_of(Context* c)
 {
   std::lock_guard<std::mutex> lock(g_groups_mu);
@@ -117,19 +132,7 @@ group_of(Context* c)
 void
 group_drop_shards(Group& g)
 {
-  for (void* sh : g.shards)
-    st_shard_destroy(sh);
-  g.shards.clear();
-  g.dim = g.world = 0;
-}
-
-void
-group_free(Group* g)
-{
-  group_drop_shards(*g);
-  for (size_t i = 1; i < g->ctx.size(); i++)
-    delete g->ctx[i];
-  delete g;
+  g.drop_shards();
 }
 
 // throws; the caller holds no context mutex
@@ -293,7 +296,7 @@ max_eigen_value(void* wq, float* mat, float* eigen_val, float* eigen_vec, st_uin
     if (!mat || !eigen_val || !eigen_vec || !iter_cnt || dim == 0)
       throw std::invalid_argument("max_eigen_value: null pointer or dim == 0");
     Context* c = as_ctx(wq);
-    if (Group* g = group_of(c); g && dim >= g->min_dim) { // several GPUs behind this handle
+    if (auto g = group_of(c); g && dim >= g->min_dim) { // several GPUs behind this handle
       st_options o;
       st_default_options(&o);
       st_result r{};
@@ -385,19 +388,14 @@ st_group_attach(void* ctx, const int* devices, uint32_t count, uint32_t min_dim)
     }
     if (devs.size() + 1 > ST_MAX_WORLD)
       throw std::invalid_argument("st_group_attach: more than ST_MAX_WORLD devices");
-    Group* g = new Group();
+    auto g = std::make_shared<Group>();
     g->ctx.push_back(c);
     g->min_dim = min_dim ? min_dim : kGroupDefaultMinDim;
-    try {
-      for (int d : devs)
-        g->ctx.push_back(new Context(d));
-    } catch (...) {
-      group_free(g);
-      throw;
-    }
+    for (int d : devs)
+      g->ctx.push_back(new Context(d)); // a throw here frees the helpers made so far (~Group)
     c->activate();
     std::lock_guard<std::mutex> lock(g_groups_mu);
-    g_groups[c] = g;
+    g_groups[c] = std::move(g);
     return ST_OK;
   });
 }
@@ -407,19 +405,19 @@ st_group_detach(void* ctx)
 {
   return guarded([&] {
     Context* c = as_ctx(ctx);
-    Group* g = nullptr;
+    std::shared_ptr<Group> g;
     {
       std::lock_guard<std::mutex> lock(g_groups_mu);
       auto it = g_groups.find(c);
       if (it == g_groups.end())
         return ST_OK;
-      g = it->second;
+      g = std::move(it->second);
       g_groups.erase(it);
     }
     {
       std::lock_guard<std::mutex> busy(g->mu); // a solve in flight finishes first
     }
-    group_free(g);
+    g.reset(); // frees the helpers unless a caller still holds the group; then its last reference does
     c->activate();
     return ST_OK;
   });
@@ -430,7 +428,7 @@ st_group_size(void* ctx)
 {
   int n = 0;
   guarded([&] {
-    Group* g = group_of(as_ctx(ctx));
+    auto g = group_of(as_ctx(ctx));
     n = g ? (int)g->ctx.size() : 1;
     return ST_OK;
   });
@@ -586,7 +584,7 @@ st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options* opt
       o = *opt;
     else
       st_default_options(&o);
-    if (Group* g = group_of(c); g && dim >= g->min_dim && h_mat)
+    if (auto g = group_of(c); g && dim >= g->min_dim && h_mat)
       return group_solve_host(*g, h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
     std::lock_guard<std::mutex> lock(c->mutex());
     return c->solve_host(h_mat, dim, o, h_eigen_val, h_eigen_vec, res);
