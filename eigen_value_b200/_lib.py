@@ -84,6 +84,7 @@ SYMBOLS = {
     "st_synchronize": (ctypes.c_int, [_VP]),
     "st_pin_host": (ctypes.c_int, [_VP, _VP, ctypes.c_size_t]),
     "st_unpin_host": (ctypes.c_int, [_VP, _VP]),
+    "st_staged_upload_bytes": (ctypes.c_uint64, [_VP]),
     "st_generate_hilbert": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "st_generate_uniform": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                            ctypes.c_uint64]),

@@ -367,6 +367,17 @@ st_destroy(void* ctx)
   });
 }
 
+uint64_t
+st_staged_upload_bytes(void* ctx)
+{
+  uint64_t n = 0;
+  guarded([&] {
+    n = as_ctx(ctx)->staged_upload_bytes();
+    return ST_OK;
+  });
+  return n;
+}
+
 int
 st_group_attach(void* ctx, const int* devices, uint32_t count, uint32_t min_dim)
 {

@@ -71,6 +71,7 @@ public:
   void timer_start();
   float timer_stop();
 
+  uint64_t staged_upload_bytes() const { return staged_bytes_; } // bytes that took the multi-threaded upload path
   std::mutex& mutex() { return mu_; }
   void activate() const; // cudaSetDevice
 
@@ -80,6 +81,7 @@ private:
   void reserve_vectors(uint32_t dim, uint32_t max_iter);
   void reserve_matrix(size_t elems);
   void reserve_work(size_t elems);
+  void copy_h2d(float* d_dst, const float* h_src, size_t bytes);
 
   int device_ = 0;
   int sm_count_ = 0;
@@ -107,6 +109,12 @@ private:
   // streamed solve: copy stream and two events per cache slot (block landed / block consumed)
   CUstream_st* copy_stream_ = nullptr;
   std::vector<CUevent_st*> slot_ready_, slot_free_;
+  // opt-in multi-threaded upload of pageable host matrices (ST_UPLOAD_THREADS)
+  int upload_threads_ = 0;
+  uint64_t staged_bytes_ = 0;
+  void* bounce_ = nullptr;
+  std::vector<CUstream_st*> up_streams_;
+  std::vector<CUevent_st*> up_events_;
   std::vector<uint64_t> last_ts_;
   std::vector<uint64_t> last_phase_ts_;
 };

@@ -9,7 +9,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <stdexcept>
+#include <thread>
 
 #include <cuda_runtime.h>
 
@@ -113,6 +115,8 @@ Context::Context(int device)
   ST_CUDA(cudaMalloc(&d_bar_, sizeof(BarrierState)));
   ST_CUDA(cudaMalloc(&d_scalars_, 64));
   ST_CUDA(cudaHostAlloc(&h_pinned_, 64, cudaHostAllocDefault));
+  if (const char* v = getenv("ST_UPLOAD_THREADS"))
+    upload_threads_ = std::max(0, std::min(16, atoi(v)));
   preload_kernels();
 }
 
@@ -133,6 +137,11 @@ Context::~Context()
     cudaEventDestroy(e);
   if (copy_stream_)
     cudaStreamDestroy(copy_stream_);
+  for (cudaStream_t st : up_streams_)
+    cudaStreamDestroy(st);
+  for (cudaEvent_t e : up_events_)
+    cudaEventDestroy(e);
+  cudaFreeHost(bounce_);
   cudaEventDestroy(ev0_);
   cudaEventDestroy(ev1_);
   cudaEventDestroy(ev_timer_[0]);
@@ -751,7 +760,93 @@ Context::upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Sh
   if (opt.form == ST_FORM_INPLACE)
     reserve_work(elems);
   // the caller's matrix is never modified (reference similarity_transform.cpp:14,19 copies it)
-  ST_CUDA(cudaMemcpyAsync(d_mat_, h_mat + (size_t)row0 * dim, sizeof(float) * elems, cudaMemcpyHostToDevice, stream_));
+  copy_h2d(d_mat_, h_mat + (size_t)row0 * dim, sizeof(float) * elems);
+}
+
+// Host -> device copy of a caller-owned matrix on the solver stream.  Pinned / registered memory goes
+// straight to the copy engine.  A PAGEABLE source (the reference wrapper's numpy array) is staged by
+// the driver through its own bounce buffer on one thread, at a fraction of the PCIe rate; with
+// ST_UPLOAD_THREADS=T (opt-in, read when the context is created) T host threads copy 4 MiB chunks into
+// their own pinned double buffers and feed the copy engine from there, so staging and DMA overlap and
+// the host-side memcpy is spread over T cores.
+void
+Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
+{
+  constexpr size_t kChunk = 4ull << 20;
+  bool staged = upload_threads_ > 0 && bytes >= 8 * kChunk;
+  if (staged) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, h_src) != cudaSuccess) {
+      (void)cudaGetLastError();
+      staged = false;
+    } else {
+      staged = attr.type == cudaMemoryTypeUnregistered;
+    }
+  }
+  if (!staged) {
+    ST_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream_));
+    return;
+  }
+  const int T = upload_threads_;
+  if (!bounce_) {
+    ST_CUDA(cudaHostAlloc(&bounce_, 2 * kChunk * (size_t)T, cudaHostAllocDefault));
+    for (int t = 0; t < T; t++) {
+      cudaStream_t st = nullptr;
+      ST_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      up_streams_.push_back(st);
+      for (int b = 0; b < 3; b++) { // two buffer events + one "this thread's copies are done"
+        cudaEvent_t ev = nullptr;
+        ST_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        up_events_.push_back(ev);
+      }
+    }
+    cudaEvent_t start = nullptr; // last entry: "the solver stream has reached this upload"
+    ST_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    up_events_.push_back(start);
+  }
+  // the destination may still be read by earlier work on the solver stream
+  cudaEvent_t up_start = up_events_.back();
+  ST_CUDA(cudaEventRecord(up_start, stream_));
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  const char* src = reinterpret_cast<const char*>(h_src);
+  char* dst = reinterpret_cast<char*>(d_dst);
+  std::vector<cudaError_t> errs((size_t)T, cudaSuccess);
+  auto work = [&](int t) {
+    cudaError_t e = cudaSetDevice(device_);
+    cudaStream_t st = up_streams_[t];
+    char* buf = static_cast<char*>(bounce_) + 2 * kChunk * (size_t)t;
+    if (e == cudaSuccess)
+      e = cudaStreamWaitEvent(st, up_start, 0);
+    int n = 0;
+    for (size_t i = (size_t)t; e == cudaSuccess && i < nchunks; i += (size_t)T, n++) {
+      const int b = n & 1;
+      const size_t len = std::min(kChunk, bytes - i * kChunk);
+      if (n >= 2)
+        e = cudaEventSynchronize(up_events_[3 * t + b]); // the DMA out of this buffer has finished
+      if (e != cudaSuccess)
+        break;
+      memcpy(buf + kChunk * b, src + i * kChunk, len);
+      e = cudaMemcpyAsync(dst + i * kChunk, buf + kChunk * b, len, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess)
+        e = cudaEventRecord(up_events_[3 * t + b], st);
+    }
+    if (e == cudaSuccess)
+      e = cudaEventRecord(up_events_[3 * t + 2], st);
+    errs[t] = e;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++)
+    pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool)
+    th.join();
+  for (int t = 0; t < T; t++)
+    ST_CUDA(errs[t]);
+  for (int t = 0; t < T; t++)
+    ST_CUDA(cudaStreamWaitEvent(stream_, up_events_[3 * t + 2], 0));
+  staged_bytes_ += bytes;
+  // the bounce buffers are reused by the next upload: that one starts by waiting for up_start on the solver
+  // stream, which is ordered after these copies
 }
 
 int

@@ -193,8 +193,41 @@ cudaHostAlloc(T** p, size_t bytes, unsigned)
 }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 enum { cudaHostRegisterDefault = 0 };
-inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
-inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+namespace emu_rt {
+inline std::mutex& pinned_mutex() { static std::mutex m; return m; }
+inline std::vector<std::pair<const char*, size_t>>& pinned_ranges() { static std::vector<std::pair<const char*, size_t>> v; return v; }
+} // namespace emu_rt
+inline cudaError_t
+cudaHostRegister(void* p, size_t n, unsigned)
+{
+  std::lock_guard<std::mutex> lock(emu_rt::pinned_mutex());
+  emu_rt::pinned_ranges().emplace_back(static_cast<const char*>(p), n);
+  return cudaSuccess;
+}
+inline cudaError_t
+cudaHostUnregister(void* p)
+{
+  std::lock_guard<std::mutex> lock(emu_rt::pinned_mutex());
+  auto& v = emu_rt::pinned_ranges();
+  for (size_t i = 0; i < v.size(); i++)
+    if (v[i].first == p) {
+      v.erase(v.begin() + i);
+      break;
+    }
+  return cudaSuccess;
+}
+inline cudaError_t
+cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p)
+{
+  std::lock_guard<std::mutex> lock(emu_rt::pinned_mutex());
+  a->type = cudaMemoryTypeUnregistered; // device memory is never asked about
+  for (auto& r : emu_rt::pinned_ranges())
+    if (static_cast<const char*>(p) >= r.first && static_cast<const char*>(p) < r.first + r.second)
+      a->type = cudaMemoryTypeHost;
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }

@@ -143,3 +143,36 @@ def test_the_environment_variable_reaches_the_unmodified_call_sequence():
     proc = subprocess.run([sys.executable, "-c", bad], cwd=ROOT, env=dict(env, ST_DEVICES="0,zero"), stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0 and "BAD_LIST_OK" in proc.stdout, proc.stdout[-3000:]
+
+
+def test_multi_threaded_upload_of_a_pageable_matrix_changes_nothing_but_the_transfer():
+    """ST_UPLOAD_THREADS (opt-in): a pageable host matrix is staged by several host threads through pinned double
+    buffers instead of by the driver.  Same bits; sizes that are not a multiple of the 4 MiB chunk; pinned sources
+    keep the direct path.  Fresh process: the variable is read when the context is created."""
+    emulated = os.environ.get("ST_EMULATED_LIB") == "1"
+    preamble = ("import sys; sys.path.insert(0, 'tests/cuda_emu'); import build as b\n"
+                "_lib._build.SO_PATH = b.build_library(); _lib._build.stale = lambda: False\n") if emulated else ""
+    code = ("import numpy as np, oracle\n"
+            "from eigen_value_b200 import _lib\n" + preamble +
+            "from eigen_value_b200 import EigenValue, Solver\n"
+            "ev = EigenValue(); staged = 0\n"
+            "for dim in (3000, 3072, 2900):\n"           # 34.3 / 36 / 32.08 MiB: above the 32 MiB threshold
+            "    mat = (oracle.uniform(dim, 77 + dim) + np.float32(0.5)).astype(np.float32)\n"
+            "    keep = mat.copy()\n"
+            "    val, vec, ms, it = ev.similarity_transform(mat)\n"
+            "    w = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)\n"
+            "    assert it == w[3] and val == w[0] and np.array_equal(vec, w[1]) and np.array_equal(mat, keep), dim\n"
+            "    staged += mat.nbytes\n"
+            "    assert ev.so_lib.st_staged_upload_bytes(ev.sycl_q) == staged, dim\n"
+            "    with ev.pinned(mat):\n"
+            "        got = ev.similarity_transform(mat)\n"
+            "    assert got[0] == val and np.array_equal(got[1], vec)\n"
+            "    assert ev.so_lib.st_staged_upload_bytes(ev.sycl_q) == staged        # pinned: the direct copy\n"
+            "s = Solver(0)\n"
+            "info, vec, plan = s.solve_streamed(oracle.hilbert(512), device_budget=4 * 64 * 512 * 4, block_rows=64)\n"
+            "assert info.iter_count == 12\n"
+            "print('UPLOAD_THREADS_OK')\n")
+    env = dict(os.environ, ST_UPLOAD_THREADS="3", PYTHONPATH=ROOT)
+    proc = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True, timeout=900)
+    assert proc.returncode == 0 and "UPLOAD_THREADS_OK" in proc.stdout, proc.stdout[-3000:]

@@ -37,4 +37,6 @@ for c in 0.5 0.9; do
   timeout 600 python tools/bench_streamed.py --dim 32768 --cached $c >> $O/first_call_bench_streamed.json 2>> $O/first_call_bench_n1.err
 done
 timeout 600 python tools/bench_streamed.py --dim 32768 --cached 0.5 --pinned 0 >> $O/first_call_bench_streamed.json 2>> $O/first_call_bench_n1.err
+# pageable host matrix through max_eigen_value: the driver's staging vs ST_UPLOAD_THREADS (opt-in until measured)
+timeout 600 python tools/bench_upload.py --dim 8192 > $O/first_call_bench_upload.json 2>> $O/first_call_bench_n1.err
 tail -5 $O/first_call_tests.txt
