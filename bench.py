@@ -219,10 +219,28 @@ def reference_arm(args, kind, dim, workload):
                 "oracle/_ref (the unmodified reference sources on a single-threaded CPU SYCL shim) is a "
                 "correctness reference, not a performance baseline: see ref_shim_sample",
         "ref_shim_sample": ref_shim_sample(),
+        "sequential_model_sample": sequential_model_sample(),
     }
     line["wall_s"] = round(time.time() - t0, 2)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def sequential_model_sample(dim: int = 1024):
+    """BASELINE.json configs[0]: Hilbert 1024 on the reference's sequential CPU model.  main.py itself cannot
+    travel to the GPU box, so its restatement (oracle/sequential.py, pinned bit for bit against fixtures made
+    by the unmodified main.py) is timed: one solve, single thread besides what numpy's BLAS uses."""
+    try:
+        import oracle
+        from oracle import sequential
+        mat = oracle.hilbert(dim)
+        ms, (val, _, rounds) = sequential.timed(mat, repeats=1)
+        return {"workload": f"hilbert-{dim}", "kind": "port of reference main.py (numpy; two dense N^3 products per round)",
+                "ms_to_converge": round(ms, 1), "rounds_main_py": int(rounds), "eigen_val": float(val),
+                "value": round(rounds * 4.0 * dim * dim / (ms * 1e-3) / 1e9, 4), "unit": "GB/s",
+                "note": "own stop rule (non-circular) and round count (rescales + 1): not comparable round for round"}
+    except Exception as exc:  # never let the side sample break the line
+        return {"error": str(exc)[:200]}
 
 
 def ref_shim_sample():
@@ -443,7 +461,8 @@ def main():
         gbs, ms_step, cpu_passes, text = run_cpu_steps(kind, cpu_dim, 8 if cpu_dim >= 8192 else 20, 1)
         cpu = {"value": round(gbs, 3), "unit": "GB/s", "cores": oracle.threads(), "kind": "port",
                "sample": f"{kind}-{cpu_dim}: {text}, 8 steps; OpenMP oracle (oracle/oracle.c)",
-               "ms_per_step": round(ms_step, 3)}
+               "ms_per_step": round(ms_step, 3),
+               "sequential_model": sequential_model_sample()}
 
     if rank == 0:
         peak, peak_src = measured_peak()

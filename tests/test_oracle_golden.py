@@ -201,3 +201,36 @@ def test_against_reference_main_py_fixture():
         assert abs(val - case["eigen_val"]) / case["eigen_val"] < 2e-3
         ref = np.array(case["eigen_vec"])
         assert np.max(np.abs(vec / vec.max() - ref / ref.max())) < 2e-3
+
+
+def test_sequential_model_restatement_reproduces_main_py_bit_for_bit():
+    """oracle/sequential.py restates reference main.py:13-47 with the same numpy operations: on the fixtures
+    generated from the unmodified main.py it must return the same value, vector and round count exactly
+    (same numpy -> same bits; another numpy build may reorder a BLAS sum, then 1e-6 relative)."""
+    from oracle import sequential
+    g = _load("main_py.json")
+    same_numpy = g.get("numpy") == np.__version__
+    for case in g["cases"]:
+        mat = np.array(case["matrix"], dtype=np.float32)
+        val, vec, rounds = sequential.max_eigen_value_and_vector(mat)
+        assert rounds == case["rounds_main_py"], case["name"]
+        if same_numpy:
+            assert float(val) == case["eigen_val"] and [float(x) for x in vec] == case["eigen_vec"], case["name"]
+        else:
+            assert abs(float(val) - case["eigen_val"]) <= 1e-6 * case["eigen_val"]
+            assert np.allclose(vec, case["eigen_vec"], rtol=1e-6, atol=0)
+
+
+def test_sequential_model_against_the_unmodified_main_py_when_the_reference_tree_is_here():
+    import importlib.util
+    path = "/root/reference/main.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle import sequential
+    spec = importlib.util.spec_from_file_location("reference_main", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for mat in (oracle.hilbert(256), (oracle.uniform(100, 9) + np.float32(0.1)).astype(np.float32)):
+        a = ref.max_eigen_value_and_vector(mat)
+        b = sequential.max_eigen_value_and_vector(mat)
+        assert a[2] == b[2] and a[0] == b[0] and np.array_equal(a[1], b[1])
