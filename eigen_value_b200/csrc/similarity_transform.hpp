@@ -81,7 +81,7 @@ private:
   void reserve_vectors(uint32_t dim, uint32_t max_iter);
   void reserve_matrix(size_t elems);
   void reserve_work(size_t elems);
-  void copy_h2d(float* d_dst, const float* h_src, size_t bytes);
+  void copy_h2d(float* d_dst, const float* h_src, size_t bytes, CUstream_st* stream = nullptr);
 
   int device_ = 0;
   int sm_count_ = 0;
@@ -115,6 +115,7 @@ private:
   void* bounce_ = nullptr;
   std::vector<CUstream_st*> up_streams_;
   std::vector<CUevent_st*> up_events_;
+  std::vector<char> up_used_; // per thread x buffer: has its event ever been recorded
   std::vector<uint64_t> last_ts_;
   std::vector<uint64_t> last_phase_ts_;
 };

@@ -770,8 +770,10 @@ Context::upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Sh
 // their own pinned double buffers and feed the copy engine from there, so staging and DMA overlap and
 // the host-side memcpy is spread over T cores.
 void
-Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
+Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes, cudaStream_t stream)
 {
+  if (!stream)
+    stream = stream_;
   constexpr size_t kChunk = 4ull << 20;
   bool staged = upload_threads_ > 0 && bytes >= 8 * kChunk;
   if (staged) {
@@ -784,7 +786,7 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
     }
   }
   if (!staged) {
-    ST_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream_));
+    ST_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
     return;
   }
   const int T = upload_threads_;
@@ -800,13 +802,14 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
         up_events_.push_back(ev);
       }
     }
+    up_used_.assign(2 * (size_t)T, 0);
     cudaEvent_t start = nullptr; // last entry: "the solver stream has reached this upload"
     ST_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     up_events_.push_back(start);
   }
-  // the destination may still be read by earlier work on the solver stream
+  // the destination may still be read by earlier work on the target stream
   cudaEvent_t up_start = up_events_.back();
-  ST_CUDA(cudaEventRecord(up_start, stream_));
+  ST_CUDA(cudaEventRecord(up_start, stream));
   const size_t nchunks = (bytes + kChunk - 1) / kChunk;
   const char* src = reinterpret_cast<const char*>(h_src);
   char* dst = reinterpret_cast<char*>(d_dst);
@@ -821,7 +824,7 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
     for (size_t i = (size_t)t; e == cudaSuccess && i < nchunks; i += (size_t)T, n++) {
       const int b = n & 1;
       const size_t len = std::min(kChunk, bytes - i * kChunk);
-      if (n >= 2)
+      if (n >= 2 || up_used_[2 * t + b]) // also across calls: the streamed solve uploads block after block
         e = cudaEventSynchronize(up_events_[3 * t + b]); // the DMA out of this buffer has finished
       if (e != cudaSuccess)
         break;
@@ -829,6 +832,7 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
       e = cudaMemcpyAsync(dst + i * kChunk, buf + kChunk * b, len, cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess)
         e = cudaEventRecord(up_events_[3 * t + b], st);
+      up_used_[2 * t + b] = 1;
     }
     if (e == cudaSuccess)
       e = cudaEventRecord(up_events_[3 * t + 2], st);
@@ -843,10 +847,11 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes)
   for (int t = 0; t < T; t++)
     ST_CUDA(errs[t]);
   for (int t = 0; t < T; t++)
-    ST_CUDA(cudaStreamWaitEvent(stream_, up_events_[3 * t + 2], 0));
+    ST_CUDA(cudaStreamWaitEvent(stream, up_events_[3 * t + 2], 0));
   staged_bytes_ += bytes;
-  // the bounce buffers are reused by the next upload: that one starts by waiting for up_start on the solver
-  // stream, which is ordered after these copies
+  // the bounce buffers are reused by the next upload: that one starts by waiting for up_start on its target
+  // stream; the callers' streams are ordered after these copies before the buffers can be reused (solve_streamed
+  // synchronises per round, solve_host per call)
 }
 
 int
@@ -1170,8 +1175,7 @@ st::Context::solve_streamed(const float* h_mat, uint32_t dim, const st_options& 
       const uint32_t rows = block_rows_of(b);
       if (slot_used[slot]) // the pass that last read this slot must be done before it is overwritten
         ST_CUDA(cudaStreamWaitEvent(copy_stream_, slot_free_[slot], 0));
-      ST_CUDA(cudaMemcpyAsync(slot_ptr(slot), h_mat + (size_t)b * B * dim, row_bytes * rows, cudaMemcpyHostToDevice,
-                              copy_stream_));
+      copy_h2d(slot_ptr(slot), h_mat + (size_t)b * B * dim, row_bytes * rows, copy_stream_);
       ST_CUDA(cudaEventRecord(slot_ready_[slot], copy_stream_));
       ST_CUDA(cudaStreamWaitEvent(stream_, slot_ready_[slot], 0));
       launch_row_pass(*this, slot_ptr(slot), E, S, dim, b * B, rows);

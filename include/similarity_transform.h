@@ -158,8 +158,9 @@ int st_pin_host(void* ctx, void* hptr, size_t bytes);
 int st_unpin_host(void* ctx, void* hptr);
 /* Opt-in alternative for matrices the caller cannot pin: with ST_UPLOAD_THREADS=T in the environment when the
  * context is created (T = 1..16), pageable host matrices of 32 MiB and up are copied by T host threads through
- * pinned double buffers (4 MiB chunks) instead of through the driver's single staging path.  Pinned / registered
- * sources keep the direct copy.  st_staged_upload_bytes reports how many bytes took that path on this context. */
+ * pinned double buffers (4 MiB chunks) instead of through the driver's single staging path (max_eigen_value,
+ * st_solve_host, and the block uploads of st_solve_streamed / st_solve_file, where the threads also spread the
+ * page faults of a file mapping).  Pinned / registered sources keep the direct copy.  st_staged_upload_bytes reports how many bytes took that path on this context. */
 uint64_t st_staged_upload_bytes(void* ctx);
 
 /* Input generation on the device, rows [row0, row0+rows) of the dim x dim matrix written

@@ -170,7 +170,13 @@ def test_multi_threaded_upload_of_a_pageable_matrix_changes_nothing_but_the_tran
             "    assert ev.so_lib.st_staged_upload_bytes(ev.sycl_q) == staged        # pinned: the direct copy\n"
             "s = Solver(0)\n"
             "info, vec, plan = s.solve_streamed(oracle.hilbert(512), device_budget=4 * 64 * 512 * 4, block_rows=64)\n"
-            "assert info.iter_count == 12\n"
+            "assert info.iter_count == 12 and s.lib.st_staged_upload_bytes(s.ctx) == 0      # blocks below 32 MiB: direct\n"
+            "big = oracle.hilbert(6144)                                  # three blocks of 2048 rows = 48 MiB, two slots\n"
+            "info, vec, plan = s.solve_streamed(big, device_budget=2 * 2048 * 6144 * 4 + 4096, block_rows=2048, max_iter=3)\n"
+            "w = oracle.similarity_transform(big, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA, max_itr=3)\n"
+            "assert info.iter_count == w[3] and info.eigen_val == w[0] and np.array_equal(vec, w[1])\n"
+            "assert plan['blocks'] == 3 and plan['slots'] == 2 and plan['h2d_bytes_total'] == 5 * 2048 * 6144 * 4\n"
+            "assert s.lib.st_staged_upload_bytes(s.ctx) == plan['h2d_bytes_total'] > big.nbytes    # every block upload was staged\n"
             "print('UPLOAD_THREADS_OK')\n")
     env = dict(os.environ, ST_UPLOAD_THREADS="3", PYTHONPATH=ROOT)
     proc = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
