@@ -138,6 +138,38 @@ main()
     int64_t tm = similarity_transform(q, h.data(), &lam, ev.data(), dim, dim >> 1, &itr);
     CHECK(tm >= 0 && itr == 13); // README.md:73
     std::printf("%-5ux%5u\t\t\t%10ld ms\t\t\t%6u round(s)   lambda = %.7f\n", dim, dim, (long)tm, itr, lam);
+
+    // ---- the same matrix streamed through a device cache of a quarter of its rows (st::Context::solve_streamed):
+    //      the step before the path in the reference is the whole-matrix copy-in (similarity_transform.cpp:14-19) ----
+    st_options opt;
+    st_default_options(&opt);
+    st_result res{};
+    st_stream_plan plan{};
+    std::vector<float> ev_streamed(dim);
+    float lam_streamed = 0.f;
+    CHECK(q.solve_streamed(h.data(), dim, opt, sizeof(float) * dim * (dim / 4), 64, &lam_streamed, ev_streamed.data(), &res,
+                           &plan) == ST_OK);
+    CHECK(res.iter_count == 13 && plan.streamed == 1 && plan.blocks == 16 && plan.slots == 4);
+    CHECK(plan.h2d_bytes_first == sizeof(float) * dim * dim && plan.h2d_bytes_per_round == sizeof(float) * dim * 64 * 12);
+    CHECK(lam_streamed == lam);
+    for (uint i = 0; i < dim; i++)
+      CHECK(ev_streamed[i] == ev[i]);
+    std::printf("streamed solve: same bits, %u blocks through %u slots, %.1f MiB over PCIe per later round\n", plan.blocks,
+                plan.slots, plan.h2d_bytes_per_round / 1048576.0);
+
+    // ---- every GPU of the box behind the one handle (st_group_attach), when there is more than one ----
+    if (st_device_count() > 1) {
+      CHECK(st_group_attach(ctx, nullptr, 0, 256) == ST_OK && st_group_size(ctx) == st_device_count());
+      std::vector<float> ev_group(dim);
+      float lam_group = 0.f;
+      uint itr_group = 0;
+      CHECK(max_eigen_value(ctx, h.data(), &lam_group, ev_group.data(), dim, &itr_group) >= 0);
+      CHECK(itr_group == 13 && lam_group == lam);
+      for (uint i = 0; i < dim; i++)
+        CHECK(ev_group[i] == ev[i]);
+      CHECK(st_group_detach(ctx) == ST_OK && st_group_size(ctx) == 1);
+      std::printf("device group of %d GPUs behind max_eigen_value: same bits\n", st_device_count());
+    }
   }
   std::printf("\nall checks passed\n");
   return 0;

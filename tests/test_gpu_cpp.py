@@ -34,3 +34,22 @@ def test_reference_cpp_scenarios_pass_on_the_gpu():
     assert proc.returncode == 0, proc.stdout
     assert "all checks passed" in proc.stdout
     assert "[ 4 iterations ]" in proc.stdout and "13 round(s)" in proc.stdout
+
+
+def test_cpp_acceptance_on_the_emulated_library():
+    """The same C++ program linked against the library built on the CPU emulation harness (tests/cuda_emu, TEST
+    INFRASTRUCTURE), two pretend GPUs: the reference's tests/test.cpp scenarios, the streamed solve and the device
+    group behind max_eigen_value run through the C++ entry points where no GPU exists."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emu"))
+    import build as emu_build
+    lib = emu_build.build_library()
+    exe = os.path.join(ROOT, "tests", "cuda_emu", "cpp_acceptance_emu.bin")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", SRC, "-o", exe, f"-L{os.path.dirname(lib)}", f"-l:{os.path.basename(lib)}",
+           f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    subprocess.run(cmd, check=True)
+    env = dict(os.environ, ST_EMU_DEVICES="2", ST_EMU_SMS="8")
+    proc = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout
+    assert "all checks passed" in proc.stdout and "[ 4 iterations ]" in proc.stdout and "13 round(s)" in proc.stdout
+    assert "streamed solve: same bits" in proc.stdout and "device group of 2 GPUs" in proc.stdout
