@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sweep-table", action="store_true")
+    ap.add_argument("--scale-base-dim", type=int, default=32768,
+                    help="N=1 only: also time Hilbert of this size (the sharded runs' workload) as the strong-scaling base; 0 = skip")
     return ap.parse_args()
 
 
@@ -453,6 +455,23 @@ def main():
             d.free()
         d_sweep_vec.free()
 
+    # ---- the sharded runs' workload on this one GPU: the strong-scaling base of the N = 2, 4, 8 lines ----
+    # (the driver's default N=1 call measures configs[1]'s roofline point, Hilbert 8192; its N>1 calls measure
+    # configs[2], Hilbert 32768 row-block sharded -- this puts the 1-GPU figure of THAT workload in the same line)
+    scale_base = None
+    if world == 1 and args.scale_base_dim > 0 and not args.no_sweep_table and not bf16:
+        n = args.scale_base_dim
+        d = solver.hilbert(n)
+        d_v = solver.alloc(4 * n)
+        runs = [solver.solve_device(d, n, d_eigen_vec=d_v, **opts)[0] for _ in range(3 + 5)][3:]
+        ms = sum(i.loop_ms for i in runs) / len(runs)
+        scale_base = {"workload": f"hilbert-{n}", "n_gpus": 1, "steps": len(runs), "warmup": 3,
+                      "value": round(sum(i.passes for i in runs) * 4.0 * n * n / (ms * len(runs) * 1e-3) / 1e9, 3),
+                      "unit": "GB/s", "ms_to_converge": round(ms, 4), "rounds": runs[-1].iter_count,
+                      "l2": "matrix larger than L2; no flush" if 4 * n * n > 2 * solver.l2_bytes else "L2-resident"}
+        d.free()
+        d_v.free()
+
     # ---- CPU baseline beside it (rank 0, N=1) ----
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
@@ -498,6 +517,8 @@ def main():
         }
         if table is not None:
             line["hilbert_sweep"] = table
+        if scale_base is not None:
+            line["strong_scaling_base"] = scale_base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

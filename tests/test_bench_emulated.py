@@ -23,7 +23,7 @@ def run(*args, timeout=900):
 
 def test_default_shape_of_the_line_with_e2e_sweep_table_and_cpu_baseline():
     # a workload smaller than the sweep's largest size: the sweep must not reuse the workload's output vector
-    line = run("--workload", "hilbert-256", "--steps", "2", "--warmup", "1")
+    line = run("--workload", "hilbert-256", "--steps", "2", "--warmup", "1", "--scale-base-dim", "512")
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in line, key
@@ -34,12 +34,15 @@ def test_default_shape_of_the_line_with_e2e_sweep_table_and_cpu_baseline():
     assert line["e2e"]["h2d_bytes_per_step"] == 4 * 256 * 256 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert [r["rounds"] for r in line["hilbert_sweep"]] == [9, 10, 12, 13, 14, 15, 17]      # reference README.md:70-76
+    assert line["strong_scaling_base"]["workload"] == "hilbert-512" and line["strong_scaling_base"]["rounds"] == 12
+    assert line["cpu_baseline"]["sequential_model"]["rounds_main_py"] == 11                # main.py on Hilbert 1024
 
 
 @pytest.mark.parametrize("extra,rounds", [(("--stop", "relative", "--eps", "1e-6"), None), (("--storage", "bf16"), 13),
                                           (("--accumulate", "f64"), 13)])
 def test_opt_in_switches(extra, rounds):
     line = run("--workload", "hilbert-1024", "--steps", "2", "--no-cpu-baseline", "--no-sweep-table", *extra)
+    assert "strong_scaling_base" not in line
     if rounds is not None:
         assert line["rounds"] == rounds
     if "--storage" in extra:
@@ -79,3 +82,18 @@ def test_group_bench_tool_on_the_emulated_library():
     assert proc.returncode == 0, proc.stderr[-3000:]
     line = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["bit_identical"] is True and line["rounds"] == 12 and line["group"]["gpus"] == 4
+
+
+def test_upload_bench_tool_on_the_emulated_library():
+    # tools/bench_upload.py's per-setting child (pageable matrix, ST_UPLOAD_THREADS read at handle creation)
+    code = ("import os, sys; sys.path.insert(0, 'tests/cuda_emu'); os.environ.setdefault('ST_EMU_SMS', '8');"
+            "import build as b; from eigen_value_b200 import _lib;"
+            "_lib._build.SO_PATH = b.build_library(); _lib._build.stale = lambda: False;"
+            "sys.path.insert(0, 'tools'); import bench_upload;"
+            "sys.exit(bench_upload.child(3000, 1))")
+    for threads, staged in (("0", 0), ("3", 2 * 4 * 3000 * 3000)):      # two pageable solves; the pinned ones go direct
+        proc = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, ST_UPLOAD_THREADS=threads),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-3000:]
+        line = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+        assert line["upload_threads"] == int(threads) and line["staged_bytes"] == staged and line["rounds"] == 15
