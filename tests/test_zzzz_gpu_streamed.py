@@ -158,3 +158,32 @@ def test_bad_arguments_are_refused_cleanly(solver, tmp_path):
     # the context is fine afterwards
     info, _ = solver.solve_device(solver.hilbert(256), 256)
     assert info.iter_count == 10
+
+
+def test_random_block_and_cache_shapes_never_change_a_bit(solver):
+    # 80 random (dim, block_rows, slots) plans, both sweep parities of every cache geometry: always the in-device bits,
+    # always (blocks - slots) blocks per later round, or a clean refusal when the budget holds one block of several
+    rng = np.random.default_rng(20261018)
+    for _ in range(80):
+        dim = int(rng.integers(1, 200))
+        block_rows = int(rng.integers(1, dim + 1))
+        blocks = -(-dim // block_rows)
+        slots = int(rng.integers(1, blocks + 2))
+        mat = (rng.random((dim, dim), dtype=np.float32) + np.float32(0.05)).astype(np.float32)
+        budget = slots * block_rows * dim * 4 + int(rng.integers(0, 4 * dim))          # slack below one more block
+        if slots < 2 and blocks > 1:
+            with pytest.raises(Exception, match="two row blocks"):
+                solver.solve_streamed(mat, device_budget=budget, block_rows=block_rows)
+            continue
+        cap = int(rng.integers(1, 9))
+        info, vec, plan = solver.solve_streamed(mat, device_budget=budget, block_rows=block_rows, max_iter=cap)
+        base, base_vec = solver.solve_host(mat, max_iter=cap)
+        assert info.iter_count == base.iter_count and info.passes == base.passes, (dim, block_rows, slots)
+        assert np.float32(info.eigen_val).view(np.uint32) == np.float32(base.eigen_val).view(np.uint32)
+        assert np.array_equal(vec.view(np.uint32), base_vec.view(np.uint32)), (dim, block_rows, slots)
+        assert plan["blocks"] == blocks and plan["slots"] == min(slots, blocks)
+        rows_missed = plan["h2d_bytes_per_round"] // (4 * dim)
+        if info.passes > 1:
+            missed = blocks - plan["slots"]
+            last_rows = dim - (blocks - 1) * block_rows
+            assert rows_missed in (missed * block_rows, max(0, missed - 1) * block_rows + (last_rows if missed else 0))
