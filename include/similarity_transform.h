@@ -7,8 +7,10 @@
  * meaning, same return value; plain pointers and sizes only.
  *
  * Part 2 is additive (st_*): device-resident inputs, on-device input generation,
- * per-kernel entry points mirroring include/similarity_transform.hpp:55-100, and the
- * row-block sharded multi-GPU solve.  None of it changes Part 1.
+ * per-kernel entry points mirroring include/similarity_transform.hpp:55-100, the row-block
+ * sharded multi-GPU solve (one process per GPU, or every GPU of the box behind one handle), and
+ * the streamed solve of host / file-backed matrices larger than the device.  None of it changes
+ * Part 1.
  *
  * Error convention (the reference has none: wrapper/similarity_transform.cpp never checks):
  * no exception ever crosses this boundary; st_* return 0 on success and a negative code on
