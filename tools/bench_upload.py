@@ -21,7 +21,6 @@ sys.path.insert(0, ROOT)
 
 
 def child(dim: int, steps: int) -> int:
-    import numpy as np
     import oracle
     from eigen_value_b200 import EigenValue
 
