@@ -41,6 +41,7 @@ def test_python_binding_table_matches_header():
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.StOptions) == 40
     assert ctypes.sizeof(_lib.StResult) == 56
+    assert ctypes.sizeof(_lib.StStreamPlan) == 48        # 4 x uint32 + 4 x uint64 (st_stream_plan)
 
 
 def test_library_is_sm100a_and_uses_no_cpu_fallback():
