@@ -95,4 +95,32 @@ cluster_ctas_for(uint32_t dim, size_t* smem_bytes)
   return best;
 }
 
+// Streamed solve (Context::solve_streamed): rows per block, number of blocks and cache slots for a
+// dim x dim fp32 host matrix and a device budget in bytes.  block_rows == 0 asks for blocks of about
+// `auto_block_bytes`, halved until two of them fit the budget.  Returns false when the budget holds
+// fewer than two blocks of a matrix that has several (no double buffering possible).
+struct StreamShape
+{
+  uint32_t block_rows, blocks, slots;
+};
+inline bool
+stream_shape_for(uint32_t dim, size_t budget, uint32_t block_rows, size_t auto_block_bytes, StreamShape* out)
+{
+  const size_t row_bytes = sizeof(float) * (size_t)dim;
+  uint32_t b = block_rows ? (block_rows < dim ? block_rows : dim) : (uint32_t)(auto_block_bytes / row_bytes);
+  if (!block_rows) {
+    b = b < 1u ? 1u : (b > dim ? dim : b);
+    while (b > 1u && budget / (row_bytes * b) < 2)
+      b = (b + 1u) / 2u;
+  }
+  const uint32_t nb = (dim + b - 1u) / b;
+  const uint64_t fit = budget / (row_bytes * b);
+  if (fit < 2 && nb > 1u)
+    return false;
+  out->block_rows = b;
+  out->blocks = nb;
+  out->slots = (uint32_t)(fit < 1 ? 1 : (fit < nb ? fit : nb));
+  return true;
+}
+
 } // namespace st

@@ -1088,18 +1088,12 @@ st::Context::solve_streamed(const float* h_mat, uint32_t dim, const st_options& 
     }
   }
 
-  // ---- plan: rows per block, blocks, cache slots ----
-  uint32_t B = block_rows ? std::min(block_rows, dim)
-                          : (uint32_t)std::max<size_t>(1, std::min<size_t>(dim, kStreamBlockBytes / row_bytes));
-  if (!block_rows)
-    while (B > 1 && budget / (row_bytes * B) < 2)
-      B = (B + 1) / 2;
-  const uint32_t nb = (dim + B - 1) / B;
-  const size_t block_bytes = row_bytes * B;
-  const uint64_t fit = budget / block_bytes;
-  if (fit < 2 && nb > 1)
+  // ---- plan: rows per block, blocks, cache slots (launch_plan.hpp) ----
+  StreamShape shape{};
+  if (!stream_shape_for(dim, budget, block_rows, kStreamBlockBytes, &shape))
     throw std::invalid_argument("solve_streamed: the device budget holds fewer than two row blocks");
-  const uint32_t C = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(fit, 1));
+  const uint32_t B = shape.block_rows, nb = shape.blocks, C = shape.slots;
+  const size_t block_bytes = row_bytes * B;
   reserve_matrix((size_t)C * B * dim);
   reserve_vectors(dim, opt.max_iter);
   if (!copy_stream_)

@@ -187,3 +187,15 @@ def test_random_block_and_cache_shapes_never_change_a_bit(solver):
             missed = blocks - plan["slots"]
             last_rows = dim - (blocks - 1) * block_rows
             assert rows_missed in (missed * block_rows, max(0, missed - 1) * block_rows + (last_rows if missed else 0))
+
+
+def test_automatic_block_size_halves_until_two_blocks_fit_the_budget(solver):
+    # block_rows = 0: about 64 MiB per block, halved until the budget holds two (launch_plan.hpp: stream_shape_for)
+    dim = 1000
+    mat = _matrix("hilbert", dim)
+    info, vec, plan = solver.solve_streamed(mat, device_budget=1_000_000)       # 250 rows of 4000 bytes
+    _same_bits(info, vec, _want(mat))
+    assert plan["block_rows"] == 125 and plan["blocks"] == 8 and plan["slots"] == 2 and plan["cache_bytes"] == 2 * 125 * 4000
+    # a budget below two rows cannot double-buffer anything
+    with pytest.raises(Exception, match="two row blocks"):
+        solver.solve_streamed(mat, device_budget=7000)
