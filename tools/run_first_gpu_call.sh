@@ -39,4 +39,10 @@ done
 timeout 600 python tools/bench_streamed.py --dim 32768 --cached 0.5 --pinned 0 >> $O/first_call_bench_streamed.json 2>> $O/first_call_bench_n1.err
 # pageable host matrix through max_eigen_value: the driver's staging vs ST_UPLOAD_THREADS (opt-in until measured)
 timeout 600 python tools/bench_upload.py --dim 8192 > $O/first_call_bench_upload.json 2>> $O/first_call_bench_n1.err
+# zero-code experiment for the Hilbert-8192 last wave: 8192 units over 148 x W warps -- W = 14 gives 3.95
+# units per warp (a nearly full last wave) against 3.46 at W = 16
+for t in 384 416 448 480 512; do
+  timeout 300 python bench.py --threads $t --steps 20 --no-e2e --no-cpu-baseline --no-sweep-table \
+    >> $O/first_call_bench_threads_sweep.json 2>> $O/first_call_bench_n1.err
+done
 tail -5 $O/first_call_tests.txt
