@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
                     help="f32 = the reference's matrix format (default, the headline); bf16 = opt-in bfloat16 storage "
                          "of the matrix with fp32 accumulation (changes results; bytes counted at 2 per element)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 LDG; 2-9 TMA ring; 10-19 single-chunk variants")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 general loop; 2-9 TMA ring; 10-19 resident-e variants; 21-23 resident-e + L2 prefetch across the barrier")
     ap.add_argument("--sweep", type=int, default=None)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)

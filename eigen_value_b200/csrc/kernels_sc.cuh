@@ -85,10 +85,11 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
 }
 
 template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float,
-         typename ACC = float>
+         typename ACC = float, int L2PF = 0>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
   static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
+  static_assert(L2PF == 0 || sizeof(T) == 4, "the L2 prefetch variant is built for fp32 storage");
   // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -281,6 +282,20 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         bulk_load(my_pf, p.A + (size_t)rl * N + (size_t)ch * kChunkCols, bytes, my_bar);
       }
       pf_issued++;
+    }
+    // L2PF > 0 (tuning variants 21-23): keep HBM busy across the barrier and the vector tail as well.  The
+    // units every warp reads FIRST in the next round are the ones this round ended on (alternating sweep:
+    // L2 hits); the ones read SECOND come from HBM.  Lane 0 asks for the first L2PF KB of the unit this warp
+    // takes second (cur = TW + gw in the next round's order) to be pulled into L2 while the grid synchronises
+    // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  A hint only: no effect on any result.
+    if (L2PF > 0 && !resident && lane == 0 && k + 1u < p.max_iter && TW + gw < U) {
+      const uint32_t cur_n = TW + gw;
+      const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - cur_n) : cur_n;
+      const uint32_t rl = u / nch;
+      const uint32_t ch = u - rl * nch;
+      const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
+      l2_prefetch_bulk(reinterpret_cast<const float*>(p.A) + (size_t)rl * N + (size_t)ch * kChunkCols,
+                       min((uint32_t)L2PF * 1024u, seg_nv * 16u));
     }
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);

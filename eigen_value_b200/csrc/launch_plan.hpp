@@ -62,7 +62,14 @@ struct ScConfig
 inline const ScConfig kScConfigs[] = {
   { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 }, { 14, 1024, 1 }, { 15, 1024, 0 },
   { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
+  // configuration 13 plus an L2 prefetch of 8 / 16 / 32 KB per warp across the round barrier (explicit only)
+  { 21, 512, 1 }, { 22, 512, 1 }, { 23, 512, 1 },
 };
+inline bool
+is_sc_kernel_id(int id)
+{
+  return (id >= 10 && id < 20) || (id >= 21 && id <= 23);
+}
 
 inline size_t
 sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t rows_cap, uint32_t* mbar_offset)

@@ -197,6 +197,14 @@ bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t*
                : "memory");
 }
 
+// Asks the memory system to pull [src_gmem, src_gmem + bytes) into L2 (no destination, no completion to
+// wait for; SASS UBLKPF.L2).  16-byte aligned address, size a multiple of 16.  A hint: never changes a result.
+__device__ __forceinline__ void
+l2_prefetch_bulk(const float* src_gmem, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void
 fence_mbarrier_init()
 {

@@ -299,6 +299,10 @@ launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStre
                                       stream));
 }
 
+template<typename K>
+static void
+launch_cooperative(K kernel, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream);
+
 static void
 launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
@@ -322,6 +326,9 @@ launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t 
     case 17: return launch_sc_one<256, 4, 16>(p, grid, threads, smem, stream);
     case 18: return launch_sc_one<256, 0, 16>(p, grid, threads, smem, stream);
     case 19: return launch_sc_one<256, 1, 16>(p, grid, threads, smem, stream);
+    case 21: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 8>, p, grid, threads, smem, stream);
+    case 22: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16>, p, grid, threads, smem, stream);
+    case 23: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 32>, p, grid, threads, smem, stream);
     default: throw std::invalid_argument("unknown resident-e kernel id");
   }
 }
@@ -553,7 +560,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     grid = cluster_ctas;
     threads = kClusterThreads;
   }
-  if (!cluster_ctas && ((opt.kernel >= 10 && opt.kernel < kClusterKernelId) ||
+  if (!cluster_ctas && (is_sc_kernel_id(opt.kernel) ||
                         (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols))) {
     if (!readonly4 || dim > (uint32_t)kResidentCols)
       throw std::invalid_argument("solve: resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
@@ -568,8 +575,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
-      if (opt.kernel == 0 && pinned > c.max_threads)
-        continue;
+      if (opt.kernel == 0 && (pinned > c.max_threads || c.id > kClusterKernelId))
+        continue; // the L2-prefetch variants (21-23) are never chosen automatically
       if (bf16 && c.id != kScBf16Id)
         continue; // bf16 storage is built for configuration 11 only
       if (opt.kernel == 0 && !bf16 && (stop == kStopRelative || acc64) && c.id != 13 && c.id != 10 && c.id != 12)

@@ -127,8 +127,8 @@ class SolveInfo:
 
     @property
     def kernel_name(self) -> str:
-        key = 30 if self.kernel_id >= 30 else 20 if self.kernel_id >= 20 else 10 if self.kernel_id >= 10 else \
-            2 if self.kernel_id >= 2 else 1
+        k = self.kernel_id
+        key = 30 if k >= 30 else 10 if 21 <= k <= 23 else 20 if k >= 20 else 10 if k >= 10 else 2 if k >= 2 else 1
         return self.KERNEL_NAMES[key]
 
     @classmethod

@@ -123,6 +123,18 @@ bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t*
   bulk_load(dst_smem, src_gmem, bytes, bar);
 }
 inline void
+l2_prefetch_bulk(const float* src_gmem, uint32_t bytes)
+{
+  if (bytes == 0u || bytes % 16u != 0u || (reinterpret_cast<uintptr_t>(src_gmem) & 15u)) {
+    fprintf(stderr, "cuda_emu: L2 bulk prefetch with misaligned address or size (%u bytes)\n", bytes);
+    abort(); // the hardware would fault
+  }
+  // touch both ends so that an out-of-bounds hint is caught by the address sanitiser / a guard page
+  volatile float first = src_gmem[0], last = src_gmem[bytes / 4u - 1u];
+  (void)first;
+  (void)last;
+}
+inline void
 fence_mbarrier_init()
 {
   __atomic_thread_fence(__ATOMIC_SEQ_CST);

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def cases(draw):
     # mostly supported combinations (so that the planner and the kernels are what is exercised), some not
     dim = draw(st.one_of(st.integers(1, 150).map(lambda k: 8 * k), st.integers(1, 300).map(lambda k: 4 * k), st.integers(1, 1200)))
-    kernel = draw(st.sampled_from([0, 0, 0, 1, 1, 2, 5, 9, 10, 11, 12, 13, 13, 14, 16, 19, 20]))
+    kernel = draw(st.sampled_from([0, 0, 0, 1, 1, 2, 5, 9, 10, 11, 12, 13, 13, 14, 16, 19, 20, 21, 23]))
     wild = draw(st.integers(0, 9)) == 0
     bf16 = draw(st.booleans()) if (wild or (kernel in (0, 1, 11) and dim % 8 == 0)) else False
     acc64 = draw(st.booleans()) if (wild or (not bf16 and kernel in (0, 1, 10, 12, 13))) else False

@@ -45,4 +45,7 @@ for t in 384 416 448 480 512; do
   timeout 300 python bench.py --threads $t --steps 20 --no-e2e --no-cpu-baseline --no-sweep-table \
     >> $O/first_call_bench_threads_sweep.json 2>> $O/first_call_bench_n1.err
 done
+# L2 prefetch across the round barrier (kernels 21-23) against the default configuration 13: one GPU and sizes where
+# barrier + tail are a visible share of the round
+KERNELS=13,21,22,23 timeout 600 python tools/sweep_kernels.py 4096 8192 16384 32768 > $O/first_call_sweep_l2_prefetch.txt 2>&1
 tail -5 $O/first_call_tests.txt
