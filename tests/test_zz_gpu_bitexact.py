@@ -85,9 +85,9 @@ def test_in_place_form_is_bit_identical_to_the_oracle(solver, dim):
     _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, FORM_INPLACE), f"in-place {dim}")
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 13, 11, 22])
+@pytest.mark.parametrize("kernel", [1, 2, 13, 11])
 def test_every_kernel_family_is_bit_identical_to_the_oracle(solver, kernel):
-    # general loop, TMA ring, resident-e with and without the cross-barrier prefetch (22: plus the L2 prefetch), at a size where
+    # general loop, TMA ring, resident-e with and without the cross-barrier prefetch, at a size where
     # rows span two work units (two 8192-column chunks)
     dim = 9216
     mat = _matrix("uniform", dim)
@@ -227,21 +227,3 @@ def test_eigenvalues_printed_by_the_b200_in_round_1_are_reproduced(ev):
             continue                                          # kept cheap: the larger sizes are covered above
         val, vec, ms, it = ev.similarity_transform(oracle.hilbert(n))
         assert it == int(rounds) and "%.7f" % float(val) == lam, (n, it, float(val), lam)
-
-
-@pytest.mark.parametrize("dim", [2052, 4100, 8200])
-def test_l2_prefetch_variants_are_hints_only(solver, dim):
-    """Kernels 21-23 = resident-e configuration 13 plus a bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the unit
-    every warp takes second in the next round, issued before the round barrier.  A hint cannot change a bit:
-    alternating / forward / static sweeps, rows of one and of two work units (8200: the second unit is 8 columns)."""
-    mat = _matrix("uniform", dim)
-    cap = 4
-    want = _oracle(mat, max_itr=cap)
-    d = solver.upload(mat)
-    for kid in (21, 22, 23):
-        for sweep in (1, 0, 3):
-            info, vec = solver.solve_device(d, dim, kernel=kid, max_iter=cap, sweep=sweep)
-            assert info.kernel_id == kid
-            _assert_same_bits((info.eigen_val, vec, info.iter_count), want, f"kernel {kid} sweep {sweep}")
-    with pytest.raises(Exception):
-        solver.solve_device(d, dim, kernel=22, stop=STOP_RELATIVE)          # tuning variants: absolute stop only
