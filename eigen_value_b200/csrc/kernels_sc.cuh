@@ -85,11 +85,11 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
 }
 
 template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float,
-         typename ACC = float, int L2PF = 0>
+         typename ACC = float, int L2PF = 0, int L2AHEAD = 0>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
   static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
-  static_assert(L2PF == 0 || sizeof(T) == 4, "the L2 prefetch variant is built for fp32 storage");
+  static_assert((L2PF == 0 && L2AHEAD == 0) || sizeof(T) == 4, "the L2 prefetch variants are built for fp32 storage");
   // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -217,6 +217,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
+          // L2AHEAD > 0 (tuning variants 24-26, static scheduling only: the next unit is known): while this
+          // unit streams, ask for the head of the warp's NEXT unit to be pulled into L2 -- the SM side then
+          // reads at L2 latency and the DRAM side sees large bulk requests.  A hint only.
+          if (L2AHEAD > 0 && !p.dynamic && !resident && lane == 0 && cur + TW < U) {
+            const uint32_t u2 = backward ? (U - 1u - (cur + TW)) : (cur + TW);
+            const uint32_t rl2 = u2 / nch;
+            const uint32_t ch2 = u2 - rl2 * nch;
+            l2_prefetch_bulk(reinterpret_cast<const float*>(p.A) + (size_t)rl2 * N + (size_t)ch2 * kChunkCols,
+                             min((uint32_t)L2AHEAD * 1024u, min(kChunkVec, nv - ch2 * kChunkVec) * 16u));
+          }
           uint32_t npre = 0;
           if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
             tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);

@@ -64,11 +64,13 @@ inline const ScConfig kScConfigs[] = {
   { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
   // configuration 13 plus an L2 prefetch of 8 / 16 / 32 KB per warp across the round barrier (explicit only)
   { 21, 512, 1 }, { 22, 512, 1 }, { 23, 512, 1 },
+  // ... and / or of the warp's next unit while the current one streams (static scheduling: st_options.sweep bit 1)
+  { 24, 512, 1 }, { 25, 512, 1 }, { 26, 512, 1 },
 };
 inline bool
 is_sc_kernel_id(int id)
 {
-  return (id >= 10 && id < 20) || (id >= 21 && id <= 23);
+  return (id >= 10 && id < 20) || (id >= 21 && id <= 26);
 }
 
 inline size_t

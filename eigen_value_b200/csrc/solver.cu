@@ -329,6 +329,9 @@ launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t 
     case 21: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 8>, p, grid, threads, smem, stream);
     case 22: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16>, p, grid, threads, smem, stream);
     case 23: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 32>, p, grid, threads, smem, stream);
+    case 24: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 32>, p, grid, threads, smem, stream);
+    case 25: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 0, 32>, p, grid, threads, smem, stream);
+    case 26: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 16>, p, grid, threads, smem, stream);
     default: throw std::invalid_argument("unknown resident-e kernel id");
   }
 }

@@ -128,7 +128,7 @@ class SolveInfo:
     @property
     def kernel_name(self) -> str:
         k = self.kernel_id
-        key = 30 if k >= 30 else 10 if 21 <= k <= 23 else 20 if k >= 20 else 10 if k >= 10 else 2 if k >= 2 else 1
+        key = 30 if k >= 30 else 10 if 21 <= k <= 26 else 20 if k >= 20 else 10 if k >= 10 else 2 if k >= 2 else 1
         return self.KERNEL_NAMES[key]
 
     @classmethod

@@ -113,7 +113,9 @@ typedef struct st_options
                         kernel (N <= 32768), general chunked loop otherwise; 1 = general loop,
                         2-9 = TMA-ring variants, 10-19 = resident-e variants, 20 = on-chip,
                         21-23 = resident-e configuration 13 plus an L2 prefetch of 8 / 16 / 32 KB per
-                        warp across the round barrier (tuning variants, ST_STOP_ABSOLUTE)          */
+                        warp across the round barrier, 24-26 = ... and / or of the warp's next unit
+                        during the pass (static scheduling, sweep bit 1); tuning variants,
+                        ST_STOP_ABSOLUTE only                                                      */
   int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
@@ -134,7 +136,7 @@ typedef struct st_result
   uint64_t bytes_per_round; /* algorithmic bytes one round moves on this GPU        */
   int32_t status;
   uint32_t grid;          /* CTAs the round kernel ran with                          */
-  uint32_t kernel_id;     /* 1 general loop, 2-9 TMA ring, 10-19 and 21-23 resident-e, 20 on-chip,
+  uint32_t kernel_id;     /* 1 general loop, 2-9 TMA ring, 10-19 and 21-26 resident-e, 20 on-chip,
                              30 streamed (host-driven rounds) */
   uint32_t threads;       /* CTA size the round kernel ran with                      */
 } st_result;

@@ -13,9 +13,9 @@ from eigen_value_b200._lib import StError
 import os
 
 pytestmark = pytest.mark.gpu
-# the L2-prefetch variants (kernels 21-23) join the random draw on the emulated library only until their own file
+# the L2-prefetch variants (kernels 21-26) join the random draw on the emulated library only until their own file
 # (tests/test_zzzzz_gpu_l2_prefetch.py, which sorts last) has passed on hardware once
-L2_PREFETCH_IDS = [21, 23] if os.environ.get("ST_EMULATED_LIB") == "1" else []
+L2_PREFETCH_IDS = [21, 23, 24, 25] if os.environ.get("ST_EMULATED_LIB") == "1" else []
 
 
 @st.composite

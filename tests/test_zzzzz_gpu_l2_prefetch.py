@@ -1,4 +1,5 @@
-"""L2 prefetch across the round barrier (st_options.kernel 21 / 22 / 23), DESIGN.md section 8.
+"""L2 prefetch across the round barrier (st_options.kernel 21 / 22 / 23) and of the next unit during the pass
+(24 / 25 / 26, static scheduling), DESIGN.md section 8.
 
 Kernels 21-23 = resident-e configuration 13 plus one bulk L2 prefetch per warp (cp.async.bulk.prefetch.L2, SASS
 UBLKPF.L2) of the unit the warp takes second in the next round, issued right before the round barrier.  A hint
@@ -42,8 +43,8 @@ def test_l2_prefetch_variants_are_hints_only(solver, dim):
     cap = 4
     want = _oracle(mat, max_itr=cap)
     d = solver.upload(mat)
-    for kid in (21, 22, 23):
-        for sweep in (1, 0, 3):
+    for kid in (21, 22, 23, 24, 25, 26):
+        for sweep in (1, 0, 3, 2):          # alternating dynamic | forward dynamic | alternating static | forward static
             info, vec = solver.solve_device(d, dim, kernel=kid, max_iter=cap, sweep=sweep)
             assert info.kernel_id == kid
             _assert_same_bits((info.eigen_val, vec, info.iter_count), want, f"kernel {kid} sweep {sweep}")
@@ -56,7 +57,7 @@ def test_l2_prefetch_variant_on_the_headline_size(solver):
     dim = 8192
     d = solver.hilbert(dim)
     base, base_vec = solver.solve_device(d, dim)
-    for kid in (21, 22, 23):
-        info, vec = solver.solve_device(d, dim, kernel=kid)
+    for kid, sweep in ((21, 1), (22, 1), (23, 1), (24, 3), (25, 3), (26, 3)):
+        info, vec = solver.solve_device(d, dim, kernel=kid, sweep=sweep)
         assert info.kernel_id == kid and info.iter_count == base.iter_count == 17
         assert info.eigen_val == base.eigen_val and np.array_equal(vec, base_vec)

@@ -48,4 +48,6 @@ done
 # L2 prefetch across the round barrier (kernels 21-23) against the default configuration 13: one GPU and sizes where
 # barrier + tail are a visible share of the round
 KERNELS=13,21,22,23 timeout 600 python tools/sweep_kernels.py 4096 8192 16384 32768 > $O/first_call_sweep_l2_prefetch.txt 2>&1
+# ... and prefetch of the next unit during the pass (24-26) under static scheduling, against 13 static and 13 dynamic
+KERNELS=13,24,25,26 SWEEPS=1,3 timeout 600 python tools/sweep_kernels.py 8192 32768 >> $O/first_call_sweep_l2_prefetch.txt 2>&1
 tail -5 $O/first_call_tests.txt

@@ -12,7 +12,9 @@ NAMES = {0: "auto", 1: "general ldg", 2: "tma 512x3x1024", 3: "tma 256x6x1024", 
          6: "tma 256x4x1024", 7: "tma 1024x1x1024", 8: "tma 512x1x2048", 9: "tma 256x2x2048",
          10: "sc 512 pf2", 11: "sc 512 pf0", 12: "sc 512 pf3", 13: "sc 512 pf1", 14: "sc 1024 pf1",
          15: "sc 1024 pf0", 16: "sc 256 pf2 ld16", 17: "sc 256 pf4 ld16", 18: "sc 256 pf0 ld16",
-         19: "sc 256 pf1 ld16", 21: "sc 512 pf1 l2pf8", 22: "sc 512 pf1 l2pf16", 23: "sc 512 pf1 l2pf32"}
+         19: "sc 256 pf1 ld16", 21: "sc 512 pf1 l2pf8", 22: "sc 512 pf1 l2pf16", 23: "sc 512 pf1 l2pf32",
+         24: "sc l2pf16 ahead32", 25: "sc l2pf0 ahead32", 26: "sc l2pf16 ahead16"}
+SWEEPS = [int(x) for x in os.environ.get("SWEEPS", "1,0").split(",") if x]   # st_options.sweep values (3 = alternating + static)
 ONLY = [int(x) for x in os.environ.get("KERNELS", "").split(",") if x]
 
 
@@ -23,7 +25,7 @@ def main():
     for dim in dims:
         d = s.hilbert(dim)
         ref = None
-        for sweep in (1, 0):
+        for sweep in SWEEPS:
             for kid in (ONLY or sorted(NAMES)):
                 try:
                     best = None
