@@ -52,7 +52,7 @@ def test_l2_prefetch_variants_are_hints_only(solver, dim):
         solver.solve_device(d, dim, kernel=22, stop=STOP_RELATIVE)          # tuning variants: absolute stop only
 
 
-def test_l2_prefetch_variant_on_the_headline_size(solver):
+def test_l2_prefetch_variants_full_size_headline(solver):
     # Hilbert 8192 (README.md:76: 17 rounds): same bits as the default configuration
     dim = 8192
     d = solver.hilbert(dim)
