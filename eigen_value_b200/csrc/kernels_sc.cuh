@@ -202,14 +202,20 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       };
       // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
       // so round k hands out the values [k * (D + TW), k * (D + TW) + D)
-      const uint32_t base = k * (D + TW);
+      // (L2AHEAD variants keep TWO grabs in flight, so that the unit after the current one is known -- and can be
+      // asked into L2 -- while the current one streams: two failing grabs per warp and round)
+      constexpr uint32_t kGrabs = L2AHEAD > 0 ? 2u : 1u;
+      const uint32_t base = k * (D + kGrabs * TW);
       uint32_t cur = gw;
       bool have = cur < U;
       bool first_unit = true;
-      uint32_t grabbed = 0, pend_row = 0, pend_old = 0;
+      uint32_t grabbed = 0, grabbed2 = 0, pend_row = 0, pend_old = 0;
       bool pending = false;
-      if (p.dynamic && lane == 0)
+      if (p.dynamic && lane == 0) {
         grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
+        if (L2AHEAD > 0)
+          grabbed2 = atomicAdd(&p.bar->row_counter, 1u);
+      }
       for (;;) {
         if (have) {
           const uint32_t u = backward ? (U - 1u - cur) : cur;
@@ -217,11 +223,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          // L2AHEAD > 0 (tuning variants 24-26, static scheduling only: the next unit is known): while this
-          // unit streams, ask for the head of the warp's NEXT unit to be pulled into L2 -- the SM side then
-          // reads at L2 latency and the DRAM side sees large bulk requests.  A hint only.
-          if (L2AHEAD > 0 && !p.dynamic && !resident && lane == 0 && cur + TW < U) {
-            const uint32_t u2 = backward ? (U - 1u - (cur + TW)) : (cur + TW);
+          // L2AHEAD > 0 (tuning variants 24-26): while this unit streams, ask for the head of the warp's NEXT
+          // unit to be pulled into L2 -- the SM side then reads at L2 latency and the DRAM side sees large bulk
+          // requests.  Static scheduling knows the next unit (cur + TW); dynamic scheduling knows it because
+          // the grab that names it was issued a whole unit ago (two grabs in flight).  A hint only.
+          uint32_t nxt = cur + TW;
+          if (L2AHEAD > 0 && p.dynamic) {
+            const uint32_t d = grabbed - base; // meaningful in lane 0 only
+            nxt = d < D ? TW + d : U;
+          }
+          if (L2AHEAD > 0 && !resident && lane == 0 && nxt < U) {
+            const uint32_t u2 = backward ? (U - 1u - nxt) : nxt;
             const uint32_t rl2 = u2 / nch;
             const uint32_t ch2 = u2 - rl2 * nch;
             l2_prefetch_bulk(reinterpret_cast<const float*>(p.A) + (size_t)rl2 * N + (size_t)ch2 * kChunkCols,
@@ -266,8 +278,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           if (d >= D)
             break;
           cur = TW + d;
-          if (lane == 0)
-            grabbed = atomicAdd(&p.bar->row_counter, 1u);
+          if (lane == 0) {
+            if (L2AHEAD > 0) {
+              grabbed = grabbed2;
+              grabbed2 = atomicAdd(&p.bar->row_counter, 1u);
+            } else {
+              grabbed = atomicAdd(&p.bar->row_counter, 1u);
+            }
+          }
         } else {
           cur += TW;
           if (cur >= U)

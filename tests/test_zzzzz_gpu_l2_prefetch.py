@@ -44,7 +44,9 @@ def test_l2_prefetch_variants_are_hints_only(solver, dim):
     want = _oracle(mat, max_itr=cap)
     d = solver.upload(mat)
     for kid in (21, 22, 23, 24, 25, 26):
-        for sweep in (1, 0, 3, 2):          # alternating dynamic | forward dynamic | alternating static | forward static
+        # st_options.sweep: bit 0 alternate the direction, bit 1 force static, bit 2 force dynamic scheduling (the
+        # default is dynamic from N = 8192 up); kernels 24-26 keep two grabs in flight under dynamic scheduling
+        for sweep in (1, 0, 3, 2, 5, 4):
             info, vec = solver.solve_device(d, dim, kernel=kid, max_iter=cap, sweep=sweep)
             assert info.kernel_id == kid
             _assert_same_bits((info.eigen_val, vec, info.iter_count), want, f"kernel {kid} sweep {sweep}")
