@@ -227,8 +227,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           // unit to be pulled into L2 -- the SM side then reads at L2 latency and the DRAM side sees large bulk
           // requests.  Static scheduling knows the next unit (cur + TW); dynamic scheduling knows it because
           // the grab that names it was issued a whole unit ago (two grabs in flight).  A hint only.
-          uint32_t nxt = cur + TW;
-          if (L2AHEAD > 0 && p.dynamic) {
+          // (not for the round's first unit when its successor was already asked for across the barrier, and
+          // never under dynamic scheduling there: the grab that names it was issued a moment ago, and waiting
+          // for it would stall the whole warp at the start of every round)
+          uint32_t nxt = (first_unit && (L2PF > 0 || p.dynamic)) ? U : cur + TW;
+          if (L2AHEAD > 0 && p.dynamic && !first_unit) {
             const uint32_t d = grabbed - base; // meaningful in lane 0 only
             nxt = d < D ? TW + d : U;
           }
