@@ -24,7 +24,7 @@ for n in 8192 32768; do
 done
 cat gpurun_out/bench_group.json
 # L2 prefetch variant on the weakest scaling point (8 GPUs x Hilbert 32768: barrier 16.6 us + tail 7.5 us of a 93 us round)
-for k in 0 22 23; do
+for k in 0 22 23 24; do
   timeout 300 $TR --nproc-per-node 8 --master-port 2966$((k % 10)) bench.py --gpus 8 --workload hilbert-32768 --kernel $k --steps 10 --warmup 3 --no-e2e 2>/dev/null | grep '^{' >> gpurun_out/scale_hilbert32768_n8_l2_prefetch.json
 done
 cut -c1-400 gpurun_out/scale_hilbert32768_n8_l2_prefetch.json
