@@ -186,7 +186,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
         r.smem = sizeof(float) * ((size_t)p.chunk_cols + cap);
         kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64);
-      } else if (kid >= 10 && kid <= 13) {
+      } else if ((kid >= 10 && kid <= 13) || (kid >= 21 && kid <= 26)) {
         if (!vec4 || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
           throw std::string("resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
         int pf = -1;
@@ -211,6 +211,18 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.row_done = r.row_done.data();
         }
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
+        if (kid >= 21) { // L2-prefetch variants of configuration 13 (hints; solver.cu launch_sc)
+          if (o->stop || bf16 || acc64)
+            throw std::string("L2-prefetch variants: fp32, absolute stop test");
+          switch (kid) {
+            case 21: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 8>; break;
+            case 22: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16>; break;
+            case 23: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 32>; break;
+            case 24: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 32>; break;
+            case 25: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 0, 32>; break;
+            default: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 16>; break;
+          }
+        }
       } else if (kid == 6 || kid == 9) {
         if (!vec4 || form != kFormReadOnly || bf16 || o->stop)
           throw std::string("TMA variants: read-only form, fp32, absolute stop test");

@@ -99,6 +99,8 @@ main(int argc, char** argv)
     { "TMA ring 6, 512", 512, with(6, 256, 2) },
     { "2 GPUs, general 200", 200, with(1, 64, 2, 2) },
     { "3 GPUs, resident-e 13 dynamic 320", 320, with(13, 64, 2, 3, 0, 0, 1) },
+    { "resident-e 24 (L2 prefetch, two grabs in flight), dynamic units, 320", 320, with(24, 64, 3, 1, 0, 0, 1) },
+    { "3 GPUs, resident-e 22 (L2 prefetch across the barrier), 320", 320, with(22, 64, 2, 3, 0, 0, 1) },
     { "resident-e 13, fp64 accumulation, 320", 320, [&] { emu_opts o = with(13, 64, 3); o.acc64 = 1; return o; }() },
   };
   int failures = 0;
@@ -114,7 +116,7 @@ main(int argc, char** argv)
     std::vector<float> vec(c.dim);
     uint32_t it = 0, passes = 0, agree = 1;
     const int rc = emu_solve(data, c.dim, &c.o, &val, vec.data(), &it, &passes, &agree);
-    printf("%-52s rc=%d rounds=%u lambda=%.6f agree=%u%s%s\n", c.name, rc, it, val, agree, rc ? " error: " : "",
+    printf("%-68s rc=%d rounds=%u lambda=%.6f agree=%u%s%s\n", c.name, rc, it, val, agree, rc ? " error: " : "",
            rc ? emu_last_error() : "");
     fflush(stdout);
     failures += (rc != 0 || !agree);

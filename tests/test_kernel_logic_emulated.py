@@ -227,3 +227,15 @@ def test_fp64_accumulation_rows_of_several_units_and_sharded():
               expect(mat, sum_mode=oracle.SUM_CUDA_F64, max_iter=3))
     mat = U(1000)
     same_bits(emu.solve(mat, 1000, kernel=13, threads=64, ctas=2, world=3, acc64=True), expect(mat, sum_mode=oracle.SUM_CUDA_F64))
+
+
+def test_l2_prefetch_variants_on_the_kernel_harness():
+    # kernels 21-26 (hints only): virtual ranks, static and dynamic units, rows of two units, small CTAs
+    mat = (oracle.uniform(520, 31) + np.float32(0.25)).astype(np.float32)
+    for kid in (21, 22, 23, 24, 25, 26):
+        for dyn in (0, 1):
+            same_bits(emu.solve(mat, 520, kernel=kid, threads=64, ctas=3, dynamic=dyn), expect(mat))
+    same_bits(emu.solve(mat, 520, kernel=24, threads=64, ctas=2, world=3, dynamic=1), expect(mat))
+    big = (oracle.uniform(8200, 7) + np.float32(0.25)).astype(np.float32)
+    same_bits(emu.solve(big, 8200, kernel=24, threads=128, ctas=3, dynamic=1, max_iter=3), expect(big, max_iter=3))
+    same_bits(emu.solve(big, 8200, kernel=22, threads=128, ctas=3, world=2, max_iter=3), expect(big, max_iter=3))
