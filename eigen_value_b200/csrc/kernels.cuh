@@ -14,7 +14,6 @@
 // column-chunked scale vector.  The specialised loops build on it:
 //   kernels_cluster.cuh  N <= 512    matrix resident in the shared memory of one cluster
 //   kernels_sc.cuh       N <= 32768  eigenvector resident in shared memory (the default)
-//   kernels_tma.cuh      tuning variant streaming the matrix through per-warp TMA rings
 //
 // Opt-in variants are template parameters, so the default instantiations stay exactly the measured
 // code: STOP (the reference's absolute stop test | relative), T (fp32 | bf16 STORAGE of the matrix),
@@ -140,13 +139,21 @@ stamp_round_end(const RoundParams& p, uint32_t k)
   }
 }
 
-
-
-
-
-
-
-
+// Bounded wait for a bulk copy (cp.async.bulk ... mbarrier::complete_tx): a wrong byte count would
+// otherwise hang the GPU.
+__device__ __forceinline__ bool
+mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns)
+{
+  if (mbar_try_wait(bar, parity))
+    return true;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > timeout_ns)
+      return false;
+  }
+  return true;
+}
 
 // L2-coherent loads/stores for data other CTAs (or other GPUs) write during the kernel.
 __device__ __forceinline__ float

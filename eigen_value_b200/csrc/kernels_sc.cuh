@@ -28,7 +28,6 @@
 #pragma once
 
 #include "kernels.cuh"
-#include "kernels_tma.cuh"
 
 namespace st {
 
@@ -84,12 +83,11 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return (float)warp_sum(acc[0]);
 }
 
-template<int MAX_THREADS, int PF_BATCHES, int LD = kUnroll, int STOP = kStopAbsolute, typename T = float,
-         typename ACC = float, int L2PF = 0, int L2AHEAD = 0>
+template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
+  constexpr int LD = kUnroll; // independent 128-bit loads in flight per lane (16 measured no better, profiles/r1_sweep_resident_e_variants.txt)
   static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
-  static_assert((L2PF == 0 && L2AHEAD == 0) || sizeof(T) == 4, "the L2 prefetch variants are built for fp32 storage");
   // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -202,20 +200,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       };
       // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
       // so round k hands out the values [k * (D + TW), k * (D + TW) + D)
-      // (L2AHEAD variants keep TWO grabs in flight, so that the unit after the current one is known -- and can be
-      // asked into L2 -- while the current one streams: two failing grabs per warp and round)
-      constexpr uint32_t kGrabs = L2AHEAD > 0 ? 2u : 1u;
-      const uint32_t base = k * (D + kGrabs * TW);
+      const uint32_t base = k * (D + TW);
       uint32_t cur = gw;
       bool have = cur < U;
       bool first_unit = true;
-      uint32_t grabbed = 0, grabbed2 = 0, pend_row = 0, pend_old = 0;
+      uint32_t grabbed = 0, pend_row = 0, pend_old = 0;
       bool pending = false;
-      if (p.dynamic && lane == 0) {
+      if (p.dynamic && lane == 0)
         grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
-        if (L2AHEAD > 0)
-          grabbed2 = atomicAdd(&p.bar->row_counter, 1u);
-      }
       for (;;) {
         if (have) {
           const uint32_t u = backward ? (U - 1u - cur) : cur;
@@ -223,25 +215,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          // L2AHEAD > 0 (tuning variants 24-26): while this unit streams, ask for the head of the warp's NEXT
-          // unit to be pulled into L2 -- the SM side then reads at L2 latency and the DRAM side sees large bulk
-          // requests.  Static scheduling knows the next unit (cur + TW); dynamic scheduling knows it because
-          // the grab that names it was issued a whole unit ago (two grabs in flight).  A hint only.
-          // (not for the round's first unit when its successor was already asked for across the barrier, and
-          // never under dynamic scheduling there: the grab that names it was issued a moment ago, and waiting
-          // for it would stall the whole warp at the start of every round)
-          uint32_t nxt = (first_unit && (L2PF > 0 || p.dynamic)) ? U : cur + TW;
-          if (L2AHEAD > 0 && p.dynamic && !first_unit) {
-            const uint32_t d = grabbed - base; // meaningful in lane 0 only
-            nxt = d < D ? TW + d : U;
-          }
-          if (L2AHEAD > 0 && !resident && lane == 0 && nxt < U) {
-            const uint32_t u2 = backward ? (U - 1u - nxt) : nxt;
-            const uint32_t rl2 = u2 / nch;
-            const uint32_t ch2 = u2 - rl2 * nch;
-            l2_prefetch_bulk(reinterpret_cast<const float*>(p.A) + (size_t)rl2 * N + (size_t)ch2 * kChunkCols,
-                             min((uint32_t)L2AHEAD * 1024u, min(kChunkVec, nv - ch2 * kChunkVec) * 16u));
-          }
           uint32_t npre = 0;
           if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
             tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
@@ -281,14 +254,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           if (d >= D)
             break;
           cur = TW + d;
-          if (lane == 0) {
-            if (L2AHEAD > 0) {
-              grabbed = grabbed2;
-              grabbed2 = atomicAdd(&p.bar->row_counter, 1u);
-            } else {
-              grabbed = atomicAdd(&p.bar->row_counter, 1u);
-            }
-          }
+          if (lane == 0)
+            grabbed = atomicAdd(&p.bar->row_counter, 1u);
         } else {
           cur += TW;
           if (cur >= U)
@@ -313,20 +280,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         bulk_load(my_pf, p.A + (size_t)rl * N + (size_t)ch * kChunkCols, bytes, my_bar);
       }
       pf_issued++;
-    }
-    // L2PF > 0 (tuning variants 21-23): keep HBM busy across the barrier and the vector tail as well.  The
-    // units every warp reads FIRST in the next round are the ones this round ended on (alternating sweep:
-    // L2 hits); the ones read SECOND come from HBM.  Lane 0 asks for the first L2PF KB of the unit this warp
-    // takes second (cur = TW + gw in the next round's order) to be pulled into L2 while the grid synchronises
-    // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  A hint only: no effect on any result.
-    if (L2PF > 0 && !resident && lane == 0 && k + 1u < p.max_iter && TW + gw < U) {
-      const uint32_t cur_n = TW + gw;
-      const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - cur_n) : cur_n;
-      const uint32_t rl = u / nch;
-      const uint32_t ch = u - rl * nch;
-      const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
-      l2_prefetch_bulk(reinterpret_cast<const float*>(p.A) + (size_t)rl * N + (size_t)ch * kChunkCols,
-                       min((uint32_t)L2PF * 1024u, seg_nv * 16u));
     }
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);

@@ -30,47 +30,34 @@ balanced_warps(uint32_t nrows, int lo, int hi)
   return best;
 }
 
-struct TmaConfig
-{
-  int id, threads, stages, tile_f;
-};
-// id 2 is the default; the others are tuning variants reachable through st_options.kernel
-inline const TmaConfig kTmaConfigs[] = {
-  { 2, 512, 3, 1024 }, { 3, 256, 6, 1024 }, { 4, 256, 3, 2048 }, { 5, 512, 2, 1024 },
-  { 6, 256, 4, 1024 }, { 7, 1024, 1, 1024 }, { 8, 512, 1, 2048 }, { 9, 256, 2, 2048 },
-};
 constexpr size_t kSmemLimit = 227 * 1024 - 1024; // opt-in maximum minus the kernel's static shared
-
-inline size_t
-tma_smem_bytes(const TmaConfig& c, uint32_t chunk_cols, uint32_t rows_cap, uint32_t* mbar_offset)
-{
-  size_t off = (size_t)(c.threads / 32) * c.stages * c.tile_f * sizeof(float);
-  off += (size_t)chunk_cols * sizeof(float);
-  off += (size_t)rows_cap * sizeof(float);
-  off = (off + 15) & ~(size_t)15;
-  *mbar_offset = (uint32_t)off;
-  return off + (size_t)(c.threads / 32) * c.stages * sizeof(uint64_t);
-}
 
 struct ScConfig
 {
   int id, max_threads, pf_batches;
 };
-// the automatic choice takes the first entry that fits (one 4 KB batch prefetched per warp --
-// measured best or tied at N = 1024..8192, profiles/r1_sweep_kernels_sc*.txt); the others are
-// tuning variants reachable through st_options.kernel
+// Resident-e configurations (st_options.kernel): {512 threads, PF_BATCHES x 4 KB prefetch slot per warp}.  The
+// automatic choice is 13 (one batch: measured best or tied at N = 1024..32768); 10 / 12 size the slot to a whole
+// row so that rows of N = 1025..3072 stay on chip for the whole solve; 11 (no slots) is the bf16-storage build.
+// Everything else round 1 tried lost on hardware and was removed in round 2: 1024- and 256-thread CTAs with 8 / 16
+// loads in flight (ids 14-19, profiles/r1_sweep_resident_e_variants.txt), per-warp TMA rings for the whole stream
+// (ids 2-9, profiles/r1_sweep_tma_ring_vs_ldg.txt) and L2 prefetch hints across the barrier or one unit ahead
+// (ids 21-26, profiles/r2_c1_sweep_l2_prefetch.txt: 1.5 % to 40 % slower at N = 8192 and 32768).
 inline const ScConfig kScConfigs[] = {
-  { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 }, { 14, 1024, 1 }, { 15, 1024, 0 },
-  { 16, 256, 2 }, { 17, 256, 4 }, { 18, 256, 0 }, { 19, 256, 1 },
-  // configuration 13 plus an L2 prefetch of 8 / 16 / 32 KB per warp across the round barrier (explicit only)
-  { 21, 512, 1 }, { 22, 512, 1 }, { 23, 512, 1 },
-  // ... and / or of the warp's next unit while the current one streams (static scheduling: st_options.sweep bit 1)
-  { 24, 512, 1 }, { 25, 512, 1 }, { 26, 512, 1 },
+  { 13, 512, 1 }, { 10, 512, 2 }, { 11, 512, 0 }, { 12, 512, 3 },
 };
 inline bool
 is_sc_kernel_id(int id)
 {
-  return (id >= 10 && id < 20) || (id >= 21 && id <= 26);
+  return id >= 10 && id <= 13;
+}
+constexpr int kGeneralKernelId = 1;
+constexpr int kClusterKernelIdPlan = 20;
+// st_options.kernel values the library accepts: 0 automatic, 1 general loop, 10-13 resident-e, 20 on-chip cluster
+inline bool
+is_known_kernel_id(int id)
+{
+  return id == 0 || id == kGeneralKernelId || is_sc_kernel_id(id) || id == kClusterKernelIdPlan;
 }
 
 inline size_t

@@ -16,7 +16,6 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
-#include "kernels_tma.cuh"
 #include "kernels_sc.cuh"
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
@@ -80,7 +79,7 @@ Context::preload_kernels()
   cudaFuncAttributes attr{};
   const void* kernels[] = {
     (const void*)round_loop_cluster_kernel<512, kStopAbsolute>,
-    (const void*)round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute>,
+    (const void*)round_loop_sc_kernel<512, 1, kStopAbsolute>,
     (const void*)round_loop_kernel<4, kFormReadOnly, 512, kStopAbsolute>,
     (const void*)round_loop_kernel<1, kFormReadOnly, 512, kStopAbsolute>,
   };
@@ -258,40 +257,12 @@ launch_by_stop(int stop, int threads, const RoundParams& p, int grid, size_t sme
   return launch_by_threads<VEC, FORM, kStopAbsolute>(threads, p, grid, smem, stream);
 }
 
-// ---- TMA-streamed variant ---------------------------------------------------------------------
-template<int THREADS, int STAGES, int TILE_F>
-static void
-launch_tma_one(const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
-{
-  auto kernel = round_loop_tma_kernel<THREADS, STAGES, TILE_F>;
-  ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = { (void*)&p };
-  ST_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(THREADS), args, smem,
-                                      stream));
-}
-
-static void
-launch_tma(int id, const RoundParams& p, int grid, size_t smem, cudaStream_t stream)
-{
-  switch (id) {
-    case 2: return launch_tma_one<512, 3, 1024>(p, grid, smem, stream);
-    case 3: return launch_tma_one<256, 6, 1024>(p, grid, smem, stream);
-    case 4: return launch_tma_one<256, 3, 2048>(p, grid, smem, stream);
-    case 5: return launch_tma_one<512, 2, 1024>(p, grid, smem, stream);
-    case 6: return launch_tma_one<256, 4, 1024>(p, grid, smem, stream);
-    case 7: return launch_tma_one<1024, 1, 1024>(p, grid, smem, stream);
-    case 8: return launch_tma_one<512, 1, 2048>(p, grid, smem, stream);
-    case 9: return launch_tma_one<256, 2, 2048>(p, grid, smem, stream);
-    default: throw std::invalid_argument("unknown TMA kernel id");
-  }
-}
-
 // ---- resident-e variant (N <= 32768): e in smem, fused tail, cross-barrier prefetch ----------
-template<int MAX_THREADS, int PF, int LD = kUnroll, int STOP = kStopAbsolute>
+template<int MAX_THREADS, int PF, int STOP = kStopAbsolute>
 static void
 launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_sc_kernel<MAX_THREADS, PF, LD, STOP>;
+  auto kernel = round_loop_sc_kernel<MAX_THREADS, PF, STOP>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
@@ -299,20 +270,16 @@ launch_sc_one(const RoundParams& p, int grid, int threads, size_t smem, cudaStre
                                       stream));
 }
 
-template<typename K>
-static void
-launch_cooperative(K kernel, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream);
-
 static void
 launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
   if (stop == kStopRelative) {
-    // the configurations the automatic choice can pick (1, 2 or 3 prefetch batches, 512 threads)
     switch (id) {
-      case 10: return launch_sc_one<512, 2, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
-      case 12: return launch_sc_one<512, 3, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
-      case 13: return launch_sc_one<512, 1, kUnroll, kStopRelative>(p, grid, threads, smem, stream);
-      default: throw std::invalid_argument("this resident-e tuning variant supports ST_STOP_ABSOLUTE only");
+      case 10: return launch_sc_one<512, 2, kStopRelative>(p, grid, threads, smem, stream);
+      case 11: return launch_sc_one<512, 0, kStopRelative>(p, grid, threads, smem, stream);
+      case 12: return launch_sc_one<512, 3, kStopRelative>(p, grid, threads, smem, stream);
+      case 13: return launch_sc_one<512, 1, kStopRelative>(p, grid, threads, smem, stream);
+      default: throw std::invalid_argument("unknown resident-e kernel id");
     }
   }
   switch (id) {
@@ -320,18 +287,6 @@ launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t 
     case 11: return launch_sc_one<512, 0>(p, grid, threads, smem, stream);
     case 12: return launch_sc_one<512, 3>(p, grid, threads, smem, stream);
     case 13: return launch_sc_one<512, 1>(p, grid, threads, smem, stream);
-    case 14: return launch_sc_one<1024, 1>(p, grid, threads, smem, stream);
-    case 15: return launch_sc_one<1024, 0>(p, grid, threads, smem, stream);
-    case 16: return launch_sc_one<256, 2, 16>(p, grid, threads, smem, stream);
-    case 17: return launch_sc_one<256, 4, 16>(p, grid, threads, smem, stream);
-    case 18: return launch_sc_one<256, 0, 16>(p, grid, threads, smem, stream);
-    case 19: return launch_sc_one<256, 1, 16>(p, grid, threads, smem, stream);
-    case 21: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 8>, p, grid, threads, smem, stream);
-    case 22: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16>, p, grid, threads, smem, stream);
-    case 23: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 32>, p, grid, threads, smem, stream);
-    case 24: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 32>, p, grid, threads, smem, stream);
-    case 25: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 0, 32>, p, grid, threads, smem, stream);
-    case 26: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 16>, p, grid, threads, smem, stream);
     default: throw std::invalid_argument("unknown resident-e kernel id");
   }
 }
@@ -344,7 +299,7 @@ template<int STOP>
 static void
 launch_sc_bf16(const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
-  auto kernel = round_loop_sc_kernel<512, 0, kUnroll, STOP, bf16_t>;
+  auto kernel = round_loop_sc_kernel<512, 0, STOP, bf16_t>;
   if (smem > 48 * 1024)
     ST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = { (void*)&p };
@@ -390,9 +345,9 @@ static void
 launch_sc_acc64(int id, const RoundParams& p, int grid, int threads, size_t smem, cudaStream_t stream)
 {
   switch (id) {
-    case 10: return launch_cooperative(round_loop_sc_kernel<512, 2, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
-    case 12: return launch_cooperative(round_loop_sc_kernel<512, 3, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
-    case 13: return launch_cooperative(round_loop_sc_kernel<512, 1, kUnroll, STOP, float, double>, p, grid, threads, smem, stream);
+    case 10: return launch_cooperative(round_loop_sc_kernel<512, 2, STOP, float, double>, p, grid, threads, smem, stream);
+    case 12: return launch_cooperative(round_loop_sc_kernel<512, 3, STOP, float, double>, p, grid, threads, smem, stream);
+    case 13: return launch_cooperative(round_loop_sc_kernel<512, 1, STOP, float, double>, p, grid, threads, smem, stream);
     default: throw std::invalid_argument("fp64 accumulation is built for resident-e configurations 13, 10 and 12");
   }
 }
@@ -460,6 +415,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const int stop = opt.stop == ST_STOP_RELATIVE ? kStopRelative : kStopAbsolute;
   if (opt.accumulate != ST_ACC_F32 && opt.accumulate != ST_ACC_F64)
     throw std::invalid_argument("solve: unknown st_options.accumulate");
+  if (!is_known_kernel_id(opt.kernel))
+    throw std::invalid_argument("solve: unknown st_options.kernel (0 automatic, 1 general loop, 10-13 resident-e, 20 on-chip cluster)");
   const bool acc64 = opt.accumulate == ST_ACC_F64;
   if (acc64) {
     if (bf16 || form != kFormReadOnly)
@@ -530,8 +487,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   // ---- launch plan ------------------------------------------------------------------------
   // one persistent CTA per SM (fewer when there are fewer rows than warps); CTA size = the warp
   // count that divides the CTA's rows best unless st_options.threads pins it.
-  // kernel: 0 = automatic (resident-e kernel when N <= 32768, else the general chunked loop),
-  // 1 = general loop, 2-9 = TMA ring configurations, 10-19 = resident-e configurations.
+  // kernel: 0 = automatic (on-chip cluster kernel for N <= 512, resident-e kernel when N <= 32768, else the
+  // general chunked loop), 1 = general loop, 10-13 = resident-e configurations, 20 = on-chip cluster kernel.
   const bool vec4 = (dim % 4u == 0u) && aligned16(d_rows) && (!p.W || aligned16(p.W));
   const int pinned = opt.threads > 0 ? std::min(1024, (opt.threads + 31) / 32 * 32) : 0;
   auto shape = [&](int max_threads, bool balance, int* out_grid, int* out_threads, uint32_t* out_cap) {
@@ -550,7 +507,6 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   int threads = 512, grid = sm_count_;
   uint32_t rows_cap = 0;
   size_t smem = 0;
-  const TmaConfig* tma = nullptr;
   const ScConfig* sc = nullptr;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
@@ -578,12 +534,12 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
-      if (opt.kernel == 0 && (pinned > c.max_threads || c.id > kClusterKernelId))
-        continue; // the L2-prefetch variants (21-23) are never chosen automatically
+      if (opt.kernel == 0 && pinned > c.max_threads)
+        continue;
       if (bf16 && c.id != kScBf16Id)
         continue; // bf16 storage is built for configuration 11 only
-      if (opt.kernel == 0 && !bf16 && (stop == kStopRelative || acc64) && c.id != 13 && c.id != 10 && c.id != 12)
-        continue; // only the automatic configurations are built with the relative stop test / fp64 accumulation
+      if (opt.kernel == 0 && !bf16 && acc64 && c.id == kScBf16Id)
+        continue; // fp64 accumulation is built for the configurations with prefetch slots
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
@@ -612,34 +568,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     if (!sc && opt.kernel >= 10)
       throw std::invalid_argument("solve: requested resident-e kernel configuration does not fit");
   }
-  if (!sc && opt.kernel >= 2 && opt.kernel < 10) {
-    if (!readonly4)
-      throw std::invalid_argument("solve: TMA kernel needs the read-only form and dim % 4 == 0");
-    if (stop != kStopAbsolute)
-      throw std::invalid_argument("solve: the TMA tuning variants support ST_STOP_ABSOLUTE only");
-    for (const TmaConfig& c : kTmaConfigs) {
-      if (c.id != opt.kernel)
-        continue;
-      int g = opt.ctas > 0 ? opt.ctas : sm_count_;
-      const int w = c.threads / 32;
-      const int use = (int)std::max<uint32_t>(1u, (rows + (uint32_t)w - 1u) / (uint32_t)w);
-      g = std::max(1, std::min(g, std::min(use, sm_count_)));
-      const uint32_t cap = (rows + (uint32_t)g - 1u) / (uint32_t)g + 1u;
-      uint32_t moff = 0;
-      const size_t need = tma_smem_bytes(c, p.chunk_cols, cap, &moff);
-      if (need <= kSmemLimit) {
-        tma = &c;
-        grid = g;
-        threads = c.threads;
-        rows_cap = cap;
-        smem = need;
-        p.mbar_offset = moff;
-      }
-    }
-    if (!tma)
-      throw std::invalid_argument("solve: requested TMA kernel configuration does not fit");
-  }
-  if (!sc && !tma && !cluster_ctas) {
+  if (!sc && !cluster_ctas) {
     shape(pinned > 512 ? 1024 : 512, true, &grid, &threads, &rows_cap);
     smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
   }
@@ -653,7 +582,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     else
       launch_sc_acc64<kStopAbsolute>(sc->id, p, grid, threads, smem, stream_);
   } else if (acc64) {
-    if (tma || cluster_ctas)
+    if (cluster_ctas)
       throw std::invalid_argument("solve: fp64 accumulation is not built for this kernel");
     if (vec4 && stop == kStopRelative)
       launch_general_acc64<4, kStopRelative>(threads, p, grid, smem, stream_);
@@ -682,8 +611,6 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
   } else if (sc) {
     launch_sc(sc->id, stop, p, grid, threads, smem, stream_);
-  } else if (tma) {
-    launch_tma(tma->id, p, grid, smem, stream_);
   } else if (vec4) {
     if (form == kFormInPlace)
       launch_by_stop<4, kFormInPlace>(stop, threads, p, grid, smem, stream_);
@@ -731,7 +658,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->launches = 1;
     res->loop_ms = loop_ms;
     res->grid = (uint32_t)grid;
-    res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : tma ? (uint32_t)tma->id : 1u;
+    res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : 1u;
     res->threads = (uint32_t)threads;
     const uint64_t per_pass = (uint64_t)rows * dim * (bf16 ? 2u : sizeof(float));
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;

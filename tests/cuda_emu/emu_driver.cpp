@@ -9,7 +9,6 @@
 #include "cuda_emu.h"
 
 #include "kernels.cuh"
-#include "kernels_tma.cuh"
 #include "kernels_sc.cuh"
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
@@ -29,7 +28,7 @@ struct emu_opts
   int32_t dynamic; // -1: automatic (dim >= 8192), 0 static, 1 dynamic work units
   int32_t threads; // CTA size
   int32_t ctas;    // grid size per emulated GPU
-  int32_t kernel;  // 1 general, 6/9 TMA ring (256 threads), 10-13 resident-e, 20 cluster
+  int32_t kernel;  // 1 general, 10-13 resident-e, 20 cluster
   int32_t stop;    // 0 absolute, 1 relative
   int32_t bf16;    // matrix is bf16 storage
   int32_t world;   // emulated GPUs (row-block sharded)
@@ -83,18 +82,18 @@ void (*sc_kernel(int pf, bool bf16, bool acc64))(const RoundParams)
 {
   if (acc64) {
     switch (pf) {
-      case 1: return round_loop_sc_kernel<512, 1, kUnroll, STOP, float, double>;
-      case 2: return round_loop_sc_kernel<512, 2, kUnroll, STOP, float, double>;
-      default: return round_loop_sc_kernel<512, 3, kUnroll, STOP, float, double>;
+      case 1: return round_loop_sc_kernel<512, 1, STOP, float, double>;
+      case 2: return round_loop_sc_kernel<512, 2, STOP, float, double>;
+      default: return round_loop_sc_kernel<512, 3, STOP, float, double>;
     }
   }
   if (bf16)
-    return round_loop_sc_kernel<512, 0, kUnroll, STOP, bf16_t>;
+    return round_loop_sc_kernel<512, 0, STOP, bf16_t>;
   switch (pf) {
-    case 0: return round_loop_sc_kernel<512, 0, kUnroll, STOP, float>;
-    case 1: return round_loop_sc_kernel<512, 1, kUnroll, STOP, float>;
-    case 2: return round_loop_sc_kernel<512, 2, kUnroll, STOP, float>;
-    default: return round_loop_sc_kernel<512, 3, kUnroll, STOP, float>;
+    case 0: return round_loop_sc_kernel<512, 0, STOP, float>;
+    case 1: return round_loop_sc_kernel<512, 1, STOP, float>;
+    case 2: return round_loop_sc_kernel<512, 2, STOP, float>;
+    default: return round_loop_sc_kernel<512, 3, STOP, float>;
   }
 }
 
@@ -186,7 +185,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
         r.smem = sizeof(float) * ((size_t)p.chunk_cols + cap);
         kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64);
-      } else if ((kid >= 10 && kid <= 13) || (kid >= 21 && kid <= 26)) {
+      } else if (kid >= 10 && kid <= 13) {
         if (!vec4 || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
           throw std::string("resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
         int pf = -1;
@@ -211,35 +210,6 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.row_done = r.row_done.data();
         }
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
-        if (kid >= 21) { // L2-prefetch variants of configuration 13 (hints; solver.cu launch_sc)
-          if (o->stop || bf16 || acc64)
-            throw std::string("L2-prefetch variants: fp32, absolute stop test");
-          switch (kid) {
-            case 21: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 8>; break;
-            case 22: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16>; break;
-            case 23: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 32>; break;
-            case 24: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 32>; break;
-            case 25: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 0, 32>; break;
-            default: kernel = round_loop_sc_kernel<512, 1, kUnroll, kStopAbsolute, float, float, 16, 16>; break;
-          }
-        }
-      } else if (kid == 6 || kid == 9) {
-        if (!vec4 || form != kFormReadOnly || bf16 || o->stop)
-          throw std::string("TMA variants: read-only form, fp32, absolute stop test");
-        const TmaConfig* cfg = nullptr;
-        for (const TmaConfig& c : kTmaConfigs)
-          if (c.id == kid)
-            cfg = &c;
-        r.threads = (unsigned)cfg->threads;
-        const unsigned w = r.threads / 32;
-        r.grid = std::max(1u, std::min(want, (rows + w - 1) / w));
-        const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
-        uint32_t moff = 0;
-        r.smem = tma_smem_bytes(*cfg, p.chunk_cols, cap, &moff);
-        if (r.smem > kSmemLimit)
-          throw std::string("TMA configuration does not fit shared memory");
-        p.mbar_offset = moff;
-        kernel = kid == 6 ? round_loop_tma_kernel<256, 4, 1024> : round_loop_tma_kernel<256, 2, 2048>;
       } else if (kid == 20) {
         if (!vec4 || form != kFormReadOnly || bf16 || world != 1 || dim > (uint32_t)kClusterCols)
           throw std::string("cluster kernel: one GPU, read-only form, fp32, dim % 4 == 0, dim <= 512");

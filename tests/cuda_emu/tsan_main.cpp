@@ -96,11 +96,8 @@ main(int argc, char** argv)
     { "resident-e 11 bf16, relative stop, 320", 320, with(11, 64, 3, 1, 0, 1, 1, 1) },
     { "resident-e 13, two units per row, 8200 x 2 rounds", 8200, with(13, 64, 4, 1, 0, 0, 1, 0, 2u) },
     { "cluster kernel 128 (DSMEM exchange)", 128, with(20, 512, 8) },
-    { "TMA ring 6, 512", 512, with(6, 256, 2) },
     { "2 GPUs, general 200", 200, with(1, 64, 2, 2) },
     { "3 GPUs, resident-e 13 dynamic 320", 320, with(13, 64, 2, 3, 0, 0, 1) },
-    { "resident-e 24 (L2 prefetch, two grabs in flight), dynamic units, 320", 320, with(24, 64, 3, 1, 0, 0, 1) },
-    { "3 GPUs, resident-e 22 (L2 prefetch across the barrier), 320", 320, with(22, 64, 2, 3, 0, 0, 1) },
     { "resident-e 13, fp64 accumulation, 320", 320, [&] { emu_opts o = with(13, 64, 3); o.acc64 = 1; return o; }() },
   };
   int failures = 0;

@@ -95,7 +95,7 @@ def test_resident_rows_stay_in_the_prefetch_slot():
         same_bits(emu.solve(mat, dim, kernel=kernel, threads=512, ctas=ctas), expect(mat))
 
 
-@pytest.mark.parametrize("kernel,dynamic", [(13, 1), (13, 0), (11, 1), (1, -1), (9, -1)])
+@pytest.mark.parametrize("kernel,dynamic", [(13, 1), (13, 0), (11, 1), (1, -1)])
 def test_rows_of_several_work_units(kernel, dynamic):
     # N = 8200: every row is two units (8192 + 8 columns); chunk sums combined by whoever completes the row
     mat = U(8200)
@@ -103,18 +103,11 @@ def test_rows_of_several_work_units(kernel, dynamic):
               expect(mat, max_iter=4))
 
 
-# ---- on-chip cluster kernel and the TMA ring ---------------------------------------------------------
+# ---- on-chip cluster kernel ---------------------------------------------------------
 @pytest.mark.parametrize("dim", [4, 8, 100, 128, 384, 512])
 def test_cluster_kernel_distributed_shared_memory(dim):
     mat = oracle.hilbert(dim) if dim >= 128 else U(dim)
     same_bits(emu.solve(mat, dim, kernel=20), expect(mat))
-
-
-@pytest.mark.parametrize("kernel", [6, 9])
-def test_tma_ring_variants(kernel):
-    for dim, ctas in ((1000, 2), (1024, 3)):
-        mat = U(dim)
-        same_bits(emu.solve(mat, dim, kernel=kernel, ctas=ctas), expect(mat))
 
 
 # ---- stop tests ------------------------------------------------------------------------------------------
@@ -227,15 +220,3 @@ def test_fp64_accumulation_rows_of_several_units_and_sharded():
               expect(mat, sum_mode=oracle.SUM_CUDA_F64, max_iter=3))
     mat = U(1000)
     same_bits(emu.solve(mat, 1000, kernel=13, threads=64, ctas=2, world=3, acc64=True), expect(mat, sum_mode=oracle.SUM_CUDA_F64))
-
-
-def test_l2_prefetch_variants_on_the_kernel_harness():
-    # kernels 21-26 (hints only): virtual ranks, static and dynamic units, rows of two units, small CTAs
-    mat = (oracle.uniform(520, 31) + np.float32(0.25)).astype(np.float32)
-    for kid in (21, 22, 23, 24, 25, 26):
-        for dyn in (0, 1):
-            same_bits(emu.solve(mat, 520, kernel=kid, threads=64, ctas=3, dynamic=dyn), expect(mat))
-    same_bits(emu.solve(mat, 520, kernel=24, threads=64, ctas=2, world=3, dynamic=1), expect(mat))
-    big = (oracle.uniform(8200, 7) + np.float32(0.25)).astype(np.float32)
-    same_bits(emu.solve(big, 8200, kernel=24, threads=128, ctas=3, dynamic=1, max_iter=3), expect(big, max_iter=3))
-    same_bits(emu.solve(big, 8200, kernel=22, threads=128, ctas=3, world=2, max_iter=3), expect(big, max_iter=3))

@@ -16,7 +16,7 @@ import emu  # noqa: E402
 
 @st.composite
 def cases(draw):
-    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 20, 9]))
+    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 20]))
     dim = draw(st.integers(1, 1100))
     if kernel != 1:
         dim = max(4, dim - dim % 4)                       # vector kernels: dim % 4 == 0
@@ -26,7 +26,7 @@ def cases(draw):
     bf16 = kernel in (1, 11) and dim % 8 == 0 and draw(st.booleans())
     acc64 = (not bf16) and kernel in (1, 13, 10, 12) and draw(st.booleans())
     form = draw(st.integers(0, 1)) if (kernel == 1 and not bf16 and not acc64) else 0
-    stop = 0 if kernel == 9 else draw(st.integers(0, 1))
+    stop = draw(st.integers(0, 1))
     return dict(kernel=kernel, dim=dim, world=world, bf16=bf16, acc64=acc64, form=form, stop=stop,
                 threads=draw(st.sampled_from([32, 64, 96, 128, 256, 512])), ctas=draw(st.integers(1, 9)),
                 dynamic=draw(st.integers(0, 1)), sweep=draw(st.integers(0, 1)),

@@ -44,12 +44,11 @@ def test_positive_control_missing_syncthreads_is_reported(tsan_exe):
 
 def test_round_kernels_are_race_free(tsan_exe):
     """general loop (both forms, scalar, relative stop), resident-e (prefetch, static / dynamic units, resident
-    rows, bf16, two units per row, fp64 accumulation, the L2-prefetch variants with two grabs in flight), cluster kernel,
-    TMA ring, 2 and 3 emulated GPUs (tsan_main.cpp)."""
+    rows, bf16, two units per row, fp64 accumulation), cluster kernel, 2 and 3 emulated GPUs (tsan_main.cpp)."""
     proc = run(tsan_exe)
     assert "ThreadSanitizer" not in proc.stderr, proc.stderr[:4000]
     assert proc.returncode == 0, proc.stdout
-    assert proc.stdout.count("rc=0") == 15 and "agree=0" not in proc.stdout
+    assert proc.stdout.count("rc=0") == 12 and "agree=0" not in proc.stdout
 
 
 MUTANTS = [

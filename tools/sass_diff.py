@@ -43,8 +43,12 @@ def digest(funcs):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("before")
+    ap.add_argument("before", nargs="?")
     ap.add_argument("after", nargs="?")
+    ap.add_argument("--refresh", action="store_true",
+                    help="disassemble the CURRENT eigen_value_b200/libsimilarity_transform.so and write the digest of its round-loop "
+                         "kernels to profiles/r2_measured_kernels_sass_digest.json: run this in the tree a GPU measurement is "
+                         "taken from, and commit the file together with the numbers")
     ap.add_argument("--write-digest", default=None,
                     help="write {kernel: sha256 of its instruction stream} of `before` to this JSON file and exit "
                          "(refreshes profiles/r1_measured_kernels_sass_digest.json after a re-measurement)")
@@ -52,6 +56,18 @@ def main():
                     help="mangled template argument(s) appended to kernels taking RoundParams, e.g. Li0E; "
                          "several alternatives separated by commas (Li0E,Li0Ef)")
     args = ap.parse_args()
+    if args.refresh:
+        import json, os, shutil, subprocess, tempfile
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+        with tempfile.NamedTemporaryFile("w", suffix=".sass") as f:
+            subprocess.run([cuobjdump, "-sass", os.path.join(root, "eigen_value_b200", "libsimilarity_transform.so")], stdout=f, check=True)
+            f.flush()
+            d = {k: v for k, v in digest(split(f.name)).items() if "round_loop" in k}
+        with open(os.path.join(root, "profiles", "r2_measured_kernels_sass_digest.json"), "w") as f:
+            json.dump({"kernels": d}, f, indent=1, sort_keys=True)
+        print(f"{len(d)} round-loop kernels")
+        return 0
     if args.write_digest:
         import json
         with open(args.write_digest, "w") as f:

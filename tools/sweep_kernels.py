@@ -1,4 +1,4 @@
-"""Kernel-variant sweep: register-staged LDG kernel (id 1) vs TMA-ring configurations (ids >= 2).
+"""Kernel-variant sweep over the st_options.kernel ids that exist (round 2 removed the TMA-ring, 256/1024-thread and L2-prefetch variants).
 Usage: python tools/sweep_kernels.py [N ...]"""
 import os
 import sys
@@ -8,12 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eigen_value_b200 import Solver  # noqa: E402
 
 PEAK = 6554.9
-NAMES = {0: "auto", 1: "general ldg", 2: "tma 512x3x1024", 3: "tma 256x6x1024", 4: "tma 256x3x2048", 5: "tma 512x2x1024",
-         6: "tma 256x4x1024", 7: "tma 1024x1x1024", 8: "tma 512x1x2048", 9: "tma 256x2x2048",
-         10: "sc 512 pf2", 11: "sc 512 pf0", 12: "sc 512 pf3", 13: "sc 512 pf1", 14: "sc 1024 pf1",
-         15: "sc 1024 pf0", 16: "sc 256 pf2 ld16", 17: "sc 256 pf4 ld16", 18: "sc 256 pf0 ld16",
-         19: "sc 256 pf1 ld16", 21: "sc 512 pf1 l2pf8", 22: "sc 512 pf1 l2pf16", 23: "sc 512 pf1 l2pf32",
-         24: "sc l2pf16 ahead32", 25: "sc l2pf0 ahead32", 26: "sc l2pf16 ahead16"}
+NAMES = {0: "auto", 1: "general ldg", 10: "sc 512 pf2", 11: "sc 512 pf0", 12: "sc 512 pf3", 13: "sc 512 pf1", 20: "cluster"}
 SWEEPS = [int(x) for x in os.environ.get("SWEEPS", "1,0").split(",") if x]   # st_options.sweep values (3 = alternating + static)
 ONLY = [int(x) for x in os.environ.get("KERNELS", "").split(",") if x]
 
