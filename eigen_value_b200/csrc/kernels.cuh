@@ -75,12 +75,14 @@ struct alignas(128) BarrierState
 {
   unsigned int count; // monotonically increasing arrival counter
   unsigned int pad0[31];
-  unsigned int gen; // number of completed barriers
+  unsigned int error; // set by any CTA whose wait timed out (1) or whose bulk-copy wait did (2)
   unsigned int pad1[31];
-  unsigned int error; // set by any CTA whose wait timed out
+  unsigned int row_counter; // resident-e / wide kernels: dynamic work-unit scheduling (monotonic)
   unsigned int pad2[31];
-  unsigned int row_counter; // resident-e kernel: dynamic row scheduling (monotonic)
-  unsigned int pad3[31];
+  // largest row sum this GPU published in a round, by round parity: ((k + 1) << 32) | bits of max(0, max_r s[r]).
+  // The round tag makes the word monotonic, so it is never reset: round k + 2 simply wins over round k.
+  unsigned long long smax[2];
+  unsigned int pad3[28];
 };
 
 struct RoundParams
@@ -106,9 +108,11 @@ struct RoundParams
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;
   float* peer_S[2][kMaxWorld];            // S buffers of every rank (own entry == S[b])
-  unsigned long long* peer_flags[kMaxWorld]; // flag array of every rank; slot [src rank]
+  unsigned long long* peer_flags[kMaxWorld]; // flag array of every rank: 2 x kMaxWorld words, slot [parity][src rank]
   unsigned long long* flags;              // this rank's flag array (written by the peers)
-  unsigned long long epoch;               // solve counter << 32; flags are never reset
+  uint32_t seq_base;                      // (solve counter & 0xff) << 24: flags are never reset between solves
+  uint32_t flip;                          // parity offset of this solve: round k uses buffer / flag set (k + flip) & 1, so that
+                                          // a rank that starts the next solve early never touches what a slower peer still reads
   // results
   float* out_eigen_vec;  // N floats (device)
   float* out_eigen_val;  // 1 float  (device)
@@ -431,25 +435,36 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
 }
 
 // ---------------------------------------------------------------------------------------
-// grid-wide (and, when sharded, cross-GPU) barrier at the end of round k
+// grid-wide (and, when sharded, cross-GPU) barrier at the end of round k -- which also carries the max
 // ---------------------------------------------------------------------------------------
-// Every CTA has written its row sums (locally and into every peer's S buffer).
-//   one GPU : arrive = one release-add on a monotonically increasing counter; everybody
-//             acquire-polls the same counter (two L2 trips on the critical path, no fences).
-//   sharded : the last CTA to arrive signals the peers with one 64-bit release store each,
-//             waits for theirs, then releases the local CTAs through the generation word.
-// All waits are bounded by timeout_ns (checked every 1024 polls) so that a missing rank turns
-// into an error code instead of a hung GPU.  Returns false on timeout.
+// Every CTA has written its row sums (locally and into every peer's S buffer) and knows the largest one it
+// published (*s_cta_max: the bits of a non-negative, non-NaN float, so unsigned order = numeric order; kernels
+// that compute the max in their own vector tail pass nullptr and ignore *s_m).
+//   arrive  : atomicMax of ((k + 1) << 32 | bits) into smax[parity], then one release-add on the monotonic
+//             arrival counter (preceded by a system fence when sharded: the CTA's peer stores come first).
+//   sharded : the CTA whose arrival completes the GPU forwards ONE 64-bit word per peer,
+//             (seq << 32) | bits of this GPU's max, with relaxed system-scope stores issued back to back
+//             (a release store per peer would serialise one NVLink round trip per peer).
+//   wait    : EVERY CTA polls the local counter and, when sharded, the G - 1 flag words the peers wrote into
+//             this GPU's memory (acquire loads at system scope) -- no second hop through a generation word.
+//   result  : *s_m = max(0, max_r s[r]) over all GPUs = the reference's find_max (:154-227), so the vector
+//             tail needs a single pass over s (stop test and eigenvector update together).
+// Flags and smax are indexed by the parity of k + flip and tagged with a monotonic sequence number, so they
+// are never reset -- not between rounds, not between solves.  All waits are bounded by timeout_ns (checked
+// every 1024 polls) so that a missing rank turns into an error code instead of a hung GPU.  Returns false on
+// timeout or when another CTA reported one.
 
 struct SpinClock
 {
   unsigned long long t0 = 0ull;
   unsigned int spins = 0u;
-  // true once the wait has lasted longer than limit_ns
-  __device__ __forceinline__ bool expired(unsigned long long limit_ns)
+  // true once the wait has lasted longer than limit_ns, or another CTA has given up
+  __device__ __forceinline__ bool expired(unsigned long long limit_ns, const unsigned int* error_word)
   {
     if ((++spins & 1023u) != 0u)
       return false;
+    if (ld_relaxed_gpu(error_word) != 0u)
+      return true;
     const unsigned long long now = globaltimer_ns();
     if (t0 == 0ull) {
       t0 = now;
@@ -459,64 +474,71 @@ struct SpinClock
   }
 };
 
-constexpr unsigned int kGenPoison = 0xffffffffu;
+constexpr uint32_t kFlagSlots = 2u * (uint32_t)kMaxWorld; // 64-bit words in a rank's flag array
 
 __device__ __forceinline__ bool
-round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort)
+round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned int* s_cta_max = nullptr,
+              volatile float* s_m = nullptr)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
     int fail = 0;
+    // the CTA's warps have folded their maxima into *s_cta_max (shared memory) before the __syncthreads; it is
+    // read and cleared here, and written again only after the closing __syncthreads (next round's pass)
+    uint32_t cta_max_bits = 0u;
+    if (s_cta_max) {
+      cta_max_bits = *s_cta_max;
+      *s_cta_max = 0u;
+    }
+    const uint32_t par = (k + p.flip) & 1u;
     const unsigned int target = (k + 1u) * gridDim.x;
+    const unsigned long long tag = (unsigned long long)(k + 1u) << 32;
     SpinClock clk;
+    atomicMax(&p.bar->smax[par], tag | cta_max_bits);
     if (p.world == 1) {
       red_release_gpu_add(&p.bar->count, 1u);
-      while (ld_acquire_gpu(&p.bar->count) < target) {
-        if (clk.expired(p.timeout_ns)) {
-          atomicExch(&p.bar->error, 1u);
-          fail = 1;
-          break;
-        }
-      }
     } else {
-      __threadfence_system();
+      __threadfence_system(); // this CTA's peer stores (ordered before here by the __syncthreads) come before its arrival
       const unsigned int prev = atomicAdd(&p.bar->count, 1u);
       if (prev + 1u == target) {
-        // ONE system fence orders every CTA's peer stores (observed through the arrival counter)
-        // before the flag stores; the flags themselves are relaxed stores issued back to back
-        // (a release store per peer would serialise one NVLink round trip per peer).
+        // ONE system fence orders every CTA's peer stores (observed through the arrival counter) before the
+        // flag stores; the flags carry this GPU's max along
         __threadfence_system();
-        const unsigned long long want = p.epoch + (unsigned long long)(k + 1u);
+        const unsigned long long mine = atomicMax(&p.bar->smax[par], 0ull); // atomic read
+        const unsigned long long word =
+          ((unsigned long long)(p.seq_base + k + 1u) << 32) | (mine & 0xffffffffull);
         for (uint32_t g = 0; g < p.world; g++)
           if (g != p.rank)
-            st_relaxed_sys(p.peer_flags[g] + p.rank, want);
-        for (uint32_t g = 0; g < p.world && !fail; g++) {
-          if (g == p.rank)
-            continue;
-          while (ld_relaxed_sys(p.flags + g) < want) {
-            if (clk.expired(p.timeout_ns)) {
-              fail = 1;
-              break;
-            }
-          }
-        }
-        __threadfence_system(); // acquire side: the peers' row sums are visible from here on
-        if (fail)
-          atomicExch(&p.bar->error, 1u);
-        st_release_gpu(&p.bar->gen, fail ? kGenPoison : k + 1u);
-      } else {
-        unsigned int g;
-        while ((g = ld_acquire_gpu(&p.bar->gen)) < k + 1u) {
-          if (clk.expired(2ull * p.timeout_ns)) {
-            atomicExch(&p.bar->error, 1u);
+            st_relaxed_sys(p.peer_flags[g] + par * (uint32_t)kMaxWorld + p.rank, word);
+      }
+    }
+    while (ld_acquire_gpu(&p.bar->count) < target) {
+      if (clk.expired(p.timeout_ns, &p.bar->error)) {
+        fail = 1;
+        break;
+      }
+    }
+    uint32_t bits = (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
+    if (p.world > 1) {
+      const uint32_t want = p.seq_base + k + 1u;
+      for (uint32_t g = 0; g < p.world && !fail; g++) {
+        if (g == p.rank)
+          continue;
+        unsigned long long v;
+        // sequence numbers compare modulo 2^32 (the solve counter wraps after 256 solves)
+        while ((int32_t)((uint32_t)((v = ld_acquire_sys(p.flags + par * (uint32_t)kMaxWorld + g)) >> 32) - want) < 0) {
+          if (clk.expired(p.timeout_ns, &p.bar->error)) {
             fail = 1;
             break;
           }
         }
-        if (g == kGenPoison)
-          fail = 1;
+        bits = max(bits, (uint32_t)(v & 0xffffffffull));
       }
     }
+    if (fail)
+      atomicExch(&p.bar->error, 1u);
+    if (s_m)
+      *s_m = __uint_as_float(bits);
     *s_abort = fail;
   }
   __syncthreads();
@@ -562,10 +584,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
 
   float m_prev = 1.f;
   for (uint32_t k = 0;; ++k) {
-    const float* Sprev = p.S[(k + 1) & 1];
-    const float* Eprev = p.E[(k + 1) & 1];
-    float* Scur = p.S[k & 1];
-    float* Ecur = p.E[k & 1];
+    const uint32_t par = (k + p.flip) & 1u; // buffer / flag set of this round (sharded: see RoundParams::flip)
+    const float* Sprev = p.S[par ^ 1u];
+    const float* Eprev = p.E[par ^ 1u];
+    float* Scur = p.S[par];
+    float* Ecur = p.E[par];
     const bool first = (k == 0);
 
     // e_k = e_{k-1} * (s_{k-1} / m_{k-1})          reference :42-43 -> :260; e_0 = 1 (:34 -> :280)
@@ -666,7 +689,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
         s = s / (ld_cg(Eprev + gr) * (ld_cg(Sprev + gr) / m_prev));
       if (p.world > 1) {
         for (uint32_t g = 0; g < p.world; g++)
-          __stcg(p.peer_S[k & 1][g] + gr, s);
+          __stcg(p.peer_S[par][g] + gr, s);
       } else {
         __stcg(Scur + gr, s);
       }

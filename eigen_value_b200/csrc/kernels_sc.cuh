@@ -32,7 +32,6 @@
 namespace st {
 
 constexpr int kResidentCols = 32768; // largest N whose eigenvector is kept in shared memory
-constexpr int kRegVec = 5;           // float4 of s a thread keeps in registers across the tail
 
 // One work unit = one 8192-column chunk of one row (<= 32 KB), reduced by one warp.  The
 // leading `npre` float4 come from the prefetched shared-memory tile, the rest from global
@@ -100,10 +99,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   float* pf_all = reinterpret_cast<float*>(smem_raw);        // kWarps x kPfFloats
   float* e_s = pf_all + (size_t)kWarps * kPfFloats;          // N floats, lives across rounds
   uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem_raw + p.mbar_offset);
-  __shared__ float red_max[32];
-  __shared__ int red_ok[32];
-  __shared__ float bc_max;
-  __shared__ int bc_ok;
+  __shared__ unsigned int s_cta_max; // bits of the largest row sum this CTA published in the current round
+  __shared__ float s_m;              // max(0, max_r s[r]) of the round, out of the barrier
   __shared__ int s_abort;
 
   const uint32_t tid = threadIdx.x;
@@ -111,7 +108,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   const uint32_t warp = tid >> 5;
   const uint32_t N = p.N;
   const uint32_t nv = N >> 2;
-  const bool reg_tail = nv <= (uint32_t)kRegVec * THREADS;
 
   // slice of the N-vector this CTA writes at the end (and its phase offset in the tail scan)
   const uint32_t cb = (uint32_t)((uint64_t)N * blockIdx.x / gridDim.x);
@@ -137,6 +133,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   uint64_t* my_bar = mbar_all + warp;
   if (PF_BATCHES > 0 && lane == 0)
     mbar_init(my_bar, 1u);
+  if (tid == 0)
+    s_cta_max = 0u;
   for (uint32_t c = tid; c < N; c += THREADS)
     e_s[c] = 1.f; // initialise_eigen_vector, reference :267-284
   fence_mbarrier_init();
@@ -165,7 +163,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   }
 
   for (uint32_t k = 0;; ++k) {
-    float* Scur = p.S[k & 1];
+    const uint32_t par = (k + p.flip) & 1u; // buffer / flag set of this round
+    float* Scur = p.S[par];
+    float wmax = 0.f; // lane 0: largest row sum this warp published this round; the reference zero-fills the max cell (:169)
     const bool backward = !resident && p.sweep && (k & 1); // resident units never change owner
 
     // ---- the pass over the matrix ----                                   reference :40 (+ :52)
@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       auto publish = [&](uint32_t rl, float t) {
         const uint32_t gr = p.row0 + rl;
         const float s = t / e_s[gr];
+        wmax = fmaxf(wmax, s); // find_max, reference :154-227 (fmaxf drops NaNs, like the running max of the old scan)
         if (p.world > 1) {
           for (uint32_t g = 0; g < p.world; g++)
-            __stcg(p.peer_S[k & 1][g] + gr, s);
+            __stcg(p.peer_S[par][g] + gr, s);
         } else {
           __stcg(Scur + gr, s);
         }
@@ -283,161 +284,74 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     }
     if (!tma_ok && lane == 0)
       atomicExch(&p.bar->error, 2u);
+    if (lane == 0 && wmax > 0.f)
+      atomicMax(&s_cta_max, __float_as_uint(wmax));
     if (blockIdx.x == 0 && tid == 0)
       stamp_phase(p, k, 0u);
 
-    if (!round_barrier(p, k, &s_abort))
+    // the barrier's first __syncthreads orders the warps' atomicMax before thread 0 reads the CTA's max
+    if (!round_barrier(p, k, &s_abort, &s_cta_max, &s_m))
       break;
     if (blockIdx.x == 0 && tid == 0)
       stamp_phase(p, k, 1u);
+    const float m_k = s_m; // max over every GPU's rows, carried by the barrier            :41
 
-    // ---- every CTA: max / circular stop over the full s, then e update ----        :41-44
-    // 128-bit L2 loads, all loads of a batch issued before anything depends on them.  The
-    // circular neighbour of a vector's last element is the next lane's first element
-    // (shuffle); only lane 31 reads it from memory -- the reference does the same with
-    // shuffle_down + one global read per sub-group (:413-417).  Every CTA scans the same N
-    // floats at the same moment, so each starts at its own offset (cb) to stay off the other
-    // CTAs' L2 lines; max and the stop flag are order-independent.
+    // ---- every CTA: circular stop test over the full s and the e update, ONE pass ----   :42-44
+    // 128-bit L2 loads, all loads of a batch (8 per thread) issued before anything depends on them.  The
+    // circular neighbour of a vector's last element is the next lane's first element (shuffle); only
+    // lane 31 reads it from memory -- the reference does the same with shuffle_down + one global read
+    // per sub-group (:413-417).  Every CTA scans the same N floats at the same moment, so each starts at
+    // its own offset (cb) to stay off the other CTAs' L2 lines; the stop flag is order-independent.
     const float4* S4 = reinterpret_cast<const float4*>(Scur);
     float4* e4_s = reinterpret_cast<float4*>(e_s);
     const uint32_t rotv = cb >> 2;
-    float4 sv4[kRegVec];
-    float mx = 0.f; // reference zero-fills the max cell (:169)
+    const float thr = STOP == kStopRelative ? p.eps * m_k : p.eps;
     int ok = 1;
-    uint32_t dbits = 0u; // relative stop test only: bits of the largest adjacent difference
     auto vec_index = [&](uint32_t idx) {
       const uint32_t v = idx + rotv;
       return v < nv ? v : v - nv;
     };
-    auto scan4 = [&](const float4& v, float nxt) {
-      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-      if (STOP == kStopRelative) {
-        dbits = max(max(dbits, diff_bits(v.x, v.y)),
-                    max(max(diff_bits(v.y, v.z), diff_bits(v.z, v.w)), diff_bits(v.w, nxt)));
-      } else {
-        // strict <, wrap pair included (:413-421)
-        ok &= (fabsf(v.x - v.y) < p.eps) & (fabsf(v.y - v.z) < p.eps) & (fabsf(v.z - v.w) < p.eps) &
-              (fabsf(v.w - nxt) < p.eps);
-      }
-    };
-    if (reg_tail) {
-      float nx[kRegVec];
+    constexpr int kTailBatch = 8;
+    for (uint32_t v0 = 0; v0 < nv; v0 += (uint32_t)kTailBatch * THREADS) {
+      float4 t4[kTailBatch];
+      float nx[kTailBatch];
 #pragma unroll
-      for (int j = 0; j < kRegVec; j++) {
-        const uint32_t idx = tid + (uint32_t)j * THREADS;
+      for (int j = 0; j < kTailBatch; j++) {
+        const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
         const bool active = idx < nv;
         const uint32_t vi = vec_index(idx);
-        sv4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool edge = active && (lane == 31 || idx + 1u >= nv);
         nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < kRegVec; j++) {
-        const uint32_t idx = tid + (uint32_t)j * THREADS;
-        if ((uint32_t)j * THREADS < nv) { // warp-uniform
-          float nxt = __shfl_down_sync(0xffffffffu, sv4[j].x, 1);
+      for (int j = 0; j < kTailBatch; j++) {
+        const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
+        if (v0 + (uint32_t)j * THREADS < nv) { // warp-uniform
+          float nxt = __shfl_down_sync(0xffffffffu, t4[j].x, 1);
           if (lane == 31 || idx + 1u >= nv)
             nxt = nx[j];
-          if (idx < nv)
-            scan4(sv4[j], nxt);
-        }
-      }
-    } else {
-      for (uint32_t v0 = 0; v0 < nv; v0 += 4u * THREADS) {
-        float4 t4[4];
-        float nx[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-          const bool active = idx < nv;
-          const uint32_t vi = vec_index(idx);
-          t4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool edge = active && (lane == 31 || idx + 1u >= nv);
-          nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-          if (v0 + (uint32_t)j * THREADS < nv) { // warp-uniform
-            float nxt = __shfl_down_sync(0xffffffffu, t4[j].x, 1);
-            if (lane == 31 || idx + 1u >= nv)
-              nxt = nx[j];
-            if (idx < nv)
-              scan4(t4[j], nxt);
+          if (idx < nv) {
+            const float4 v = t4[j];
+            // strict <, wrap pair included (:413-421).  Relative test: every pair below eps * m is the same
+            // statement as "the largest difference is below eps * m" (a NaN difference fails either way)
+            ok &= (fabsf(v.x - v.y) < thr) & (fabsf(v.y - v.z) < thr) & (fabsf(v.z - v.w) < thr) &
+                  (fabsf(v.w - nxt) < thr);
+            // e_{k+1} = e_k * (s_k / m_k), in place in shared memory                       :260
+            const uint32_t vi = vec_index(idx);
+            float4 e = e4_s[vi];
+            e.x = e.x * (v.x / m_k);
+            e.y = e.y * (v.y / m_k);
+            e.z = e.z * (v.z / m_k);
+            e.w = e.w * (v.w / m_k);
+            e4_s[vi] = e;
           }
-        }
-      }
-    }
-    if (STOP == kStopRelative)
-      ok = (int)dbits; // from here on `ok` carries the difference bits; max instead of AND
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (STOP == kStopRelative)
-        ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
-      else
-        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
-    }
-    if (lane == 0) {
-      red_max[warp] = mx;
-      red_ok[warp] = ok;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      mx = (uint32_t)lane < kWarps ? red_max[lane] : 0.f;
-      ok = (uint32_t)lane < kWarps ? red_ok[lane] : (STOP == kStopRelative ? 0 : 1);
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (STOP == kStopRelative)
-          ok = (int)max((uint32_t)ok, (uint32_t)__shfl_xor_sync(0xffffffffu, ok, o));
-        else
-          ok &= __shfl_xor_sync(0xffffffffu, ok, o);
-      }
-      if (lane == 0) {
-        bc_max = mx;
-        bc_ok = STOP == kStopRelative ? (__uint_as_float((uint32_t)ok) < p.eps * mx ? 1 : 0) : ok;
-      }
-    }
-    __syncthreads();
-    const float m_k = bc_max;
-    const bool converged = bc_ok != 0;
-
-    // e_{k+1} = e_k * (s_k / m_k), in place in shared memory                       :260
-    auto update4 = [&](uint32_t vi, const float4& sv) {
-      float4 e = e4_s[vi];
-      e.x = e.x * (sv.x / m_k);
-      e.y = e.y * (sv.y / m_k);
-      e.z = e.z * (sv.z / m_k);
-      e.w = e.w * (sv.w / m_k);
-      e4_s[vi] = e;
-    };
-    if (reg_tail) {
-#pragma unroll
-      for (int j = 0; j < kRegVec; j++) {
-        const uint32_t idx = tid + (uint32_t)j * THREADS;
-        if (idx < nv)
-          update4(vec_index(idx), sv4[j]);
-      }
-    } else {
-      for (uint32_t v0 = 0; v0 < nv; v0 += 4u * THREADS) {
-        float4 t4[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-          t4[j] = idx < nv ? ld_cg(S4 + vec_index(idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-          if (idx < nv)
-            update4(vec_index(idx), t4[j]);
         }
       }
     }
     if (blockIdx.x == 0 && tid == 0)
       stamp_round_end(p, k);
-    __syncthreads();
+    const bool converged = __syncthreads_and(ok) != 0; // also orders the e update before the next pass
 
     if (converged || k + 1u == p.max_iter) {
       // the eigenvector update of this round still happens before the break (:42-50)

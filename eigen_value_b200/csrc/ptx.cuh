@@ -29,6 +29,22 @@ ld_acquire_gpu(const unsigned int* p)
   return v;
 }
 
+__device__ __forceinline__ unsigned int
+ld_relaxed_gpu(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long
+ld_relaxed_gpu(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void
 st_release_gpu(unsigned int* p, unsigned int v)
 {

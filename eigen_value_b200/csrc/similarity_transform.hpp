@@ -134,6 +134,7 @@ struct Shard
   bool peer_is_ipc[ST_MAX_WORLD] = {};
   bool linked = false;
   uint64_t solves = 0;
+  uint32_t flip = 0; // parity offset of the next solve's exchange buffers and flag sets (RoundParams::flip)
 };
 
 } // namespace st

@@ -473,8 +473,13 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     p.S[0] = p.peer_S[0][shard->rank];
     p.S[1] = p.peer_S[1][shard->rank];
     p.flags = p.peer_flags[shard->rank];
+    // flags are never reset: their sequence numbers carry the solve counter in the top 8 bits (compared modulo
+    // 2^32) and the round in the low 24; buffers and flag sets start from the parity the last solve did NOT end on
     shard->solves += 1;
-    p.epoch = shard->solves << 32;
+    p.seq_base = (uint32_t)(shard->solves & 0xffu) << 24;
+    p.flip = shard->flip;
+    if (opt.max_iter >= (1u << 24) - 1u)
+      throw std::invalid_argument("solve: a sharded solve supports max_iter below 2^24 - 1");
   }
   p.out_eigen_vec = d_out_vec;
   p.out_eigen_val = d_scalars_;
@@ -642,6 +647,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     return ST_ERR_TIMEOUT;
   }
   const uint32_t passes = words[2];
+  if (shard)
+    shard->flip = (shard->flip + passes) & 1u; // every rank saw the same number of rounds
   const uint32_t stamped = std::min<uint32_t>(passes, p.ts_rounds);
   last_ts_.assign((size_t)stamped + 1, 0);
   ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)stamped + 1),

@@ -442,6 +442,21 @@ inline int atomicMax(int* p, int v)
   return old;
 }
 
+inline unsigned atomicMax(unsigned* p, unsigned v)
+{
+  unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, EMU_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
+{
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, EMU_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
+
 // ---- arithmetic --------------------------------------------------------------------------------------
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }

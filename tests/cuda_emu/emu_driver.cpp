@@ -160,7 +160,8 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         p.S[0] = p.peer_S[0][g];
         p.S[1] = p.peer_S[1][g];
         p.flags = p.peer_flags[g];
-        p.epoch = 1ull << 32;
+        p.seq_base = 1u << 24;
+        p.flip = (uint32_t)(o->max_iter & 1u); // either parity offset must work
       }
       p.out_eigen_val = r.scalars;
       p.out_iter = reinterpret_cast<uint32_t*>(r.scalars + 1);

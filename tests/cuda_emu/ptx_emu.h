@@ -23,6 +23,16 @@ ld_acquire_gpu(const unsigned int* p)
   sched_yield();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
+inline unsigned int
+ld_relaxed_gpu(const unsigned int* p)
+{
+  return __atomic_load_n(p, EMU_RELAXED_LOAD);
+}
+inline unsigned long long
+ld_relaxed_gpu(const unsigned long long* p)
+{
+  return __atomic_load_n(p, EMU_RELAXED_LOAD);
+}
 inline void
 st_release_gpu(unsigned int* p, unsigned int v)
 {

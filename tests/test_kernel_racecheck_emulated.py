@@ -59,7 +59,7 @@ MUTANTS = [
     # the parity double-buffering of the row-sum vector: one barrier per round is only enough because a CTA
     # that runs one round ahead writes the OTHER buffer
     ("resident_e_single_buffered_s", "kernels_sc.cuh",
-     "    float* Scur = p.S[k & 1];",
+     "    float* Scur = p.S[par];",
      "    float* Scur = p.S[0];"),
 ]
 
