@@ -121,6 +121,7 @@ SYMBOLS = {
     "st_shard_export": (ctypes.c_int, [_VP, _VP]),
     "st_shard_import": (ctypes.c_int, [_VP, _VP]),
     "st_shard_link_local": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_uint32]),
+    "st_shard_prepare": (ctypes.c_int, [_VP, ctypes.POINTER(StOptions)]),
     "st_shard_rows": (ctypes.c_int, [_VP, c_u32p, c_u32p]),
     "st_shard_solve": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(StOptions), _VP, ctypes.POINTER(StResult)]),
     "st_shard_solve_bf16": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(StOptions), _VP, ctypes.POINTER(StResult)]),

@@ -845,7 +845,34 @@ st_shard_create(void* ctx, uint32_t dim, uint32_t rank, uint32_t world, void** s
     ABI_CUDA(cudaMemset(s->block, 0, s->block_bytes));
     s->peer_block[rank] = s->block;
     s->linked = (world == 1);
+    // scratch for solves with the default options, now -- a sharded solve never allocates (Context::solve)
+    st_options o;
+    st_default_options(&o);
+    try {
+      std::lock_guard<std::mutex> lock(c->mutex());
+      c->prepare(dim, s->rows, o);
+    } catch (...) {
+      cudaFree(s->block);
+      delete s;
+      throw;
+    }
     *shard = s;
+    return ST_OK;
+  });
+}
+
+int
+st_shard_prepare(void* shard, const st_options* opt)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(s->ctx->mutex());
+    s->ctx->prepare(s->dim, s->rows, o);
     return ST_OK;
   });
 }

@@ -55,6 +55,12 @@ public:
   // its own row block, collectively with the other ranks of the shard group.
   int solve_host(const float* h_mat, uint32_t dim, const st_options& opt, float* h_eigen_val,
                  float* h_eigen_vec, st_result* res, Shard* shard = nullptr);
+  // Every device allocation a solve() of `rows` rows of a dim-column matrix with these options needs (vectors,
+  // stamps, working copy / chunk sums).  solve() calls it itself on one GPU; a SHARDED solve never allocates --
+  // a cudaMalloc / cudaFree on a device with peer mappings may wait for peers that already spin in the collective
+  // round kernel -- so st_shard_create / st_shard_prepare / upload_rows call it before any rank launches.
+  void prepare(uint32_t dim, uint32_t rows, const st_options& opt);
+  bool prepared(uint32_t dim, uint32_t rows, const st_options& opt) const;
   // the two halves of solve_host: every allocation + the (asynchronous) upload | the solve + read-back
   void upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Shard* shard);
   int solve_uploaded(uint32_t dim, const st_options& opt, float* h_eigen_val, float* h_eigen_vec, st_result* res,
@@ -78,6 +84,12 @@ public:
 private:
   friend struct Shard;
   void preload_kernels();
+  struct ScratchNeed
+  {
+    uint32_t vec = 0, stamps = 0;
+    size_t work = 0;
+  };
+  ScratchNeed scratch_need(uint32_t dim, uint32_t rows, const st_options& opt) const;
   void reserve_vectors(uint32_t dim, uint32_t max_iter);
   void reserve_matrix(size_t elems);
   void reserve_work(size_t elems);

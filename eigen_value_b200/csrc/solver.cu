@@ -176,6 +176,40 @@ Context::timer_stop()
 // caller raises max_iter far above the reference's 1000)
 constexpr uint32_t kMaxStampedRounds = 1u << 16;
 
+// Scratch a solve needs, as a function of the problem only (never of the kernel the planner ends up choosing):
+// the five N-vectors, the stamp buffers, and either the in-place working copy or -- rows wider than one
+// 8192-column work unit -- the chunk sums and arrival counters of the unit-scheduled kernels.
+Context::ScratchNeed
+Context::scratch_need(uint32_t dim, uint32_t rows, const st_options& opt) const
+{
+  ScratchNeed n;
+  n.vec = (dim + 31u) & ~31u;
+  n.stamps = std::min<uint32_t>(opt.max_iter, kMaxStampedRounds) + 2u;
+  const size_t units = ((size_t)dim + (size_t)kChunkCols - 1u) / (size_t)kChunkCols;
+  if (opt.form == ST_FORM_INPLACE)
+    n.work = (size_t)rows * dim;
+  else if (units > 1)
+    n.work = (size_t)rows * units + rows;
+  return n;
+}
+
+bool
+Context::prepared(uint32_t dim, uint32_t rows, const st_options& opt) const
+{
+  const ScratchNeed n = scratch_need(dim, rows, opt);
+  return n.vec <= vec_cap_ && n.stamps <= ts_cap_ && n.work <= work_cap_;
+}
+
+void
+Context::prepare(uint32_t dim, uint32_t rows, const st_options& opt)
+{
+  activate();
+  const ScratchNeed n = scratch_need(dim, rows, opt);
+  reserve_vectors(dim, opt.max_iter);
+  if (n.work)
+    reserve_work(n.work);
+}
+
 void
 Context::reserve_vectors(uint32_t dim, uint32_t max_iter)
 {
@@ -405,10 +439,16 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     throw std::invalid_argument("solve: shard not linked or dimension mismatch");
   const auto host_t0 = std::chrono::steady_clock::now();
   activate();
-  reserve_vectors(dim, opt.max_iter);
-
   const uint32_t row0 = shard ? shard->row0 : 0u;
   const uint32_t rows = shard ? shard->rows : dim;
+  // A sharded solve is collective: peers may already spin in the round barrier, and an allocation on a device
+  // with peer mappings may wait for them.  Its scratch was reserved before any rank launched (st_shard_create for
+  // the default options, st_shard_prepare / upload_rows otherwise); refuse instead of allocating here.
+  if (shard && shard->world > 1 && !prepared(dim, rows, opt))
+    throw std::invalid_argument("solve: these options need more scratch than the shard was prepared for -- call "
+                                "st_shard_prepare on every rank and synchronise the ranks before this solve");
+  prepare(dim, rows, opt);
+
   const int form = opt.form == ST_FORM_INPLACE ? kFormInPlace : kFormReadOnly;
   if (opt.stop != ST_STOP_ABSOLUTE && opt.stop != ST_STOP_RELATIVE)
     throw std::invalid_argument("solve: unknown st_options.stop");
@@ -437,10 +477,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   RoundParams p{};
   p.A = d_rows;
   p.W = nullptr;
-  if (form == kFormInPlace) {
-    reserve_work((size_t)rows * dim);
+  if (form == kFormInPlace)
     p.W = d_work_;
-  }
   p.N = dim;
   p.row0 = row0;
   p.rows = rows;
@@ -561,8 +599,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         p.chunk_cols = dim; // the whole eigenvector is resident
         const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
         if (units > 1u) {
-          // chunk sums + per-row arrival counters of rows that span several work units
-          reserve_work((size_t)rows * units + rows);
+          // chunk sums + per-row arrival counters of rows that span several work units (reserved by prepare())
           p.partial = d_work_;
           p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
           ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * rows, stream_));
@@ -700,9 +737,7 @@ Context::upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Sh
   const uint32_t rows = shard ? shard->rows : dim;
   const size_t elems = (size_t)rows * dim;
   reserve_matrix(elems);
-  reserve_vectors(dim, opt.max_iter);
-  if (opt.form == ST_FORM_INPLACE)
-    reserve_work(elems);
+  prepare(dim, rows, opt);
   // the caller's matrix is never modified (reference similarity_transform.cpp:14,19 copies it)
   copy_h2d(d_mat_, h_mat + (size_t)row0 * dim, sizeof(float) * elems);
 }

@@ -51,8 +51,12 @@ class ShardedSolver:
     """This rank's shard of a dim x dim problem plus the mapped exchange blocks of its peers."""
 
     def __init__(self, solver: Solver, dim: int, rank: int, world: int,
-                 exchange: Optional[Callable[[bytes, int, int], Sequence[bytes]]] = None):
+                 exchange: Optional[Callable[[bytes, int, int], Sequence[bytes]]] = None,
+                 barrier: Optional[Callable[[], None]] = None):
         self.solver, self.dim, self.rank, self.world = solver, dim, rank, world
+        self._barrier = barrier
+        self._prepared = (1000, 0)      # (max_iter, in-place form) st_shard_create reserved scratch for
+        self._vec: Optional[DeviceBuffer] = None
         self.row0, self.rows = shard_rows(dim, rank, world)
         self.lib = solver.lib
         self.shard = ctypes.c_void_p()
@@ -82,15 +86,38 @@ class ShardedSolver:
         o = make_options(self.lib, **opts)
         res = StResult()
         own = d_eigen_vec is None
-        vec = self.solver.alloc(4 * self.dim) if own else d_eigen_vec
+        # A sharded solve never allocates on the device (an allocation may wait for peers that already spin in the
+        # collective kernel): scratch for options beyond what st_shard_create reserved is taken here, on every rank
+        # (the options of a collective call are the same everywhere), followed by a host barrier.
+        need = (int(o.max_iter), 1 if int(o.form) != 0 else 0)
+        grow = need[0] > self._prepared[0] or need[1] > self._prepared[1] or (own and self._vec is None)
+        if grow:
+            check(self.lib.st_shard_prepare(self.shard, ctypes.byref(o)), "st_shard_prepare")
+            if own and self._vec is None:
+                self._vec = self.solver.alloc(4 * self.dim)
+            self._prepared = (max(need[0], self._prepared[0]), max(need[1], self._prepared[1]))
+            self.solver.synchronize()
+            self._host_barrier()
+        vec = self._vec if own else d_eigen_vec
         fn = self.lib.st_shard_solve_bf16 if bf16 else self.lib.st_shard_solve   # bf16: rows in bfloat16 storage
         check(fn(self.shard, d_rows.ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res)), "st_shard_solve")
         out = vec.download(np.float32, self.dim) if own else None
-        if own:
-            vec.free()
         return SolveInfo.from_c(res), out
 
+    def _host_barrier(self) -> None:
+        if self.world == 1:
+            return
+        if self._barrier is not None:
+            self._barrier()
+            return
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+
     def close(self) -> None:
+        if self._vec is not None:
+            self._vec.free()
+            self._vec = None
         if self.shard is not None and self.shard.value:
             self.lib.st_shard_destroy(self.shard)
             self.shard = None

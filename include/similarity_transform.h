@@ -292,6 +292,12 @@ int st_shard_import(void* shard, const void* handles);
 /* Same-process alternative to export/import (one host thread per GPU): links `world` shards
  * created in this process, in rank order, through plain CUDA peer access. */
 int st_shard_link_local(void** shards, uint32_t world);
+/* Reserves every device allocation st_shard_solve needs with these options (NULL = defaults).  A sharded solve
+ * never allocates: a cudaMalloc / cudaFree on a device with peer mappings may wait for peers that already spin in
+ * the collective kernel.  st_shard_create prepares for the default options; before the first solve with options
+ * that need more (the in-place form, max_iter above ST_MAX_ITR) call this on EVERY rank and synchronise the ranks
+ * on the host.  st_shard_solve returns ST_ERR_ARG when it would have to allocate. */
+int st_shard_prepare(void* shard, const st_options* opt);
 int st_shard_rows(void* shard, uint32_t* row0, uint32_t* rows);
 int st_shard_solve(void* shard, const float* d_rows, const st_options* opt, float* d_eigen_vec,
                    st_result* res);
