@@ -82,6 +82,36 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return (float)warp_sum(acc[0]);
 }
 
+// One SHARE of a work unit = one of its kUnroll accumulators: the vectors j with (j / 32) % 8 == a, i.e.
+// j = lane + 32 a + 256 b for b = 0, 1, ... -- eight 512-byte pieces of the 32 KB unit, all eight loads in flight
+// at once.  The accumulators of a unit are independent FMA chains (chunk_dot_prefetched folds them only at the
+// end), so eight warps can each run one chain in its own order of b and a ninth step folds the eight per-lane
+// results exactly like one warp would have: splitting a unit this way cannot change a bit.  Used for the last
+// units of a round, so that the end-of-round straggle is an eighth of a unit instead of a whole one.
+constexpr uint32_t kShares = (uint32_t)kUnroll;
+constexpr uint32_t kEndgameMaxUnits = 2048; // scratch is reserved for this many end-game units (>= TW / 2 up to 256 SMs)
+
+__device__ __forceinline__ float
+share_dot(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane, uint32_t acc_idx)
+{
+  constexpr int kBatches = kChunkCols / 4 / (32 * kUnroll); // 8 batches of 256 vectors in a full unit
+  float4 v[kBatches];
+  const uint32_t j0 = (uint32_t)lane + 32u * acc_idx;
+#pragma unroll
+  for (int b = 0; b < kBatches; b++) {
+    const uint32_t j = j0 + 256u * (uint32_t)b;
+    v[b] = j < nv ? ld_stream(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int b = 0; b < kBatches; b++) {
+    const uint32_t j = j0 + 256u * (uint32_t)b;
+    if (j < nv)
+      acc = dot_acc(v[b], es[j], acc);
+  }
+  return acc;
+}
+
 template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
@@ -128,6 +158,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // small, L2-resident matrices the one-address atomic stream costs more than the skew it removes)
   const uint32_t D = (p.dynamic && U > TW) ? U - TW : 0u; // dynamically scheduled units per round
   constexpr uint32_t kChunkVec = kChunkCols / 4;
+  // End game: the LAST E dynamically scheduled units of a round are handed out as 8 shares each (one accumulator
+  // per grab, share_dot), so the warps that finish early fill the gaps the last whole units leave, and the round
+  // ends within an eighth of a unit's time.  fp32 storage and accumulation only; E == 0 switches it off.
+  constexpr bool kCanShare = sizeof(ACC) == 4 && !kBf16;
+  const uint32_t E = kCanShare ? min(p.endgame, D) : 0u;
+  const uint32_t D1 = D - E;            // whole units handed out dynamically
+  const uint32_t G = D1 + kShares * E;  // successful grabs per round
 
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
@@ -200,13 +237,54 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
       };
       // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
-      // so round k hands out the values [k * (D + TW), k * (D + TW) + D)
-      const uint32_t base = k * (D + TW);
+      // so round k hands out the values [k * (G + TW), k * (G + TW) + G)
+      const uint32_t base = k * (G + TW);
       uint32_t cur = gw;
       bool have = cur < U;
       bool first_unit = true;
-      uint32_t grabbed = 0, pend_row = 0, pend_old = 0;
-      bool pending = false;
+      bool is_share = false;
+      uint32_t share_acc = 0;
+      // what the previous work item left to be settled one item later, when the atomic that decides it has long
+      // returned: 1 = a row's arrival counter (lane 0), 2 = a share's arrival counter (the whole warp folds)
+      enum { kPendNone = 0, kPendRow = 1, kPendShare = 2 };
+      int pend_kind = kPendNone;          // warp-uniform
+      uint32_t pend_unit = 0;             // row (kPendRow) or dynamic unit index (kPendShare), warp-uniform
+      uint32_t grabbed = 0, pend_old = 0; // lane 0
+      auto settle = [&]() {
+        if (pend_kind == kPendRow) {
+          if (lane == 0)
+            finish_row(pend_unit, pend_old);
+        } else if (pend_kind == kPendShare) {
+          const uint32_t old = __shfl_sync(0xffffffffu, pend_old, 0);
+          if (old % kShares == kShares - 1u) { // this warp's share completed the unit: fold the eight chains
+            __threadfence();
+            const uint32_t slot = pend_unit - (TW + D1);
+            const float* sb = p.share_buf + (size_t)slot * (kShares * 32u) + (uint32_t)lane;
+            float acc[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++)
+              acc[u] = ld_cg(sb + 32 * u);
+#pragma unroll
+            for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
+#pragma unroll
+              for (int u = 0; u < s2; u++)
+                acc[u] += acc[u + s2];
+            const float t = warp_sum(acc[0]);
+            if (lane == 0) {
+              const uint32_t u = backward ? (U - 1u - pend_unit) : pend_unit;
+              const uint32_t rl = u / nch;
+              if (nch == 1u) {
+                publish(rl, t);
+              } else { // rare (one share in eight): the row's counter is waited for on the spot
+                __stcg(p.partial + (size_t)rl * nch + (u - rl * nch), t);
+                __threadfence();
+                finish_row(rl, atomicAdd(p.row_done + rl, 1u));
+              }
+            }
+          }
+        }
+        pend_kind = kPendNone;
+      };
       if (p.dynamic && lane == 0)
         grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
       for (;;) {
@@ -216,45 +294,66 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          uint32_t npre = 0;
-          if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
-            tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
-            pf_consumed++;
-            npre = min(kPfFloats >> 2, seg_nv);
-          } else if (resident && first_unit) {
-            npre = seg_nv; // landed before round 0 and never evicted
-          }
-          float t;
-          if (kBf16) {
-            // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
-            const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
-                                 ch * (kChunkVec >> 1);
-            t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
-          } else {
-            t = chunk_dot_prefetched<LD, ACC>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
-                                              reinterpret_cast<const float4*>(my_pf), npre);
-          }
-          if (lane == 0) {
-            if (pending)
-              finish_row(pend_row, pend_old); // the atomic issued one unit ago has long returned
-            pending = false;
-            if (nch == 1u) {
-              publish(rl, t);
-            } else {
-              __stcg(p.partial + (size_t)rl * nch + ch, t);
+          if (kCanShare && is_share) {
+            const float acc = share_dot(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, share_acc);
+            settle();
+            const uint32_t slot = cur - (TW + D1);
+            __stcg(p.share_buf + (size_t)slot * (kShares * 32u) + share_acc * 32u + (uint32_t)lane, acc);
+            __syncwarp();
+            if (lane == 0) {
               __threadfence();
-              pend_old = atomicAdd(p.row_done + rl, 1u);
-              pend_row = rl;
-              pending = true;
+              pend_old = atomicAdd(p.share_done + slot, 1u); // monotonic: + 8 per round
+            }
+            pend_kind = kPendShare;
+            pend_unit = cur;
+          } else {
+            uint32_t npre = 0;
+            if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
+              tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
+              pf_consumed++;
+              npre = min(kPfFloats >> 2, seg_nv);
+            } else if (resident && first_unit) {
+              npre = seg_nv; // landed before round 0 and never evicted
+            }
+            float t;
+            if (kBf16) {
+              // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
+              const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
+                                   ch * (kChunkVec >> 1);
+              t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
+            } else {
+              t = chunk_dot_prefetched<LD, ACC>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
+                                                reinterpret_cast<const float4*>(my_pf), npre);
+            }
+            settle(); // the atomic issued one item ago has long returned
+            if (nch == 1u) {
+              if (lane == 0)
+                publish(rl, t);
+            } else {
+              if (lane == 0) {
+                __stcg(p.partial + (size_t)rl * nch + ch, t);
+                __threadfence();
+                pend_old = atomicAdd(p.row_done + rl, 1u);
+              }
+              pend_kind = kPendRow;
+              pend_unit = rl;
             }
           }
         }
         first_unit = false;
         if (p.dynamic) {
           const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
-          if (d >= D)
+          if (d >= G)
             break;
-          cur = TW + d;
+          if (d < D1) {
+            cur = TW + d;
+            is_share = false;
+          } else {
+            const uint32_t sh = d - D1;
+            cur = TW + D1 + sh / kShares;
+            share_acc = sh % kShares;
+            is_share = true;
+          }
           if (lane == 0)
             grabbed = atomicAdd(&p.bar->row_counter, 1u);
         } else {
@@ -264,8 +363,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
         have = true;
       }
-      if (lane == 0 && pending)
-        finish_row(pend_row, pend_old);
+      settle();
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
     if (PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {

@@ -186,10 +186,14 @@ Context::scratch_need(uint32_t dim, uint32_t rows, const st_options& opt) const
   n.vec = (dim + 31u) & ~31u;
   n.stamps = std::min<uint32_t>(opt.max_iter, kMaxStampedRounds) + 2u;
   const size_t units = ((size_t)dim + (size_t)kChunkCols - 1u) / (size_t)kChunkCols;
-  if (opt.form == ST_FORM_INPLACE)
+  if (opt.form == ST_FORM_INPLACE) {
     n.work = (size_t)rows * dim;
-  else if (units > 1)
-    n.work = (size_t)rows * units + rows;
+  } else {
+    if (units > 1)
+      n.work = (size_t)rows * units + rows;
+    if (dim >= (uint32_t)kChunkCols) // end-game shares: 8 x 32 partial sums + one counter per end-game unit
+      n.work += (size_t)kEndgameMaxUnits * (kShares * 32u + 1u);
+  }
   return n;
 }
 
@@ -598,11 +602,24 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         p.mbar_offset = moff;
         p.chunk_cols = dim; // the whole eigenvector is resident
         const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
+        size_t off = 0; // layout of d_work_ (reserved by prepare()): chunk sums | row counters | share sums | share counters
         if (units > 1u) {
-          // chunk sums + per-row arrival counters of rows that span several work units (reserved by prepare())
+          // chunk sums + per-row arrival counters of rows that span several work units
           p.partial = d_work_;
           p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
           ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * rows, stream_));
+          off = (size_t)rows * units + rows;
+        }
+        // End game: the last min(D, TW / 2) dynamically scheduled units of a round go out as 8 shares each.  When the
+        // whole units run out every warp is, on average, half way through one, so half a warp-population's worth of
+        // finer work is what fills the gaps until the last whole unit ends.  st_options.sweep bit 4 switches it off.
+        const uint64_t all_units = (uint64_t)rows * units;
+        const uint32_t tw = (uint32_t)g * (uint32_t)(t / 32);
+        if (p.dynamic && !(opt.sweep & 16) && !bf16 && !acc64 && dim >= (uint32_t)kChunkCols && all_units > tw) {
+          p.endgame = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(all_units - tw, tw / 2u), kEndgameMaxUnits);
+          p.share_buf = d_work_ + off;
+          p.share_done = reinterpret_cast<unsigned int*>(p.share_buf + (size_t)p.endgame * (kShares * 32u));
+          ST_CUDA(cudaMemsetAsync(p.share_done, 0, sizeof(unsigned int) * p.endgame, stream_));
         }
         break;
       }

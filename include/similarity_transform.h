@@ -106,20 +106,21 @@ typedef struct st_options
   int32_t form;      /* ST_FORM_*                                                   */
   int32_t sweep;     /* bit 0: alternate the row order every round so the tail of one pass is
                         the L2-resident head of the next (default on); bit 1 / bit 2: force
-                        static / dynamic work-unit scheduling in the resident-e kernel    */
+                        static / dynamic work-unit scheduling in the unit-scheduled kernels; bit 3:
+                        no in-kernel time stamps; bit 4: no end game (the last units of a round are
+                        normally handed out as eight shares each, csrc/kernels_sc.cuh)          */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
   int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, one GPU), resident-e
                         kernel (N <= 32768), general chunked loop otherwise; 1 = general loop,
-                        2-9 = TMA-ring variants, 10-19 = resident-e variants, 20 = on-chip,
-                        21-23 = resident-e configuration 13 plus an L2 prefetch of 8 / 16 / 32 KB per
-                        warp across the round barrier, 24-26 = ... and / or of the warp's next unit
-                        during the pass (static scheduling, sweep bit 1); tuning variants,
-                        ST_STOP_ABSOLUTE only                                                      */
+                        10-13 = resident-e configurations (prefetch slot of 2 / 0 / 3 / 1 x 4 KB per
+                        warp), 20 = on-chip cluster kernel; any other value is refused (the TMA-ring,
+                        256- / 1024-thread and L2-prefetch variants of round 1 lost on hardware and
+                        were removed)                                                              */
   int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
-  int32_t stop;        /* ST_STOP_*; tuning kernels 2-9, 11, 14-19 support ST_STOP_ABSOLUTE only */
+  int32_t stop;        /* ST_STOP_*                                                               */
   int32_t accumulate;  /* ST_ACC_*                                                                */
 } st_options;
 

@@ -80,6 +80,11 @@ def lib() -> ctypes.CDLL:
             ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
             ctypes.POINTER(ctypes.c_double)]
         L.oracle_similarity_transform_ex2.restype = ctypes.c_int64
+        L.oracle_similarity_transform_generated.argtypes = [
+            ctypes.c_int, ctypes.c_uint64, _f32p, _f32p, ctypes.c_uint32,
+            np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS"),
+            ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.oracle_similarity_transform_generated.restype = ctypes.c_int64
         L.oracle_stop_relative.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float]
         L.oracle_stop_relative.restype = ctypes.c_uint32
         L.oracle_time_rounds.argtypes = [_f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
@@ -176,6 +181,22 @@ def similarity_transform(mat: np.ndarray, eps: float = EPS, max_itr: int = MAX_I
     ms = ctypes.c_double(0.0)
     rc = lib().oracle_similarity_transform_ex2(mat, val, vec, n, itr, eps, max_itr, form, sum_mode,
                                                ranks, stop, ctypes.byref(ms))
+    if rc < 0:
+        raise MemoryError("oracle allocation failed")
+    return val[0], vec, ms.value, int(itr[0])
+
+
+def similarity_transform_generated(kind: str, dim: int, seed: int = 0, eps: float = EPS, max_itr: int = MAX_ITR,
+                                   sum_mode: int = SUM_CUDA, stop: int = STOP_ABSOLUTE):
+    """The read-only loop on a Hilbert ("hilbert") or seeded uniform ("uniform") matrix that is generated row by
+    row and never stored: O(N) memory, the same bits as similarity_transform(hilbert(dim) / uniform(dim, seed),
+    form=FORM_READONLY, ...).  How the sizes no host can hold get CPU-computed expected values."""
+    val = np.empty(1, dtype=np.float32)
+    vec = np.empty(dim, dtype=np.float32)
+    itr = np.zeros(1, dtype=np.uint32)
+    ms = ctypes.c_double(0.0)
+    rc = lib().oracle_similarity_transform_generated({"hilbert": 0, "uniform": 1}[kind], seed, val, vec, dim, itr,
+                                                     eps, max_itr, sum_mode, stop, ctypes.byref(ms))
     if rc < 0:
         raise MemoryError("oracle allocation failed")
     return val[0], vec, ms.value, int(itr[0])

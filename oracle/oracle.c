@@ -540,6 +540,65 @@ oracle_similarity_transform_ex2(const float* mat, float* eigen_val, float* eigen
   return (int64_t)(t1 - t0); /* :57-58 duration_cast<milliseconds> truncates */
 }
 
+/*
+ * The same loop on a GENERATED matrix that is never materialised (read-only form only): every row is produced
+ * into a per-thread buffer by the generator of SURVEY 8(d) -- kind 0: Hilbert (utils.cpp:150), kind 1: the
+ * seeded Philox uniform (0,1] fill -- and reduced right away.  Bit for bit what oracle_similarity_transform_ex2
+ * returns on the stored matrix (tests/test_oracle_cuda_order.py), but it needs O(N) memory, so the sizes no host
+ * can hold (N = 65536: 16 GiB, N = 131072: 64 GiB -- BASELINE configs 3 to 5) get CPU-computed expected bits too.
+ */
+int64_t
+oracle_similarity_transform_generated(int kind, uint64_t seed, float* eigen_val, float* eigen_vec, uint32_t dim,
+                                      uint32_t* iter_count, float eps, uint32_t max_itr, int sum_mode,
+                                      int stop_mode, double* elapsed_ms)
+{
+  const size_t n = dim;
+  if (dim == 0 || (kind != 0 && kind != 1))
+    return -1;
+  float* sum_vec = (float*)malloc(sizeof(float) * n);
+  if (!sum_vec)
+    return -1;
+  oracle_initialise_eigen_vector(eigen_vec, dim); /* :34 */
+  double t0 = now_ms();
+  uint32_t i = 0;
+  int failed = 0;
+  for (; i < max_itr && !failed; i++) {
+#pragma omp parallel
+    {
+      float* row = (float*)malloc(sizeof(float) * n);
+      if (!row) {
+#pragma omp atomic write
+        failed = 1;
+      } else {
+#pragma omp for schedule(dynamic, 16)
+        for (size_t r = 0; r < n; r++) {
+          if (kind == 0)
+            oracle_generate_hilbert(row, dim, (uint32_t)r, 1);
+          else
+            oracle_generate_uniform(row, dim, (uint32_t)r, 1, seed);
+          sum_vec[r] = row_dot(row, eigen_vec, n, sum_mode) / eigen_vec[r];
+        }
+        free(row);
+      }
+    }
+    if (failed)
+      break;
+    float m = oracle_find_max(sum_vec, dim);                 /* :41 */
+    oracle_compute_eigen_vector(sum_vec, m, eigen_vec, dim); /* :42-43 */
+    const uint32_t converged = stop_mode == ORACLE_STOP_RELATIVE ? oracle_stop_relative(sum_vec, dim, eps, m)
+                                                                 : oracle_stop(sum_vec, dim, eps);
+    if (converged == 1) /* :44-50 */
+      break;
+  }
+  double t1 = now_ms();
+  *iter_count = i;         /* :54 */
+  *eigen_val = sum_vec[0]; /* :60-65 */
+  if (elapsed_ms)
+    *elapsed_ms = t1 - t0;
+  free(sum_vec);
+  return failed ? -1 : (int64_t)(t1 - t0);
+}
+
 /* The reference's stop test (the only one parity is defined on). */
 int64_t
 oracle_similarity_transform_ex(const float* mat, float* eigen_val, float* eigen_vec, uint32_t dim,
