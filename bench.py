@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sweep-table", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="skip the side records on BASELINE configs 3-5 (hilbert-65536 on one GPU, hilbert-131072 and "
+                         "uniform-131072 capped at 50 rounds at every GPU count); they only run with the default workload")
     ap.add_argument("--scale-base-dim", type=int, default=32768,
                     help="N=1 only: also time Hilbert of this size (the sharded runs' workload) as the strong-scaling base; 0 = skip")
     return ap.parse_args()
@@ -88,6 +91,71 @@ def recorded_traffic(workload: str):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# parity verdict: the solve's bits against CPU-computed expected values
+# ---------------------------------------------------------------------------------------------
+def expected_result(workload: str, max_iter: int):
+    """(entry, source) for this workload from the committed golden files, or (None, None).
+    tests/golden/generated_expected.json: the oracle's matrix-free loop in the CUDA kernels' evaluation order
+    (tests/golden/make_generated_golden.py), the uniform cases capped at 50 rounds.
+    tests/golden/gpu_recorded.json: B200 outputs of round 1 that the oracle reproduced on the CPU afterwards."""
+    def usable(e_iter, e_cap):
+        if e_iter < e_cap:                  # converged: any cap above the round count gives the same result
+            return max_iter > e_iter
+        return max_iter == e_cap            # ran into its cap: only the same cap compares
+
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "generated_expected.json")) as f:
+            e = json.load(f)["cases"].get(workload)
+        if e is not None and usable(e["iter_count"], e["max_iter"]):
+            return e, "tests/golden/generated_expected.json"
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "gpu_recorded.json")) as f:
+            rec = json.load(f)["cases"]
+        kind, dim = parse_workload(workload)
+        for e in rec:
+            if (e["workload"] == kind and e["dim"] == dim and e.get("form") == "readonly" and "eigen_val" in e
+                    and usable(e["iter_count"], 1000)):
+                return e, "tests/golden/gpu_recorded.json"
+    except Exception:
+        pass
+    return None, None
+
+
+def parity_record(workload: str, max_iter: int, eigen_val: float, iter_count: int, vec=None):
+    """{"checked_against", "bits_equal", ...}: eigenvalue bits, round count and (where the golden file has one) the
+    sha256 of the raw eigenvector.  Only meaningful for the default options (read-only form, eps 1e-3, absolute stop)."""
+    import hashlib
+    import numpy as np
+    e, src = expected_result(workload, max_iter)
+    if e is None:
+        return {"checked_against": None, "bits_equal": None}
+    got_bits = int(np.float32(eigen_val).view(np.uint32))
+    want_bits = int(np.float32(e["eigen_val"]).view(np.uint32))
+    out = {"checked_against": src, "eigen_val_bits": got_bits, "expected_bits": want_bits,
+           "rounds": int(iter_count), "expected_rounds": int(e["iter_count"]),
+           "bits_equal": bool(got_bits == want_bits and int(iter_count) == int(e["iter_count"]))}
+    if vec is not None and "eigen_vec_sha256" in e:
+        digest = hashlib.sha256(np.ascontiguousarray(vec, dtype=np.float32).tobytes()).hexdigest()
+        out["eigen_vec_sha256_equal"] = bool(digest == e["eigen_vec_sha256"])
+        out["bits_equal"] = bool(out["bits_equal"] and out["eigen_vec_sha256_equal"])
+    return out
+
+
+def bind_near_gpu(index: int):
+    """NUMA placement of this rank's host buffers: run on the CPUs next to the GPU before allocating pinned memory
+    (first touch decides the node).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
     except Exception:
         return None
 
@@ -294,6 +362,7 @@ def main():
     from eigen_value_b200.sharded import ShardedSolver
 
     torch.cuda.set_device(local_rank)
+    near_cpus = bind_near_gpu(local_rank)      # NUMA: this rank's pinned host buffers live next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     solver = Solver(local_rank)
@@ -388,54 +457,69 @@ def main():
     last = infos[-1]
     round_us = statistics.median(i.round_us_median for i in infos)
 
+    # ---- parity verdict on the timed solves' result (default options only) ----
+    default_opts = (args.form == 0 and args.eps == 1e-3 and args.stop == "absolute" and not bf16
+                    and args.accumulate == "f32")
+    parity = None
+    if default_opts and rank == 0:
+        parity = parity_record(workload, args.max_iter, last.eigen_val, last.iter_count,
+                               d_vec.download(np.float32, dim))
+
     # ---- e2e through the C ABI with host buffers ----
     e2e = None
+    e2e_pageable = None
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 5))
-        host = torch.empty((rows, dim), dtype=torch.float32).pin_memory()
         check = _lib.check
-        check(solver.lib.st_memcpy_d2h(solver.ctx, host.data_ptr(), d_rows.ptr, 4 * rows * dim), "d2h")
-        h_np = host.numpy()
-        e2e_ms, e2e_passes = [], 0
+        pinned_host = torch.empty((rows, dim), dtype=torch.float32).pin_memory()
+        check(solver.lib.st_memcpy_d2h(solver.ctx, pinned_host.data_ptr(), d_rows.ptr, 4 * rows * dim), "d2h")
+        ev = None
         if sh is None:
             from eigen_value_b200 import EigenValue
             ev = EigenValue()                            # make_queue(): device 0 == this process's GPU
+
+        def e2e_leg(h_np, what):
+            """The metric through the C ABI with HOST buffers: per step the host->device copy of the matrix (rows),
+            the solve and the device->host read of lambda / eigenvector / round count are all inside the timed region."""
+            e2e_ms, e2e_passes = [], 0
             val = np.empty(1, np.float32)
             vec = np.empty(dim, np.float32)
             slot = np.zeros(1, np.uint64)
             for i in range(1 + e2e_steps):
-                t0 = time.perf_counter()
-                ms = solver.lib.max_eigen_value(ev.sycl_q, h_np.ctypes.data, val.ctypes.data, vec.ctypes.data,
-                                                dim, slot.ctypes.data)
-                t1 = time.perf_counter()
-                assert ms >= 0
+                if sh is None:
+                    t0 = time.perf_counter()
+                    ms = solver.lib.max_eigen_value(ev.sycl_q, h_np.ctypes.data, val.ctypes.data, vec.ctypes.data,
+                                                    dim, slot.ctypes.data)
+                    t1 = time.perf_counter()
+                    assert ms >= 0
+                    passes_i = min(int(slot[0]) + 1, 1000)
+                else:
+                    barrier()
+                    t0 = time.perf_counter()
+                    check(solver.lib.st_memcpy_h2d(solver.ctx, d_rows.ptr, h_np.ctypes.data, 4 * rows * dim), "h2d")
+                    info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, **opts)
+                    check(solver.lib.st_memcpy_d2h(solver.ctx, vec.ctypes.data, d_vec.ptr, 4 * dim), "d2h")
+                    barrier()
+                    t1 = time.perf_counter()
+                    passes_i = info.passes
                 if i:
                     e2e_ms.append((t1 - t0) * 1e3)
-                    e2e_passes += min(int(slot[0]) + 1, 1000)
-            d2h = 4 * dim + 4 + 4
-        else:
-            vec = np.empty(dim, np.float32)
-            for i in range(1 + e2e_steps):
-                barrier()
-                t0 = time.perf_counter()
-                check(solver.lib.st_memcpy_h2d(solver.ctx, d_rows.ptr, host.data_ptr(), 4 * rows * dim), "h2d")
-                info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, **opts)
-                check(solver.lib.st_memcpy_d2h(solver.ctx, vec.ctypes.data, d_vec.ptr, 4 * dim), "d2h")
-                barrier()
-                t1 = time.perf_counter()
-                if i:
-                    e2e_ms.append((t1 - t0) * 1e3)
-                    e2e_passes += info.passes
-            d2h = 4 * dim + 8
-        tt = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_total_ms = float(tt[0])
-        e2e = {"value": round(e2e_passes * 4.0 * dim * dim / (e2e_total_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
-               "h2d_bytes_per_step": 4 * rows * dim, "d2h_bytes_per_step": d2h,
-               "ms_per_step": round(e2e_total_ms / e2e_steps, 3), "steps": e2e_steps,
-               "api": "max_eigen_value (C ABI, pinned host matrix)" if sh is None
-                      else "st_memcpy_h2d + st_shard_solve + st_memcpy_d2h (C ABI, pinned host rows)"}
+                    e2e_passes += passes_i
+            tt = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_ms = float(tt[0])
+            api = ("max_eigen_value (C ABI)" if sh is None else "st_memcpy_h2d + st_shard_solve + st_memcpy_d2h (C ABI)")
+            return {"value": round(e2e_passes * 4.0 * dim * dim / (total_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
+                    "h2d_bytes_per_step": 4 * rows * dim, "d2h_bytes_per_step": 4 * dim + 8,
+                    "ms_per_step": round(total_ms / e2e_steps, 3), "steps": e2e_steps, "api": f"{api}, {what}"}
+
+        e2e = e2e_leg(pinned_host.numpy(), "pinned host matrix")
+        # what the reference's wrapper passes (wrapper/python/similarity_transform.py:71-76): a plain numpy array.
+        # Pageable memory is staged through pinned bounce buffers by the library's upload threads (csrc/solver.cu)
+        pageable = np.array(pinned_host.numpy(), copy=True)
+        e2e_pageable = e2e_leg(pageable, "pageable host matrix (plain numpy array, as the reference wrapper passes)")
+        del pageable, pinned_host
 
     # ---- Hilbert sweep of the README sizes (config 2), N=1 only: ms to converge per size ----
     table = None
@@ -471,6 +555,69 @@ def main():
                       "l2": "matrix larger than L2; no flush" if 4 * n * n > 2 * solver.l2_bytes else "L2-resident"}
         d.free()
         d_v.free()
+
+    # ---- north-star side records: BASELINE configs 3-5 at this GPU count, driver-observed ----
+    # hilbert-131072 to convergence and uniform-131072 (seed 0x5EED0002) capped at 50 rounds, row-block sharded over
+    # the ranks (64 GiB / world per GPU), plus hilbert-65536 on one GPU; each with its own parity verdict against the
+    # CPU-computed expected bits.  The main workload's buffers are released first.
+    north_star = None
+    if args.workload is None and not args.no_north_star and default_opts:
+        d_rows.free()
+        d_vec.free()
+        if sh is not None:
+            sh.close()
+            sh = None
+        north_star = []
+        cases = [("hilbert-131072", 1000, 2), ("uniform-131072", 50, 1)]
+        if world == 1:
+            cases.insert(0, ("hilbert-65536", 1000, 2))
+        for name, cap, reps in cases:
+            k2, n2 = parse_workload(name)
+            sh2 = ShardedSolver(solver, n2, rank, world) if world > 1 else None
+            r0, rws = (sh2.row0, sh2.rows) if sh2 else (0, n2)
+            seed2 = SEEDS.get(n2, 0x5EED0000 + n2)
+            d2 = solver.hilbert(n2, r0, rws) if k2 == "hilbert" else solver.uniform(n2, seed2, r0, rws)
+            v2 = solver.alloc(4 * n2)
+            solver.synchronize()
+            o2 = dict(opts, max_iter=cap)
+
+            def one():
+                if sh2 is None:
+                    return solver.solve_device(d2, n2, d_eigen_vec=v2, **o2)[0]
+                return sh2.solve(d2, d_eigen_vec=v2, **o2)[0]
+
+            barrier()
+            one()                                           # warm-up (first touch of the matrix, module state)
+            runs = []
+            with ClockSampler(local_rank) as ck:
+                for _ in range(reps):
+                    barrier()
+                    runs.append(one())
+                barrier()
+                ph = solver.phase_breakdown()
+            tms = torch.tensor([sum(i.loop_ms for i in runs)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms2 = float(tms[0]) / len(runs)
+            lastr = runs[-1]
+            gbs = lastr.passes * 4.0 * n2 * n2 / (ms2 * 1e-3) / 1e9
+            rec = {"workload": name, "N": n2, "n_gpus": world, "rows_per_gpu": rws, "max_iter": cap, "steps": len(runs),
+                   "warmup": 1, "rounds": lastr.iter_count, "passes_per_step": lastr.passes,
+                   "ms_per_step": round(ms2, 4), "value": round(gbs, 3), "unit": "GB/s",
+                   "us_per_round": round(statistics.median(i.round_us_median for i in runs), 3),
+                   "phase_us": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in ph.items()},
+                   "eigen_val": float(lastr.eigen_val), "kernel": f"{lastr.kernel_name} id {lastr.kernel_id}",
+                   "clocks": ck.summary()}
+            if rank == 0:
+                peak2, _ = measured_peak()
+                rec["frac"] = round(gbs / (peak2 * world), 4)
+                rec["parity"] = parity_record(name, cap, lastr.eigen_val, lastr.iter_count, v2.download(np.float32, n2))
+                north_star.append(rec)
+            d2.free()
+            v2.free()
+            if sh2 is not None:
+                barrier()
+                sh2.close()
 
     # ---- CPU baseline beside it (rank 0, N=1) ----
     cpu = None
@@ -513,8 +660,11 @@ def main():
                          "kernel": f"{last.kernel_name} id {last.kernel_id}, {last.threads} threads x {last.grid} CTAs "
                                    "(one launch = one whole solve)",
                          "bytes_per_launch": int(last.passes * elem_bytes * dim * dim)},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": launches, "clocks": clk,
+            "parity": parity, "host_cpus_near_gpu": (len(near_cpus) if near_cpus else None),
         }
+        if north_star is not None:
+            line["north_star"] = north_star
         if table is not None:
             line["hilbert_sweep"] = table
         if scale_base is not None:
@@ -522,8 +672,20 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        sh.close()
+        if sh is not None:
+            sh.close()
         dist.destroy_process_group()
+    # a result whose bits differ from the CPU-computed expectation is not a result: say so with the exit code
+    bad = []
+    if rank == 0:
+        if parity and parity.get("bits_equal") is False:
+            bad.append(workload)
+        for rec in north_star or []:
+            if rec["parity"].get("bits_equal") is False:
+                bad.append(rec["workload"])
+    if bad:
+        sys.stderr.write("PARITY MISMATCH against the CPU-computed expected bits: " + ", ".join(bad) + "\n")
+        return 3
     return 0
 
 

@@ -493,9 +493,10 @@ st_memcpy_h2d(void* ctx, void* dptr, const void* hptr, size_t bytes)
 {
   return guarded([&] {
     Context* c = as_ctx(ctx);
-    c->activate();
-    ABI_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream()));
-    ABI_CUDA(cudaStreamSynchronize(c->stream()));
+    if (!dptr || !hptr)
+      throw std::invalid_argument("st_memcpy_h2d: null pointer");
+    std::lock_guard<std::mutex> lock(c->mutex());
+    c->upload(dptr, hptr, bytes); // pageable sources: multi-threaded staging, like max_eigen_value's own copy
     return ST_OK;
   });
 }

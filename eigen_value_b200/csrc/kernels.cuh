@@ -104,9 +104,7 @@ struct RoundParams
   BarrierState* bar;
   float* partial;         // resident-e kernel: chunk sums of multi-unit rows, rows x units
   unsigned int* row_done; // resident-e kernel: per-row arrival counters (monotonic)
-  uint32_t endgame;         // resident-e kernel: the last `endgame` dynamic units of a round are handed out as 8 shares each
-  float* share_buf;         //   per end-game unit: 8 accumulators x 32 lanes of partial sums
-  unsigned int* share_done; //   per end-game unit: arrival counter (monotonic, + 8 per round)
+  uint32_t endgame;       // resident-e kernel: end-game units per CTA and round (taken apart in 8 shares each); 0 = none
   unsigned long long timeout_ns;
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;

@@ -89,7 +89,7 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
 // results exactly like one warp would have: splitting a unit this way cannot change a bit.  Used for the last
 // units of a round, so that the end-of-round straggle is an eighth of a unit instead of a whole one.
 constexpr uint32_t kShares = (uint32_t)kUnroll;
-constexpr uint32_t kEndgameMaxUnits = 2048; // scratch is reserved for this many end-game units (>= TW / 2 up to 256 SMs)
+constexpr uint32_t kEndgameMaxPerCta = 8; // end-game units a CTA owns per round (1 KB of shared memory each)
 
 __device__ __forceinline__ float
 share_dot(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane, uint32_t acc_idx)
@@ -158,13 +158,20 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // small, L2-resident matrices the one-address atomic stream costs more than the skew it removes)
   const uint32_t D = (p.dynamic && U > TW) ? U - TW : 0u; // dynamically scheduled units per round
   constexpr uint32_t kChunkVec = kChunkCols / 4;
-  // End game: the LAST E dynamically scheduled units of a round are handed out as 8 shares each (one accumulator
-  // per grab, share_dot), so the warps that finish early fill the gaps the last whole units leave, and the round
-  // ends within an eighth of a unit's time.  fp32 storage and accumulation only; E == 0 switches it off.
+  // End game: the LAST units of a round are not handed out whole.  Every CTA owns `epc` of them (p.endgame, at most
+  // kEndgameMaxPerCta) and its warps, as they run out of whole units, take them apart in shares (one accumulator each,
+  // share_dot) through a counter in shared memory; the per-lane results meet in shared memory too, and the warp whose
+  // share completes a unit folds them.  When the whole units run out every warp is on average half way through one:
+  // half a warp-population's worth of eighth-size work is what fills those gaps, and the round then ends within an
+  // eighth of a unit's time instead of a whole one.  No global traffic besides the loads.  fp32 storage and
+  // accumulation only; p.endgame == 0 switches it off.
   constexpr bool kCanShare = sizeof(ACC) == 4 && !kBf16;
-  const uint32_t E = kCanShare ? min(p.endgame, D) : 0u;
-  const uint32_t D1 = D - E;            // whole units handed out dynamically
-  const uint32_t G = D1 + kShares * E;  // successful grabs per round
+  const uint32_t epc = (kCanShare && D > 0u) ? min(min(p.endgame, kEndgameMaxPerCta), D / gridDim.x) : 0u;
+  const uint32_t E = epc * gridDim.x;   // end-game units per round
+  const uint32_t D1 = D - E;            // whole units handed out dynamically (successful grabs per round)
+  __shared__ unsigned int eg_next;                            // next share of this CTA's end-game units (reset every round)
+  __shared__ unsigned int eg_done[kEndgameMaxPerCta];         // shares of a unit that have been delivered
+  __shared__ float eg_acc[kEndgameMaxPerCta][kShares][32];    // their per-lane results
 
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
@@ -172,6 +179,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     mbar_init(my_bar, 1u);
   if (tid == 0)
     s_cta_max = 0u;
+  if (tid <= kEndgameMaxPerCta) {
+    if (tid == 0)
+      eg_next = 0u;
+    else
+      eg_done[tid - 1u] = 0u;
+  }
   for (uint32_t c = tid; c < N; c += THREADS)
     e_s[c] = 1.f; // initialise_eigen_vector, reference :267-284
   fence_mbarrier_init();
@@ -237,54 +250,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
       };
       // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
-      // so round k hands out the values [k * (G + TW), k * (G + TW) + G)
-      const uint32_t base = k * (G + TW);
+      // so round k hands out the values [k * (D1 + TW), k * (D1 + TW) + D1)
+      const uint32_t base = k * (D1 + TW);
       uint32_t cur = gw;
       bool have = cur < U;
       bool first_unit = true;
-      bool is_share = false;
-      uint32_t share_acc = 0;
-      // what the previous work item left to be settled one item later, when the atomic that decides it has long
-      // returned: 1 = a row's arrival counter (lane 0), 2 = a share's arrival counter (the whole warp folds)
-      enum { kPendNone = 0, kPendRow = 1, kPendShare = 2 };
-      int pend_kind = kPendNone;          // warp-uniform
-      uint32_t pend_unit = 0;             // row (kPendRow) or dynamic unit index (kPendShare), warp-uniform
-      uint32_t grabbed = 0, pend_old = 0; // lane 0
-      auto settle = [&]() {
-        if (pend_kind == kPendRow) {
-          if (lane == 0)
-            finish_row(pend_unit, pend_old);
-        } else if (pend_kind == kPendShare) {
-          const uint32_t old = __shfl_sync(0xffffffffu, pend_old, 0);
-          if (old % kShares == kShares - 1u) { // this warp's share completed the unit: fold the eight chains
-            __threadfence();
-            const uint32_t slot = pend_unit - (TW + D1);
-            const float* sb = p.share_buf + (size_t)slot * (kShares * 32u) + (uint32_t)lane;
-            float acc[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; u++)
-              acc[u] = ld_cg(sb + 32 * u);
-#pragma unroll
-            for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
-#pragma unroll
-              for (int u = 0; u < s2; u++)
-                acc[u] += acc[u + s2];
-            const float t = warp_sum(acc[0]);
-            if (lane == 0) {
-              const uint32_t u = backward ? (U - 1u - pend_unit) : pend_unit;
-              const uint32_t rl = u / nch;
-              if (nch == 1u) {
-                publish(rl, t);
-              } else { // rare (one share in eight): the row's counter is waited for on the spot
-                __stcg(p.partial + (size_t)rl * nch + (u - rl * nch), t);
-                __threadfence();
-                finish_row(rl, atomicAdd(p.row_done + rl, 1u));
-              }
-            }
-          }
-        }
-        pend_kind = kPendNone;
-      };
+      uint32_t grabbed = 0, pend_row = 0, pend_old = 0;
+      bool pending = false;
       if (p.dynamic && lane == 0)
         grabbed = atomicAdd(&p.bar->row_counter, 1u); // one grab always in flight
       for (;;) {
@@ -294,66 +266,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          if (kCanShare && is_share) {
-            const float acc = share_dot(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, share_acc);
-            settle();
-            const uint32_t slot = cur - (TW + D1);
-            __stcg(p.share_buf + (size_t)slot * (kShares * 32u) + share_acc * 32u + (uint32_t)lane, acc);
-            __syncwarp();
-            if (lane == 0) {
-              __threadfence();
-              pend_old = atomicAdd(p.share_done + slot, 1u); // monotonic: + 8 per round
-            }
-            pend_kind = kPendShare;
-            pend_unit = cur;
+          uint32_t npre = 0;
+          if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
+            tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
+            pf_consumed++;
+            npre = min(kPfFloats >> 2, seg_nv);
+          } else if (resident && first_unit) {
+            npre = seg_nv; // landed before round 0 and never evicted
+          }
+          float t;
+          if (kBf16) {
+            // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
+            const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
+                                 ch * (kChunkVec >> 1);
+            t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
           } else {
-            uint32_t npre = 0;
-            if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
-              tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
-              pf_consumed++;
-              npre = min(kPfFloats >> 2, seg_nv);
-            } else if (resident && first_unit) {
-              npre = seg_nv; // landed before round 0 and never evicted
-            }
-            float t;
-            if (kBf16) {
-              // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
-              const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
-                                   ch * (kChunkVec >> 1);
-              t = row_dot_bf16<LD>(seg16, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 1, lane);
-            } else {
-              t = chunk_dot_prefetched<LD, ACC>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
-                                                reinterpret_cast<const float4*>(my_pf), npre);
-            }
-            settle(); // the atomic issued one item ago has long returned
+            t = chunk_dot_prefetched<LD, ACC>(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane,
+                                              reinterpret_cast<const float4*>(my_pf), npre);
+          }
+          if (lane == 0) {
+            if (pending)
+              finish_row(pend_row, pend_old); // the atomic issued one unit ago has long returned
+            pending = false;
             if (nch == 1u) {
-              if (lane == 0)
-                publish(rl, t);
+              publish(rl, t);
             } else {
-              if (lane == 0) {
-                __stcg(p.partial + (size_t)rl * nch + ch, t);
-                __threadfence();
-                pend_old = atomicAdd(p.row_done + rl, 1u);
-              }
-              pend_kind = kPendRow;
-              pend_unit = rl;
+              __stcg(p.partial + (size_t)rl * nch + ch, t);
+              __threadfence();
+              pend_old = atomicAdd(p.row_done + rl, 1u);
+              pend_row = rl;
+              pending = true;
             }
           }
         }
         first_unit = false;
         if (p.dynamic) {
           const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
-          if (d >= G)
+          if (d >= D1)
             break;
-          if (d < D1) {
-            cur = TW + d;
-            is_share = false;
-          } else {
-            const uint32_t sh = d - D1;
-            cur = TW + D1 + sh / kShares;
-            share_acc = sh % kShares;
-            is_share = true;
-          }
+          cur = TW + d;
           if (lane == 0)
             grabbed = atomicAdd(&p.bar->row_counter, 1u);
         } else {
@@ -363,7 +314,59 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
         have = true;
       }
-      settle();
+      if (lane == 0 && pending)
+        finish_row(pend_row, pend_old);
+
+      // ---- end game: this CTA's own last units, taken apart in shares through shared memory ----
+      if (kCanShare && epc > 0u) {
+        const uint32_t nshares = epc * kShares;
+        for (;;) {
+          uint32_t sh = 0;
+          if (lane == 0)
+            sh = atomicAdd(&eg_next, 1u);
+          sh = __shfl_sync(0xffffffffu, sh, 0);
+          if (sh >= nshares)
+            break;
+          const uint32_t i = sh / kShares;  // which of the CTA's end-game units
+          const uint32_t a = sh % kShares;  // which accumulator of it
+          const uint32_t unit = TW + D1 + blockIdx.x * epc + i;
+          const uint32_t u = backward ? (U - 1u - unit) : unit;
+          const uint32_t rl = u / nch;
+          const uint32_t ch = u - rl * nch;
+          const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
+          const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
+          eg_acc[i][a][lane] = share_dot(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, a);
+          __syncwarp();
+          uint32_t old = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            old = atomicAdd(&eg_done[i], 1u);
+          }
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old == kShares - 1u) { // this share completed the unit: fold the eight chains like one warp would have
+            __threadfence_block();
+            float acc[kUnroll];
+#pragma unroll
+            for (int q = 0; q < kUnroll; q++)
+              acc[q] = eg_acc[i][q][lane];
+#pragma unroll
+            for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
+#pragma unroll
+              for (int q = 0; q < s2; q++)
+                acc[q] += acc[q + s2];
+            const float t = warp_sum(acc[0]);
+            if (lane == 0) {
+              if (nch == 1u) {
+                publish(rl, t);
+              } else { // the row's arrival counter is waited for on the spot (one share in eight)
+                __stcg(p.partial + (size_t)rl * nch + ch, t);
+                __threadfence();
+                finish_row(rl, atomicAdd(p.row_done + rl, 1u));
+              }
+            }
+          }
+        }
+      }
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
     if (PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {
@@ -449,6 +452,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     }
     if (blockIdx.x == 0 && tid == 0)
       stamp_round_end(p, k);
+    if (tid <= kEndgameMaxPerCta) { // every warp left the end game before the round barrier: re-arm its pool
+      if (tid == 0)
+        eg_next = 0u;
+      else
+        eg_done[tid - 1u] = 0u;
+    }
     const bool converged = __syncthreads_and(ok) != 0; // also orders the e update before the next pass
 
     if (converged || k + 1u == p.max_iter) {

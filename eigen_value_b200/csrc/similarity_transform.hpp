@@ -77,6 +77,8 @@ public:
   void timer_start();
   float timer_stop();
 
+  // host -> device copy on the context's stream, synchronous; pageable sources take the multi-threaded staging path
+  void upload(void* d_dst, const void* h_src, size_t bytes);
   uint64_t staged_upload_bytes() const { return staged_bytes_; } // bytes that took the multi-threaded upload path
   std::mutex& mutex() { return mu_; }
   void activate() const; // cudaSetDevice
@@ -94,6 +96,8 @@ private:
   void reserve_matrix(size_t elems);
   void reserve_work(size_t elems);
   void copy_h2d(float* d_dst, const float* h_src, size_t bytes, CUstream_st* stream = nullptr);
+  void load_local_cpus();
+  void bind_this_thread_near_device() const;
 
   int device_ = 0;
   int sm_count_ = 0;
@@ -121,8 +125,9 @@ private:
   // streamed solve: copy stream and two events per cache slot (block landed / block consumed)
   CUstream_st* copy_stream_ = nullptr;
   std::vector<CUevent_st*> slot_ready_, slot_free_;
-  // opt-in multi-threaded upload of pageable host matrices (ST_UPLOAD_THREADS)
+  // multi-threaded staging of pageable host matrices (ST_UPLOAD_THREADS, default 4; 0 = the driver's own staging)
   int upload_threads_ = 0;
+  std::vector<int> local_cpus_; // CPUs on this GPU's NUMA node that the process may use (empty: unknown)
   uint64_t staged_bytes_ = 0;
   void* bounce_ = nullptr;
   std::vector<CUstream_st*> up_streams_;

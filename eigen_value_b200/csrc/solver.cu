@@ -13,6 +13,9 @@
 #include <stdexcept>
 #include <thread>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
@@ -114,9 +117,74 @@ Context::Context(int device)
   ST_CUDA(cudaMalloc(&d_bar_, sizeof(BarrierState)));
   ST_CUDA(cudaMalloc(&d_scalars_, 64));
   ST_CUDA(cudaHostAlloc(&h_pinned_, 64, cudaHostAllocDefault));
+  // Pageable host matrices (what the reference's wrapper passes: a numpy array) are staged by T host threads
+  // through pinned double buffers.  Measured on a B200 box, Hilbert 8192 through max_eigen_value
+  // (profiles/r2_c1_bench_upload.json): driver staging 24.6 ms, T = 2: 11.9, T = 4: 7.6, T = 8: 7.5, pinned 5.6.
+  // ST_UPLOAD_THREADS overrides (0 = leave pageable sources to the driver).
+  upload_threads_ = 4;
   if (const char* v = getenv("ST_UPLOAD_THREADS"))
     upload_threads_ = std::max(0, std::min(16, atoi(v)));
+  load_local_cpus();
   preload_kernels();
+}
+
+// CPUs next to this GPU (sysfs: local_cpulist of its PCI function), intersected with the CPUs this process may
+// use.  The staging threads of copy_h2d bind themselves to them, so that on a two-socket box the bounce buffers
+// and the memcpy into them stay on the GPU's own NUMA node.  Best effort: an empty set means "do not bind".
+void
+Context::load_local_cpus()
+{
+  local_cpus_.clear();
+  char bus[32] = {};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device_) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return;
+  }
+  for (char* c = bus; *c; ++c)
+    *c = (char)tolower((unsigned char)*c);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f)
+    return;
+  char line[1024] = {};
+  const bool ok = fgets(line, sizeof line, f) != nullptr;
+  fclose(f);
+  if (!ok)
+    return;
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0)
+    return;
+  for (const char* q = line; *q && *q != '\n';) { // "0-23,48-71"
+    char* end = nullptr;
+    const long a = strtol(q, &end, 10);
+    if (end == q)
+      break;
+    long b = a;
+    if (*end == '-') {
+      q = end + 1;
+      b = strtol(q, &end, 10);
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+      if (c >= 0 && CPU_ISSET((int)c, &allowed))
+        local_cpus_.push_back((int)c);
+    q = *end == ',' ? end + 1 : end;
+    if (*end != ',' )
+      break;
+  }
+}
+
+void
+Context::bind_this_thread_near_device() const
+{
+  if (local_cpus_.empty())
+    return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int c : local_cpus_)
+    CPU_SET(c, &set);
+  (void)pthread_setaffinity_np(pthread_self(), sizeof set, &set);
 }
 
 Context::~Context()
@@ -191,8 +259,6 @@ Context::scratch_need(uint32_t dim, uint32_t rows, const st_options& opt) const
   } else {
     if (units > 1)
       n.work = (size_t)rows * units + rows;
-    if (dim >= (uint32_t)kChunkCols) // end-game shares: 8 x 32 partial sums + one counter per end-game unit
-      n.work += (size_t)kEndgameMaxUnits * (kShares * 32u + 1u);
   }
   return n;
 }
@@ -602,25 +668,16 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
         p.mbar_offset = moff;
         p.chunk_cols = dim; // the whole eigenvector is resident
         const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
-        size_t off = 0; // layout of d_work_ (reserved by prepare()): chunk sums | row counters | share sums | share counters
         if (units > 1u) {
           // chunk sums + per-row arrival counters of rows that span several work units
           p.partial = d_work_;
           p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
           ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * rows, stream_));
-          off = (size_t)rows * units + rows;
         }
-        // End game: the last min(D, TW / 2) dynamically scheduled units of a round go out as 8 shares each.  When the
-        // whole units run out every warp is, on average, half way through one, so half a warp-population's worth of
-        // finer work is what fills the gaps until the last whole unit ends.  st_options.sweep bit 4 switches it off.
-        const uint64_t all_units = (uint64_t)rows * units;
-        const uint32_t tw = (uint32_t)g * (uint32_t)(t / 32);
-        if (p.dynamic && !(opt.sweep & 16) && !bf16 && !acc64 && dim >= (uint32_t)kChunkCols && all_units > tw) {
-          p.endgame = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(all_units - tw, tw / 2u), kEndgameMaxUnits);
-          p.share_buf = d_work_ + off;
-          p.share_done = reinterpret_cast<unsigned int*>(p.share_buf + (size_t)p.endgame * (kShares * 32u));
-          ST_CUDA(cudaMemsetAsync(p.share_done, 0, sizeof(unsigned int) * p.endgame, stream_));
-        }
+        // End game: every CTA owns up to 8 of the round's last units and takes them apart in shares (kernels_sc.cuh);
+        // with 16 warps per CTA that is half a warp-population's worth of work.  st_options.sweep bit 4 switches it off.
+        if (p.dynamic && !(opt.sweep & 16) && !bf16 && !acc64)
+          p.endgame = std::max(1u, (uint32_t)(t / 32) / 2u);
         break;
       }
     }
@@ -766,6 +823,14 @@ Context::upload_rows(const float* h_mat, uint32_t dim, const st_options& opt, Sh
 // their own pinned double buffers and feed the copy engine from there, so staging and DMA overlap and
 // the host-side memcpy is spread over T cores.
 void
+Context::upload(void* d_dst, const void* h_src, size_t bytes)
+{
+  activate();
+  copy_h2d(static_cast<float*>(d_dst), static_cast<const float*>(h_src), bytes);
+  ST_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void
 Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes, cudaStream_t stream)
 {
   if (!stream)
@@ -811,6 +876,8 @@ Context::copy_h2d(float* d_dst, const float* h_src, size_t bytes, cudaStream_t s
   char* dst = reinterpret_cast<char*>(d_dst);
   std::vector<cudaError_t> errs((size_t)T, cudaSuccess);
   auto work = [&](int t) {
+    if (t > 0)
+      bind_this_thread_near_device(); // worker threads only: the caller's own thread keeps its affinity
     cudaError_t e = cudaSetDevice(device_);
     cudaStream_t st = up_streams_[t];
     char* buf = static_cast<char*>(bounce_) + 2 * kChunk * (size_t)t;

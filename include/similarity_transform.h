@@ -164,11 +164,14 @@ int st_synchronize(void* ctx);
  * of the ~55 GB/s a pinned one reaches.  Pin once, solve many times, unpin before freeing the buffer. */
 int st_pin_host(void* ctx, void* hptr, size_t bytes);
 int st_unpin_host(void* ctx, void* hptr);
-/* Opt-in alternative for matrices the caller cannot pin: with ST_UPLOAD_THREADS=T in the environment when the
- * context is created (T = 1..16), pageable host matrices of 32 MiB and up are copied by T host threads through
- * pinned double buffers (4 MiB chunks) instead of through the driver's single staging path (max_eigen_value,
- * st_solve_host, and the block uploads of st_solve_streamed / st_solve_file, where the threads also spread the
- * page faults of a file mapping).  Pinned / registered sources keep the direct copy.  st_staged_upload_bytes reports how many bytes took that path on this context. */
+/* Matrices the caller cannot pin (the reference's wrapper passes a plain numpy array): pageable host matrices of
+ * 32 MiB and up are copied by T host threads through pinned double buffers (4 MiB chunks; the threads bind to the
+ * CPUs next to the GPU) instead of through the driver's single staging path -- in max_eigen_value, st_solve_host,
+ * st_memcpy_h2d and the block uploads of st_solve_streamed / st_solve_file, where the threads also spread the page
+ * faults of a file mapping.  T = 4 by default (measured, Hilbert 8192 end to end: driver staging 24.6 ms, T = 4
+ * 7.6 ms, pinned 5.6 ms); ST_UPLOAD_THREADS=T in the environment when the context is created overrides it (0..16;
+ * 0 = the driver's staging).  Pinned / registered sources keep the direct copy.  st_staged_upload_bytes reports how
+ * many bytes took the threaded path on this context. */
 uint64_t st_staged_upload_bytes(void* ctx);
 
 /* Input generation on the device, rows [row0, row0+rows) of the dim x dim matrix written

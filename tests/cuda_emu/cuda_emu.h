@@ -430,6 +430,7 @@ inline float4 __ldcg(const float4* p)
 inline void __stcg(float4* p, float4 v) { __stcg(&p->x, v.x); __stcg(&p->y, v.y); __stcg(&p->z, v.z); __stcg(&p->w, v.w); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, EMU_RELAXED); }
 inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, EMU_RELAXED); }

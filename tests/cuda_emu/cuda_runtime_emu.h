@@ -143,6 +143,7 @@ cudaGetDeviceProperties(cudaDeviceProp* p, int)
   return cudaSuccess;
 }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetPCIBusId(char* buf, int len, int) { if (len > 0) buf[0] = 0; return cudaErrorInvalidDevice; } // no PCI device: no CPU binding
 inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
 inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }

@@ -52,8 +52,6 @@ struct Rank
   std::vector<float> vecs;    // S0 S1 (world == 1), E0 E1, OUT
   std::vector<float> partial; // chunk sums
   std::vector<unsigned> row_done;
-  std::vector<float> share_buf;
-  std::vector<unsigned> share_done;
   std::vector<unsigned long long> ts;
   std::vector<unsigned char> work; // in-place working copy
   BarrierState* bar = nullptr;
@@ -212,16 +210,9 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.partial = r.partial.data();
           p.row_done = r.row_done.data();
         }
-        // end game (solver.cu): the last min(D, TW / 2) dynamic units as 8 shares each; o->sweep bit 4 switches it off
-        const uint64_t all_units = (uint64_t)rows * units;
-        const uint32_t tw = r.grid * warps;
-        if (p.dynamic && !(o->sweep & 16) && !bf16 && !acc64 && all_units > tw) {
-          p.endgame = (uint32_t)std::min<uint64_t>(all_units - tw, std::max(1u, tw / 2u));
-          r.share_buf.assign((size_t)p.endgame * kShares * 32u, -5.f);
-          r.share_done.assign(p.endgame, 0u);
-          p.share_buf = r.share_buf.data();
-          p.share_done = r.share_done.data();
-        }
+        // end game (solver.cu): every CTA takes up to warps / 2 of the round's last units apart in shares; o->sweep bit 4: off
+        if (p.dynamic && !(o->sweep & 16) && !bf16 && !acc64)
+          p.endgame = std::max(1u, warps / 2u);
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
       } else if (kid == 20) {
         if (!vec4 || form != kFormReadOnly || bf16 || world != 1 || dim > (uint32_t)kClusterCols)

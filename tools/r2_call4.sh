@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, call 4 (--gpus 2): end-game shares (the last units of a round handed out as 8 accumulator shares) on / off.
 set -u
-O=gpurun_out/r2c4; mkdir -p $O
+O=gpurun_out/r2c5; mkdir -p $O
 B="--no-cpu-baseline --no-sweep-table --no-e2e"
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_bitexact.py tests/test_gpu_sharded.py -m gpu -q -x > $O/pytest.txt 2>&1
 tail -3 $O/pytest.txt
