@@ -91,20 +91,26 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
 constexpr uint32_t kShares = (uint32_t)kUnroll;
 constexpr uint32_t kEndgameMaxPerCta = 8; // end-game units a CTA owns per round (1 KB of shared memory each)
 
-__device__ __forceinline__ float
-share_dot(const float4* __restrict__ a, const float4* es, uint32_t nv, int lane, uint32_t acc_idx)
+constexpr int kShareBatches = kChunkCols / 4 / (32 * kUnroll); // 8 batches of 256 vectors in a full unit
+
+__device__ __forceinline__ void
+share_load(float4 (&v)[kShareBatches], const float4* __restrict__ a, uint32_t nv, int lane, uint32_t acc_idx)
 {
-  constexpr int kBatches = kChunkCols / 4 / (32 * kUnroll); // 8 batches of 256 vectors in a full unit
-  float4 v[kBatches];
   const uint32_t j0 = (uint32_t)lane + 32u * acc_idx;
 #pragma unroll
-  for (int b = 0; b < kBatches; b++) {
+  for (int b = 0; b < kShareBatches; b++) {
     const uint32_t j = j0 + 256u * (uint32_t)b;
     v[b] = j < nv ? ld_stream(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+__device__ __forceinline__ float
+share_fma(const float4 (&v)[kShareBatches], const float4* es, uint32_t nv, int lane, uint32_t acc_idx)
+{
+  const uint32_t j0 = (uint32_t)lane + 32u * acc_idx;
   float acc = 0.f;
 #pragma unroll
-  for (int b = 0; b < kBatches; b++) {
+  for (int b = 0; b < kShareBatches; b++) {
     const uint32_t j = j0 + 256u * (uint32_t)b;
     if (j < nv)
       acc = dot_acc(v[b], es[j], acc);
@@ -169,9 +175,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   const uint32_t epc = (kCanShare && D > 0u) ? min(min(p.endgame, kEndgameMaxPerCta), D / gridDim.x) : 0u;
   const uint32_t E = epc * gridDim.x;   // end-game units per round
   const uint32_t D1 = D - E;            // whole units handed out dynamically (successful grabs per round)
-  __shared__ unsigned int eg_next;                            // next share of this CTA's end-game units (reset every round)
-  __shared__ unsigned int eg_done[kEndgameMaxPerCta];         // shares of a unit that have been delivered
-  __shared__ float eg_acc[kEndgameMaxPerCta][kShares][32];    // their per-lane results
+  __shared__ unsigned int eg_next;                    // next share of this CTA's end-game units (reset every round)
+  __shared__ unsigned int eg_done[kEndgameMaxPerCta]; // shares of a unit that have been delivered
+  float* eg_acc = reinterpret_cast<float*>(smem_raw + p.eg_offset); // their per-lane results: epc x 8 x 32 floats
 
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
@@ -318,15 +324,49 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         finish_row(pend_row, pend_old);
 
       // ---- end game: this CTA's own last units, taken apart in shares through shared memory ----
+      // Software-pipelined: the counter grab for the NEXT share is in flight while this one streams, and the arrival
+      // counter of the PREVIOUS share is looked at only after this one's loads have been issued.
       if (kCanShare && epc > 0u) {
         const uint32_t nshares = epc * kShares;
+        uint32_t next = 0, pend_i = 0, pend_u = 0, old = 0;
+        bool eg_pending = false;
+        if (lane == 0)
+          next = atomicAdd(&eg_next, 1u);
+        // the previous share of this warp may have completed its unit: fold the eight chains like one warp would have
+        auto settle = [&]() {
+          if (!eg_pending)
+            return;
+          eg_pending = false;
+          if (__shfl_sync(0xffffffffu, old, 0) != kShares - 1u)
+            return;
+          __threadfence_block();
+          float acc[kUnroll];
+#pragma unroll
+          for (int q = 0; q < kUnroll; q++)
+            acc[q] = eg_acc[(pend_i * kShares + (uint32_t)q) * 32u + (uint32_t)lane];
+#pragma unroll
+          for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
+#pragma unroll
+            for (int q = 0; q < s2; q++)
+              acc[q] += acc[q + s2];
+          const float t = warp_sum(acc[0]);
+          if (lane == 0) {
+            const uint32_t rl = pend_u / nch;
+            if (nch == 1u) {
+              publish(rl, t);
+            } else { // the row's arrival counter is waited for on the spot (one share in eight)
+              __stcg(p.partial + (size_t)rl * nch + (pend_u - rl * nch), t);
+              __threadfence();
+              finish_row(rl, atomicAdd(p.row_done + rl, 1u));
+            }
+          }
+        };
         for (;;) {
-          uint32_t sh = 0;
-          if (lane == 0)
-            sh = atomicAdd(&eg_next, 1u);
-          sh = __shfl_sync(0xffffffffu, sh, 0);
+          const uint32_t sh = __shfl_sync(0xffffffffu, next, 0);
           if (sh >= nshares)
             break;
+          if (lane == 0)
+            next = atomicAdd(&eg_next, 1u);
           const uint32_t i = sh / kShares;  // which of the CTA's end-game units
           const uint32_t a = sh % kShares;  // which accumulator of it
           const uint32_t unit = TW + D1 + blockIdx.x * epc + i;
@@ -335,37 +375,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t ch = u - rl * nch;
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          eg_acc[i][a][lane] = share_dot(seg, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, a);
+          float4 v[kShareBatches];
+          share_load(v, seg, seg_nv, lane, a);
+          settle();
+          eg_acc[(i * kShares + a) * 32u + (uint32_t)lane] =
+            share_fma(v, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, a);
           __syncwarp();
-          uint32_t old = 0;
           if (lane == 0) {
             __threadfence_block();
             old = atomicAdd(&eg_done[i], 1u);
           }
-          old = __shfl_sync(0xffffffffu, old, 0);
-          if (old == kShares - 1u) { // this share completed the unit: fold the eight chains like one warp would have
-            __threadfence_block();
-            float acc[kUnroll];
-#pragma unroll
-            for (int q = 0; q < kUnroll; q++)
-              acc[q] = eg_acc[i][q][lane];
-#pragma unroll
-            for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
-#pragma unroll
-              for (int q = 0; q < s2; q++)
-                acc[q] += acc[q + s2];
-            const float t = warp_sum(acc[0]);
-            if (lane == 0) {
-              if (nch == 1u) {
-                publish(rl, t);
-              } else { // the row's arrival counter is waited for on the spot (one share in eight)
-                __stcg(p.partial + (size_t)rl * nch + ch, t);
-                __threadfence();
-                finish_row(rl, atomicAdd(p.row_done + rl, 1u));
-              }
-            }
-          }
+          eg_pending = true;
+          pend_i = i;
+          pend_u = u;
         }
+        settle();
       }
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit

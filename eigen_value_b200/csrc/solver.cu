@@ -656,10 +656,25 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
-      uint32_t cap, moff = 0;
+      uint32_t cap, moff = 0, egoff = 0;
       shape(c.max_threads, false, &g, &t, &cap);
-      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, cap, &moff);
+      // End game: every CTA owns up to warps / 2 of the round's last units and takes them apart in shares whose results
+      // meet in shared memory (kernels_sc.cuh), 1 KB per unit -- as many as fit without crossing the carve-out step.
+      // st_options.sweep bit 4 switches it off; ST_ENDGAME=n in the environment overrides the count (tuning).
+      const bool dyn = (opt.sweep & 4) ? true : (opt.sweep & 2) ? false : dim >= (uint32_t)kChunkCols;
+      uint32_t epc = (dyn && !(opt.sweep & 16) && !bf16 && !acc64) ? std::max(1u, (uint32_t)(t / 32) / 2u) : 0u;
+      if (const char* v = getenv("ST_ENDGAME"))
+        epc = epc ? (uint32_t)std::max(0, std::min((int)kEndgameMaxPerCta, atoi(v))) : 0u;
+      epc = std::min(epc, kEndgameMaxPerCta);
+      while (epc > 0u && sc_smem_bytes(t, c.pf_batches, dim, epc, &moff) > kSmemCarveoutStep &&
+             sc_smem_bytes(t, c.pf_batches, dim, 0u, &moff) <= kSmemCarveoutStep)
+        epc--;
+      while (epc > 0u && sc_smem_bytes(t, c.pf_batches, dim, epc, &moff) > kSmemLimit)
+        epc--;
+      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, epc, &moff, &egoff);
       if (need <= kSmemLimit) {
+        p.endgame = epc;
+        p.eg_offset = egoff;
         sc = &c;
         grid = g;
         threads = t;
@@ -674,10 +689,6 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
           p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
           ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * rows, stream_));
         }
-        // End game: every CTA owns up to 8 of the round's last units and takes them apart in shares (kernels_sc.cuh);
-        // with 16 warps per CTA that is half a warp-population's worth of work.  st_options.sweep bit 4 switches it off.
-        if (p.dynamic && !(opt.sweep & 16) && !bf16 && !acc64)
-          p.endgame = std::max(1u, (uint32_t)(t / 32) / 2u);
         break;
       }
     }
