@@ -104,8 +104,6 @@ struct RoundParams
   BarrierState* bar;
   float* partial;         // resident-e kernel: chunk sums of multi-unit rows, rows x units
   unsigned int* row_done; // resident-e kernel: per-row arrival counters (monotonic)
-  uint32_t endgame;       // resident-e kernel: end-game units per CTA and round (taken apart in 8 shares each); 0 = none
-  uint32_t eg_offset;     //   byte offset in dynamic shared memory of their per-lane results (endgame x 8 x 32 floats)
   unsigned long long timeout_ns;
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;

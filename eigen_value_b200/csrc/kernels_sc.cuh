@@ -82,42 +82,6 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return (float)warp_sum(acc[0]);
 }
 
-// One SHARE of a work unit = one of its kUnroll accumulators: the vectors j with (j / 32) % 8 == a, i.e.
-// j = lane + 32 a + 256 b for b = 0, 1, ... -- eight 512-byte pieces of the 32 KB unit, all eight loads in flight
-// at once.  The accumulators of a unit are independent FMA chains (chunk_dot_prefetched folds them only at the
-// end), so eight warps can each run one chain in its own order of b and a ninth step folds the eight per-lane
-// results exactly like one warp would have: splitting a unit this way cannot change a bit.  Used for the last
-// units of a round, so that the end-of-round straggle is an eighth of a unit instead of a whole one.
-constexpr uint32_t kShares = (uint32_t)kUnroll;
-constexpr uint32_t kEndgameMaxPerCta = 8; // end-game units a CTA owns per round (1 KB of shared memory each)
-
-constexpr int kShareBatches = kChunkCols / 4 / (32 * kUnroll); // 8 batches of 256 vectors in a full unit
-
-__device__ __forceinline__ void
-share_load(float4 (&v)[kShareBatches], const float4* __restrict__ a, uint32_t nv, int lane, uint32_t acc_idx)
-{
-  const uint32_t j0 = (uint32_t)lane + 32u * acc_idx;
-#pragma unroll
-  for (int b = 0; b < kShareBatches; b++) {
-    const uint32_t j = j0 + 256u * (uint32_t)b;
-    v[b] = j < nv ? ld_stream(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-__device__ __forceinline__ float
-share_fma(const float4 (&v)[kShareBatches], const float4* es, uint32_t nv, int lane, uint32_t acc_idx)
-{
-  const uint32_t j0 = (uint32_t)lane + 32u * acc_idx;
-  float acc = 0.f;
-#pragma unroll
-  for (int b = 0; b < kShareBatches; b++) {
-    const uint32_t j = j0 + 256u * (uint32_t)b;
-    if (j < nv)
-      acc = dot_acc(v[b], es[j], acc);
-  }
-  return acc;
-}
-
 template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
@@ -164,33 +128,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // small, L2-resident matrices the one-address atomic stream costs more than the skew it removes)
   const uint32_t D = (p.dynamic && U > TW) ? U - TW : 0u; // dynamically scheduled units per round
   constexpr uint32_t kChunkVec = kChunkCols / 4;
-  // End game: the LAST units of a round are not handed out whole.  Every CTA owns `epc` of them (p.endgame, at most
-  // kEndgameMaxPerCta) and its warps, as they run out of whole units, take them apart in shares (one accumulator each,
-  // share_dot) through a counter in shared memory; the per-lane results meet in shared memory too, and the warp whose
-  // share completes a unit folds them.  When the whole units run out every warp is on average half way through one:
-  // half a warp-population's worth of eighth-size work is what fills those gaps, and the round then ends within an
-  // eighth of a unit's time instead of a whole one.  No global traffic besides the loads.  fp32 storage and
-  // accumulation only; p.endgame == 0 switches it off.
-  constexpr bool kCanShare = sizeof(ACC) == 4 && !kBf16;
-  const uint32_t epc = (kCanShare && D > 0u) ? min(min(p.endgame, kEndgameMaxPerCta), D / gridDim.x) : 0u;
-  const uint32_t E = epc * gridDim.x;   // end-game units per round
-  const uint32_t D1 = D - E;            // whole units handed out dynamically (successful grabs per round)
-  __shared__ unsigned int eg_next;                    // next share of this CTA's end-game units (reset every round)
-  __shared__ unsigned int eg_done[kEndgameMaxPerCta]; // shares of a unit that have been delivered
-  float* eg_acc = reinterpret_cast<float*>(smem_raw + p.eg_offset); // their per-lane results: epc x 8 x 32 floats
-
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
   uint64_t* my_bar = mbar_all + warp;
   if (PF_BATCHES > 0 && lane == 0)
     mbar_init(my_bar, 1u);
   if (tid == 0)
     s_cta_max = 0u;
-  if (tid <= kEndgameMaxPerCta) {
-    if (tid == 0)
-      eg_next = 0u;
-    else
-      eg_done[tid - 1u] = 0u;
-  }
   for (uint32_t c = tid; c < N; c += THREADS)
     e_s[c] = 1.f; // initialise_eigen_vector, reference :267-284
   fence_mbarrier_init();
@@ -256,8 +199,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         }
       };
       // the unit counter is monotonic too: every warp makes exactly one failing grab per round,
-      // so round k hands out the values [k * (D1 + TW), k * (D1 + TW) + D1)
-      const uint32_t base = k * (D1 + TW);
+      // so round k hands out the values [k * (D + TW), k * (D + TW) + D)
+      const uint32_t base = k * (D + TW);
       uint32_t cur = gw;
       bool have = cur < U;
       bool first_unit = true;
@@ -308,7 +251,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         first_unit = false;
         if (p.dynamic) {
           const uint32_t d = __shfl_sync(0xffffffffu, grabbed, 0) - base;
-          if (d >= D1)
+          if (d >= D)
             break;
           cur = TW + d;
           if (lane == 0)
@@ -322,75 +265,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       }
       if (lane == 0 && pending)
         finish_row(pend_row, pend_old);
-
-      // ---- end game: this CTA's own last units, taken apart in shares through shared memory ----
-      // Software-pipelined: the counter grab for the NEXT share is in flight while this one streams, and the arrival
-      // counter of the PREVIOUS share is looked at only after this one's loads have been issued.
-      if (kCanShare && epc > 0u) {
-        const uint32_t nshares = epc * kShares;
-        uint32_t next = 0, pend_i = 0, pend_u = 0, old = 0;
-        bool eg_pending = false;
-        if (lane == 0)
-          next = atomicAdd(&eg_next, 1u);
-        // the previous share of this warp may have completed its unit: fold the eight chains like one warp would have
-        auto settle = [&]() {
-          if (!eg_pending)
-            return;
-          eg_pending = false;
-          if (__shfl_sync(0xffffffffu, old, 0) != kShares - 1u)
-            return;
-          __threadfence_block();
-          float acc[kUnroll];
-#pragma unroll
-          for (int q = 0; q < kUnroll; q++)
-            acc[q] = eg_acc[(pend_i * kShares + (uint32_t)q) * 32u + (uint32_t)lane];
-#pragma unroll
-          for (int s2 = kUnroll / 2; s2 >= 1; s2 >>= 1)
-#pragma unroll
-            for (int q = 0; q < s2; q++)
-              acc[q] += acc[q + s2];
-          const float t = warp_sum(acc[0]);
-          if (lane == 0) {
-            const uint32_t rl = pend_u / nch;
-            if (nch == 1u) {
-              publish(rl, t);
-            } else { // the row's arrival counter is waited for on the spot (one share in eight)
-              __stcg(p.partial + (size_t)rl * nch + (pend_u - rl * nch), t);
-              __threadfence();
-              finish_row(rl, atomicAdd(p.row_done + rl, 1u));
-            }
-          }
-        };
-        for (;;) {
-          const uint32_t sh = __shfl_sync(0xffffffffu, next, 0);
-          if (sh >= nshares)
-            break;
-          if (lane == 0)
-            next = atomicAdd(&eg_next, 1u);
-          const uint32_t i = sh / kShares;  // which of the CTA's end-game units
-          const uint32_t a = sh % kShares;  // which accumulator of it
-          const uint32_t unit = TW + D1 + blockIdx.x * epc + i;
-          const uint32_t u = backward ? (U - 1u - unit) : unit;
-          const uint32_t rl = u / nch;
-          const uint32_t ch = u - rl * nch;
-          const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
-          const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
-          float4 v[kShareBatches];
-          share_load(v, seg, seg_nv, lane, a);
-          settle();
-          eg_acc[(i * kShares + a) * 32u + (uint32_t)lane] =
-            share_fma(v, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv, lane, a);
-          __syncwarp();
-          if (lane == 0) {
-            __threadfence_block();
-            old = atomicAdd(&eg_done[i], 1u);
-          }
-          eg_pending = true;
-          pend_i = i;
-          pend_u = u;
-        }
-        settle();
-      }
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
     if (PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {
@@ -476,12 +350,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     }
     if (blockIdx.x == 0 && tid == 0)
       stamp_round_end(p, k);
-    if (tid <= kEndgameMaxPerCta) { // every warp left the end game before the round barrier: re-arm its pool
-      if (tid == 0)
-        eg_next = 0u;
-      else
-        eg_done[tid - 1u] = 0u;
-    }
     const bool converged = __syncthreads_and(ok) != 0; // also orders the e update before the next pass
 
     if (converged || k + 1u == p.max_iter) {

@@ -60,26 +60,21 @@ is_known_kernel_id(int id)
   return id == 0 || id == kGeneralKernelId || is_sc_kernel_id(id) || id == kClusterKernelIdPlan;
 }
 
-// dynamic shared memory of the resident-e kernel: prefetch slots | e | mbarriers | end-game results (1 KB per unit)
+// dynamic shared memory of the resident-e kernel: prefetch slots | e | mbarriers
 inline size_t
-sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t endgame_units, uint32_t* mbar_offset,
-              uint32_t* eg_offset = nullptr)
+sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t* mbar_offset)
 {
   size_t off = (size_t)(threads / 32) * pf_batches * 1024 * sizeof(float);
   off += (size_t)cols * sizeof(float);
   off = (off + 15) & ~(size_t)15;
   *mbar_offset = (uint32_t)off;
-  off += (size_t)(threads / 32) * sizeof(uint64_t);
-  off = (off + 127) & ~(size_t)127;
-  if (eg_offset)
-    *eg_offset = (uint32_t)off;
-  return off + (size_t)endgame_units * 8 * 32 * sizeof(float);
+  return off + (size_t)(threads / 32) * sizeof(uint64_t);
 }
-// The shared-memory carve-out of an SM comes in steps (..., 164, 196, 228 KB) and what is left of the 256 KB is L1,
-// which the streaming loads pass through: a CTA that needs 197 KB leaves 28 KB of L1 instead of 60 KB, and Hilbert
-// 32768 (64 KB of slots + 128 KB of e) lost 15 % when 8 KB of end-game results pushed it over
-// (profiles/r2_c5_endgame_n1.json).  Optional shared memory is therefore sized to stay under this line.
-constexpr size_t kSmemCarveoutStep = 196 * 1024 - 256; // minus the kernel's static shared memory
+// The shared-memory carve-out of an SM comes in steps (..., 164, 196, 228 KB; a CTA can use the step minus 1 KB) and
+// what is left of the 256 KB is L1, which the streaming loads pass through.  Measured in round 2
+// (profiles/r2_c5_endgame_v2_n1.json, r2_c6_endgame_v3_n1.json): Hilbert 32768 -- 64 KB of slots + 128 KB of e --
+// runs a round in 587 us with up to 198.8 KB of shared memory per CTA and in 676 us with 199.8 KB.  Anything
+// optional in shared memory has to stay under 195 KB.
 
 // Cluster size (1, 2, 4, 8 CTAs): the largest that still leaves every CTA >= 16 rows (one per
 // warp) -- the loop is latency-bound, so more SMs means shorter per-warp row chains -- and never

@@ -656,25 +656,10 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
       int g, t;
-      uint32_t cap, moff = 0, egoff = 0;
+      uint32_t cap, moff = 0;
       shape(c.max_threads, false, &g, &t, &cap);
-      // End game: every CTA owns up to warps / 2 of the round's last units and takes them apart in shares whose results
-      // meet in shared memory (kernels_sc.cuh), 1 KB per unit -- as many as fit without crossing the carve-out step.
-      // st_options.sweep bit 4 switches it off; ST_ENDGAME=n in the environment overrides the count (tuning).
-      const bool dyn = (opt.sweep & 4) ? true : (opt.sweep & 2) ? false : dim >= (uint32_t)kChunkCols;
-      uint32_t epc = (dyn && !(opt.sweep & 16) && !bf16 && !acc64) ? std::max(1u, (uint32_t)(t / 32) / 2u) : 0u;
-      if (const char* v = getenv("ST_ENDGAME"))
-        epc = epc ? (uint32_t)std::max(0, std::min((int)kEndgameMaxPerCta, atoi(v))) : 0u;
-      epc = std::min(epc, kEndgameMaxPerCta);
-      while (epc > 0u && sc_smem_bytes(t, c.pf_batches, dim, epc, &moff) > kSmemCarveoutStep &&
-             sc_smem_bytes(t, c.pf_batches, dim, 0u, &moff) <= kSmemCarveoutStep)
-        epc--;
-      while (epc > 0u && sc_smem_bytes(t, c.pf_batches, dim, epc, &moff) > kSmemLimit)
-        epc--;
-      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, epc, &moff, &egoff);
+      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, &moff);
       if (need <= kSmemLimit) {
-        p.endgame = epc;
-        p.eg_offset = egoff;
         sc = &c;
         grid = g;
         threads = t;

@@ -107,8 +107,7 @@ typedef struct st_options
   int32_t sweep;     /* bit 0: alternate the row order every round so the tail of one pass is
                         the L2-resident head of the next (default on); bit 1 / bit 2: force
                         static / dynamic work-unit scheduling in the unit-scheduled kernels; bit 3:
-                        no in-kernel time stamps; bit 4: no end game (the last units of a round are
-                        normally handed out as eight shares each, csrc/kernels_sc.cuh)          */
+                        no in-kernel time stamps                                                 */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
   int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, one GPU), resident-e

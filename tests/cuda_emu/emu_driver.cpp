@@ -197,19 +197,12 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           throw std::string("bf16 storage is built for configuration 11");
         r.grid = std::max(1u, std::min(want, (rows + warps - 1) / warps));
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
-        // end game (solver.cu): every CTA takes up to warps / 2 of the round's last units apart in shares; o->sweep bit 4: off
-        const bool dyn = o->dynamic < 0 ? dim >= (uint32_t)kChunkCols : o->dynamic != 0;
-        uint32_t epc = (dyn && !(o->sweep & 16) && !bf16 && !acc64) ? std::min(std::max(1u, warps / 2u), kEndgameMaxPerCta) : 0u;
-        uint32_t moff = 0, egoff = 0;
+        uint32_t moff = 0;
         (void)cap;
-        while (epc > 0u && sc_smem_bytes((int)r.threads, pf, dim, epc, &moff) > kSmemLimit)
-          epc--;
-        r.smem = sc_smem_bytes((int)r.threads, pf, dim, epc, &moff, &egoff);
+        r.smem = sc_smem_bytes((int)r.threads, pf, dim, &moff);
         if (r.smem > kSmemLimit)
           throw std::string("resident-e configuration does not fit shared memory");
         p.mbar_offset = moff;
-        p.endgame = epc;
-        p.eg_offset = egoff;
         p.chunk_cols = dim;
         const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
         if (units > 1u) {

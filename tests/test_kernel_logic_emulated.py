@@ -221,21 +221,3 @@ def test_fp64_accumulation_rows_of_several_units_and_sharded():
     mat = U(1000)
     same_bits(emu.solve(mat, 1000, kernel=13, threads=64, ctas=2, world=3, acc64=True), expect(mat, sum_mode=oracle.SUM_CUDA_F64))
 
-
-# ---- end game: the last dynamic units of a round are handed out as 8 shares (one accumulator each) ----------
-@pytest.mark.parametrize("dim,threads,ctas,world,sweep", [(520, 128, 8, 1, 1), (520, 128, 8, 1, 0), (1000, 64, 3, 1, 1),
-                                                          (1000, 64, 2, 3, 1), (96, 64, 2, 1, 1), (36, 32, 1, 1, 1)])
-def test_end_game_shares_do_not_change_a_bit(dim, threads, ctas, world, sweep):
-    # TW = ctas * threads / 32 warps per emulated GPU; E = min(D, TW / 2) units are split, so with 520 rows on 32
-    # warps 16 units (128 shares) end every round; sweep bit 4 (16) switches the end game off: same bits either way
-    mat = U(dim)
-    want = expect(mat)
-    same_bits(emu.solve(mat, dim, kernel=13, threads=threads, ctas=ctas, world=world, dynamic=1, sweep=sweep), want)
-    same_bits(emu.solve(mat, dim, kernel=13, threads=threads, ctas=ctas, world=world, dynamic=1, sweep=sweep | 16), want)
-
-
-def test_end_game_shares_with_rows_of_two_units_and_a_short_last_chunk():
-    # N = 8200: every row is an 8192-column unit plus an 8-column one; shares of the short unit are mostly empty
-    mat = U(8200)
-    same_bits(emu.solve(mat, 8200, kernel=13, threads=128, ctas=6, dynamic=1, max_iter=3), expect(mat, max_iter=3))
-    same_bits(emu.solve(mat, 8200, kernel=10, threads=64, ctas=5, world=2, dynamic=1, max_iter=2), expect(mat, max_iter=2))
