@@ -39,7 +39,8 @@
 namespace st {
 
 constexpr int kMaxWorld = 8;      // ST_MAX_WORLD
-constexpr int kChunkCols = 8192;  // columns of the scale vector staged in shared memory at a time
+constexpr int kChunkCols = 8192;  // columns of one work unit: a row is reduced in chunks of this many columns, added left to right
+constexpr int kWindowCols = 32768; // general loop: columns of the scale vector staged in shared memory at a time (4 chunks)
 constexpr int kUnroll = 8;        // independent 128-bit loads in flight per lane
 
 enum : int
@@ -99,7 +100,7 @@ struct RoundParams
   int sweep;           // 1: alternate the row order every round (L2 reuse of the pass tail)
   int dynamic;         // resident-e kernel: hand out work units through an atomic counter
   uint32_t keep_rows_pct; // share of each CTA's rows loaded L2 evict_last (rest evict_first); 0: no hints
-  uint32_t chunk_cols; // columns staged per chunk (<= kChunkCols)
+  uint32_t chunk_cols; // columns of the scale vector staged at a time (general loop: <= kWindowCols, a multiple of kChunkCols or N)
   uint32_t mbar_offset; // TMA variant: byte offset of the mbarrier array in dynamic smem
   BarrierState* bar;
   float* partial;         // resident-e kernel: chunk sums of multi-unit rows, rows x units
@@ -652,29 +653,38 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
         }
       }
       __syncthreads();
+      // the staged window holds up to four 8192-column chunks: a warp streams its row through all of them (128 KB
+      // of one row in a piece) -- one chunk sum at a time, added left to right, exactly as if each chunk had been staged
+      // on its own; only the number of rebuilds and CTA-wide synchronisations per round drops (N / 32768 instead of N / 8192)
       for (uint32_t i = warp; i < nrows; i += kWarps) {
         const uint32_t rl = backward ? (nrows - 1u - i) : i;
-        const size_t off = (size_t)(rb + rl) * N + c0;
-        float t;
-        if (kBf16) {
-          const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
-          t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(scale_s), clen >> 3, lane);
-        } else if (FORM == kFormReadOnly) {
-          if (sizeof(ACC) == 8)
-            t = row_dot_readonly<VEC, false, ACC>(p.A + off, scale_s, clen, lane);
-          else if (p.keep_rows_pct == 0u)
-            t = row_dot_readonly<VEC>(p.A + off, scale_s, clen, lane);
-          else
-            t = row_dot_readonly<VEC, true>(p.A + off, scale_s, clen, lane,
-                                            rl * 100u < nrows * p.keep_rows_pct ? pol_keep : pol_stream);
-        } else if (first) {
-          t = row_pass_inplace<VEC, true>(p.A + off, p.W + off, scale_s, 1.f, clen, lane);
-        } else {
-          const float inv_r = 1.f / ld_cg(Sprev + p.row0 + rb + rl);
-          t = row_pass_inplace<VEC, false>(p.W + off, p.W + off, scale_s, inv_r, clen, lane);
+        float inv_r = 1.f;
+        if (FORM == kFormInPlace && !first)
+          inv_r = 1.f / ld_cg(Sprev + p.row0 + rb + rl);
+        for (uint32_t s0 = 0; s0 < clen; s0 += (uint32_t)kChunkCols) {
+          const uint32_t slen = min((uint32_t)kChunkCols, clen - s0);
+          const size_t off = (size_t)(rb + rl) * N + c0 + s0;
+          const float* sc = scale_s + s0;
+          float t;
+          if (kBf16) {
+            const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
+            t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 3, lane);
+          } else if (FORM == kFormReadOnly) {
+            if (sizeof(ACC) == 8)
+              t = row_dot_readonly<VEC, false, ACC>(p.A + off, sc, slen, lane);
+            else if (p.keep_rows_pct == 0u)
+              t = row_dot_readonly<VEC>(p.A + off, sc, slen, lane);
+            else
+              t = row_dot_readonly<VEC, true>(p.A + off, sc, slen, lane,
+                                              rl * 100u < nrows * p.keep_rows_pct ? pol_keep : pol_stream);
+          } else if (first) {
+            t = row_pass_inplace<VEC, true>(p.A + off, p.W + off, sc, 1.f, slen, lane);
+          } else {
+            t = row_pass_inplace<VEC, false>(p.W + off, p.W + off, sc, inv_r, slen, lane);
+          }
+          if (lane == 0)
+            part_s[rl] += t;
         }
-        if (lane == 0)
-          part_s[rl] += t;
       }
     }
     if (blockIdx.x == 0 && tid == 0)

@@ -566,7 +566,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   // once a unit is a full 32 KB chunk (N >= 8192), where the matrix no longer lives in L2
   p.dynamic = (opt.sweep & 4) ? 1 : (opt.sweep & 2) ? 0 : (dim >= (uint32_t)kChunkCols ? 1 : 0);
   p.keep_rows_pct = (uint32_t)std::max(0, std::min(100, opt.l2_keep_pct));
-  p.chunk_cols = std::min<uint32_t>((uint32_t)kChunkCols, dim);
+  p.chunk_cols = std::min<uint32_t>((uint32_t)kWindowCols, dim); // general loop: staged window of the scale vector
   p.bar = d_bar_;
   p.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
   p.rank = shard ? shard->rank : 0u;

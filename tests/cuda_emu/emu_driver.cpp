@@ -146,7 +146,9 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
       p.sweep = o->sweep & 1;
       p.dynamic = o->dynamic < 0 ? (dim >= (uint32_t)kChunkCols ? 1 : 0) : (o->dynamic ? 1 : 0);
       p.keep_rows_pct = 0;
-      p.chunk_cols = std::min<uint32_t>((uint32_t)kChunkCols, dim);
+      p.chunk_cols = std::min<uint32_t>((uint32_t)kWindowCols, dim);
+      if (const char* w = getenv("ST_EMU_WINDOW")) // tests: a smaller staged window, so that several windows per row fit an emulated size
+        p.chunk_cols = std::min<uint32_t>((uint32_t)std::max(kChunkCols, atoi(w) / kChunkCols * kChunkCols), dim);
       p.bar = r.bar;
       p.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
       p.rank = g;

@@ -221,3 +221,16 @@ def test_fp64_accumulation_rows_of_several_units_and_sharded():
     mat = U(1000)
     same_bits(emu.solve(mat, 1000, kernel=13, threads=64, ctas=2, world=3, acc64=True), expect(mat, sum_mode=oracle.SUM_CUDA_F64))
 
+
+
+def test_general_loop_with_several_staged_windows_per_row(monkeypatch):
+    # The general loop stages up to 32768 columns of the scale vector at a time and reduces a row in 8192-column chunks
+    # inside the window.  With the window shrunk to 8192 / 16384 columns a 16400-column row crosses three / two windows
+    # (the last one 16 columns wide): same chunk sums, same left-to-right order, same bits.
+    mat = U(16400)
+    want = expect(mat, max_iter=2)
+    for window in ("8192", "16384", "32768"):
+        monkeypatch.setenv("ST_EMU_WINDOW", window)
+        same_bits(emu.solve(mat, 16400, kernel=1, threads=128, ctas=5, max_iter=2), want)
+    monkeypatch.setenv("ST_EMU_WINDOW", "8192")
+    same_bits(emu.solve(mat, 16400, kernel=1, threads=64, ctas=3, world=2, form=1, max_iter=2), expect(mat, 1, max_iter=2))
