@@ -118,8 +118,12 @@ struct Group
 constexpr uint32_t kGroupDefaultMinDim = 8192;
 
 // a caller that looked its group up keeps it alive until its solve returns, whatever st_group_detach does meanwhile
-std::mutex g_groups_mu;
-std::map<Context*, std::shared_ptr<Group>> g_groups;
+// Heap-allocated and never freed on purpose: the reference's wrapper never destroys its queue, so with ST_DEVICES set a
+// namespace-scope map would tear its groups down during static destruction -- cudaFree / cudaIpcCloseMemHandle /
+// cudaStreamSynchronize while the CUDA runtime unloads, which is undefined.  Groups are released by st_group_detach /
+// st_destroy only; whatever is still attached at exit goes with the process.
+std::mutex& g_groups_mu = *new std::mutex;
+std::map<Context*, std::shared_ptr<Group>>& g_groups = *new std::map<Context*, std::shared_ptr<Group>>;
 
 std::shared_ptr<Group>
 group_of(Context* c)

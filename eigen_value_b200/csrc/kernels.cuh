@@ -197,6 +197,14 @@ struct Vec<1>
   using type = float;
 };
 
+// Independent loads a lane keeps in flight in the row reductions: 4 KB per warp either way.
+template<int VEC>
+__host__ __device__ constexpr int
+kLoadsInFlight()
+{
+  return VEC == 4 ? kUnroll : 4 * kUnroll;
+}
+
 __device__ __forceinline__ float
 dot_acc(float4 a, float4 e, float acc)
 {
@@ -328,25 +336,28 @@ row_dot_readonly(const float* __restrict__ row, const float* e_s, uint32_t len, 
   const V* __restrict__ a = reinterpret_cast<const V*>(row);
   const V* es = reinterpret_cast<const V*>(e_s);
   const uint32_t nv = len / VEC;
+  // loads in flight per lane: 8 x 16 bytes, or -- scalar units, dim % 4 != 0 -- 32 x 4 bytes: the same 4 KB per warp.
+  // Unit j still goes to accumulator (j / 32) % 8 = u % 8, in ascending j, so the count does not touch the order.
+  constexpr int LDN = kLoadsInFlight<VEC>();
   ACC acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
     acc[u] = ACC(0);
   uint32_t i = (uint32_t)lane;
-  for (; i + 32u * (kUnroll - 1) < nv; i += 32u * kUnroll) {
-    V v[kUnroll];
+  for (; i + 32u * (LDN - 1) < nv; i += 32u * LDN) {
+    V v[LDN];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++)
+    for (int u = 0; u < LDN; u++)
       v[u] = HINT ? ld_stream(a + i + 32u * u, pol) : ld_stream(a + i + 32u * u);
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-      acc[u] = dot_acc(v[u], es[i + 32u * u], acc[u]);
+    for (int u = 0; u < LDN; u++)
+      acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
   }
 #pragma unroll
-  for (int u = 0; u < kUnroll; u++) {
+  for (int u = 0; u < LDN; u++) {
     const uint32_t j = i + 32u * u;
     if (j < nv)
-      acc[u] = dot_acc(HINT ? ld_stream(a + j, pol) : ld_stream(a + j), es[j], acc[u]);
+      acc[u % kUnroll] = dot_acc(HINT ? ld_stream(a + j, pol) : ld_stream(a + j), es[j], acc[u % kUnroll]);
   }
 #pragma unroll
   for (int s = kUnroll / 2; s >= 1; s >>= 1)
@@ -398,33 +409,34 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
   V* w = reinterpret_cast<V*>(dst);
   const V* ss = reinterpret_cast<const V*>(sc_s);
   const uint32_t nv = len / VEC;
+  constexpr int LDN = kLoadsInFlight<VEC>();
   float acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
     acc[u] = 0.f;
   uint32_t i = (uint32_t)lane;
-  for (; i + 32u * (kUnroll - 1) < nv; i += 32u * kUnroll) {
-    V v[kUnroll];
+  for (; i + 32u * (LDN - 1) < nv; i += 32u * LDN) {
+    V v[LDN];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++)
+    for (int u = 0; u < LDN; u++)
       v[u] = FIRST ? ld_stream(a + i + 32u * u) : ld_cg(a + i + 32u * u);
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
+    for (int u = 0; u < LDN; u++) {
       if (!FIRST)
         v[u] = rescale(v[u], inv_r, ss[i + 32u * u]);
       __stcg(w + i + 32u * u, v[u]);
-      acc[u] = sum_acc(v[u], acc[u]);
+      acc[u % kUnroll] = sum_acc(v[u], acc[u % kUnroll]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < kUnroll; u++) {
+  for (int u = 0; u < LDN; u++) {
     const uint32_t j = i + 32u * u;
     if (j < nv) {
       V v = FIRST ? ld_stream(a + j) : ld_cg(a + j);
       if (!FIRST)
         v = rescale(v, inv_r, ss[j]);
       __stcg(w + j, v);
-      acc[u] = sum_acc(v, acc[u]);
+      acc[u % kUnroll] = sum_acc(v, acc[u % kUnroll]);
     }
   }
 #pragma unroll
