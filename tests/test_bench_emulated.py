@@ -32,6 +32,8 @@ def test_default_shape_of_the_line_with_e2e_sweep_table_and_cpu_baseline():
     assert line["config"]["stop"] == "absolute" and line["config"]["storage"] == "f32" and line["config"]["accumulate"] == "f32"
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert line["e2e"]["h2d_bytes_per_step"] == 4 * 256 * 256 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["e2e_pageable"]["h2d_bytes_per_step"] == 4 * 256 * 256 and "pageable" in line["e2e_pageable"]["api"]
+    assert line["parity"] == {"checked_against": None, "bits_equal": None} and "north_star" not in line   # no golden entry for 256
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert [r["rounds"] for r in line["hilbert_sweep"]] == [9, 10, 12, 13, 14, 15, 17]      # reference README.md:70-76
     assert line["strong_scaling_base"]["workload"] == "hilbert-512" and line["strong_scaling_base"]["rounds"] == 12
@@ -48,6 +50,23 @@ def test_opt_in_switches(extra, rounds):
     if "--storage" in extra:
         assert line["e2e"] is None and line["roofline"]["bytes_per_launch"] == line["passes_per_step"] * 2 * 1024 * 1024
         assert "bf16 storage" in line["metric"]
+
+
+def test_parity_verdict_against_the_cpu_computed_expected_bits():
+    # hilbert-16384 is in tests/golden/generated_expected.json but far too slow here; the verdict logic itself:
+    sys.path.insert(0, ROOT)
+    import bench
+    e, src = bench.expected_result("hilbert-131072", 1000)
+    assert src == "tests/golden/generated_expected.json" and e["iter_count"] == 23
+    assert bench.expected_result("uniform-131072", 1000) == (None, None)          # computed for a 50-round cap only
+    assert bench.expected_result("uniform-131072", 50)[0]["iter_count"] == 50
+    assert bench.expected_result("uniform-65536", 1000)[1] == "tests/golden/gpu_recorded.json"
+    assert bench.expected_result("hilbert-32768", 10) == (None, None)             # a cap below the 20 rounds it takes
+    ok = bench.parity_record("hilbert-131072", 1000, e["eigen_val"], 23)
+    assert ok["bits_equal"] is True and ok["checked_against"].endswith("generated_expected.json")
+    assert bench.parity_record("hilbert-131072", 1000, e["eigen_val"], 22)["bits_equal"] is False
+    assert bench.parity_record("hilbert-131072", 1000, 2.7381439, 23)["bits_equal"] is False
+    assert bench.parity_record("hilbert-777", 1000, 1.0, 3) == {"checked_against": None, "bits_equal": None}
 
 
 def test_streamed_bench_tool_on_the_emulated_library():

