@@ -444,6 +444,13 @@ def main():
                 step()
             barrier()
     clk = clocks.summary()
+    # every rank's view of the last timed solve (CTA 0 of each GPU): shows whether the barrier share of a round is a
+    # protocol cost (the same on every rank) or one rank waiting for a systematically slower one (skewed pass times)
+    phase_by_rank = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phase.items()})
+        phase_by_rank = gathered
 
     dev_ms = sum(i.loop_ms for i in infos)              # CUDA events on the solver's stream
     passes = sum(i.passes for i in infos)
@@ -595,6 +602,10 @@ def main():
                     runs.append(one())
                 barrier()
                 ph = solver.phase_breakdown()
+            ph_all = None
+            if world > 1:
+                ph_all = [None] * world
+                dist.all_gather_object(ph_all, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in ph.items()})
             tms = torch.tensor([sum(i.loop_ms for i in runs)], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -606,6 +617,7 @@ def main():
                    "ms_per_step": round(ms2, 4), "value": round(gbs, 3), "unit": "GB/s",
                    "us_per_round": round(statistics.median(i.round_us_median for i in runs), 3),
                    "phase_us": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in ph.items()},
+                   "phase_us_by_rank": ph_all,
                    "eigen_val": float(lastr.eigen_val), "kernel": f"{lastr.kernel_name} id {lastr.kernel_id}",
                    "clocks": ck.summary()}
             if rank == 0:
@@ -651,6 +663,7 @@ def main():
             "rounds": last.iter_count, "passes_per_step": last.passes, "eigen_val": float(last.eigen_val),
             "us_per_round": round(round_us, 3),
             "phase_us": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phase.items()},
+            "phase_us_by_rank": phase_by_rank,
             "wall_ms_per_step": round(wall_ms / args.steps, 5),
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
                          "frac": round(value / agg_peak, 4),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO_NAME = "libsimilarity_transform.so"   # the artefact name of reference Makefile:69
 SO_PATH = os.path.join(HERE, SO_NAME)
 SOURCES = ["solver.cu", "abi.cu"]
-HEADERS = ["kernels.cuh", "ptx.cuh", "launch_plan.hpp", "kernels_sc.cuh", "kernels_cluster.cuh", "similarity_transform.hpp", os.path.join("..", "..", "include", "similarity_transform.h")]
+HEADERS = ["kernels.cuh", "ptx.cuh", "launch_plan.hpp", "kernels_sc.cuh", "kernels_wide.cuh", "kernels_cluster.cuh", "similarity_transform.hpp", os.path.join("..", "..", "include", "similarity_transform.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -105,6 +105,7 @@ struct RoundParams
   BarrierState* bar;
   float* partial;         // resident-e kernel: chunk sums of multi-unit rows, rows x units
   unsigned int* row_done; // resident-e kernel: per-row arrival counters (monotonic)
+  unsigned int* phase_counter; // wide kernel: one monotonic work-unit counter per 32768-column window, 128 bytes apart
   unsigned long long timeout_ns;
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;

@@ -52,12 +52,13 @@ is_sc_kernel_id(int id)
   return id >= 10 && id <= 13;
 }
 constexpr int kGeneralKernelId = 1;
+constexpr int kWideKernelId = 2; // unit-scheduled, eigenvector staged one window at a time (automatic for N > 32768)
 constexpr int kClusterKernelIdPlan = 20;
-// st_options.kernel values the library accepts: 0 automatic, 1 general loop, 10-13 resident-e, 20 on-chip cluster
+// st_options.kernel values the library accepts: 0 automatic, 1 general loop, 2 wide, 10-13 resident-e, 20 on-chip cluster
 inline bool
 is_known_kernel_id(int id)
 {
-  return id == 0 || id == kGeneralKernelId || is_sc_kernel_id(id) || id == kClusterKernelIdPlan;
+  return id == 0 || id == kGeneralKernelId || id == kWideKernelId || is_sc_kernel_id(id) || id == kClusterKernelIdPlan;
 }
 
 // dynamic shared memory of the resident-e kernel: prefetch slots | e | mbarriers

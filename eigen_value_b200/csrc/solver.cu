@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "kernels_sc.cuh"
+#include "kernels_wide.cuh"
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
 
@@ -83,6 +84,7 @@ Context::preload_kernels()
   const void* kernels[] = {
     (const void*)round_loop_cluster_kernel<512, kStopAbsolute>,
     (const void*)round_loop_sc_kernel<512, 1, kStopAbsolute>,
+    (const void*)round_loop_wide_kernel<512, kStopAbsolute>,
     (const void*)round_loop_kernel<4, kFormReadOnly, 512, kStopAbsolute>,
     (const void*)round_loop_kernel<1, kFormReadOnly, 512, kStopAbsolute>,
   };
@@ -257,8 +259,8 @@ Context::scratch_need(uint32_t dim, uint32_t rows, const st_options& opt) const
   if (opt.form == ST_FORM_INPLACE) {
     n.work = (size_t)rows * dim;
   } else {
-    if (units > 1)
-      n.work = (size_t)rows * units + rows;
+    if (units > 1) // chunk sums, per-row arrival counters and (wide kernel) one work-unit counter per window
+      n.work = (size_t)rows * units + rows + 32u * (size_t)kWideMaxWindows;
   }
   return n;
 }
@@ -526,7 +528,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   if (opt.accumulate != ST_ACC_F32 && opt.accumulate != ST_ACC_F64)
     throw std::invalid_argument("solve: unknown st_options.accumulate");
   if (!is_known_kernel_id(opt.kernel))
-    throw std::invalid_argument("solve: unknown st_options.kernel (0 automatic, 1 general loop, 10-13 resident-e, 20 on-chip cluster)");
+    throw std::invalid_argument("solve: unknown st_options.kernel (0 automatic, 1 general loop, 2 wide, 10-13 resident-e, 20 on-chip cluster)");
   const bool acc64 = opt.accumulate == ST_ACC_F64;
   if (acc64) {
     if (bf16 || form != kFormReadOnly)
@@ -680,7 +682,36 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     if (!sc && opt.kernel >= 10)
       throw std::invalid_argument("solve: requested resident-e kernel configuration does not fit");
   }
-  if (!sc && !cluster_ctas) {
+  // wide kernel (kernel 2): unit-scheduled like the resident-e kernel, the eigenvector staged one 32768-column window at
+  // a time.  Automatic above the resident limit for the default form / storage / accumulator; explicit for any dim % 4 == 0.
+  bool wide = false;
+  if (!sc && !cluster_ctas && (opt.kernel == kWideKernelId || (opt.kernel == 0 && readonly4 && !bf16 && !acc64 &&
+                                                                dim > (uint32_t)kResidentCols && pinned <= 512))) {
+    if (!readonly4 || bf16 || acc64)
+      throw std::invalid_argument("solve: the wide kernel needs the read-only form, fp32 storage and accumulation, dim % 4 == 0");
+    const uint32_t window = std::min<uint32_t>((uint32_t)kResidentCols, (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols * (uint32_t)kChunkCols);
+    if ((dim + window - 1u) / window > (uint32_t)kWideMaxWindows)
+      throw std::invalid_argument("solve: the wide kernel supports up to 64 windows of 32768 columns");
+    uint32_t moff = 0;
+    shape(512, false, &grid, &threads, &rows_cap);
+    smem = sc_smem_bytes(threads, 1, std::min<uint32_t>(window, dim), &moff);
+    p.mbar_offset = moff;
+    p.chunk_cols = window;
+    const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
+    // a row of ONE unit still goes through the chunk-sum protocol here: reserve for it (small matrices, explicit kernel 2)
+    const size_t need_work = (size_t)rows * units + rows + 32u * (size_t)kWideMaxWindows;
+    if (need_work > work_cap_) {
+      if (shard && shard->world > 1)
+        throw std::invalid_argument("solve: the wide kernel's scratch was not prepared for this shard (st_shard_prepare)");
+      reserve_work(need_work);
+    }
+    p.partial = d_work_;
+    p.row_done = reinterpret_cast<unsigned int*>(d_work_ + (size_t)rows * units);
+    p.phase_counter = p.row_done + rows;
+    ST_CUDA(cudaMemsetAsync(p.row_done, 0, sizeof(unsigned int) * ((size_t)rows + 32u * (size_t)kWideMaxWindows), stream_));
+    wide = true;
+  }
+  if (!sc && !cluster_ctas && !wide) {
     shape(pinned > 512 ? 1024 : 512, true, &grid, &threads, &rows_cap);
     smem = sizeof(float) * ((size_t)p.chunk_cols + rows_cap);
   }
@@ -723,6 +754,11 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
   } else if (sc) {
     launch_sc(sc->id, stop, p, grid, threads, smem, stream_);
+  } else if (wide) {
+    if (stop == kStopRelative)
+      launch_cooperative(round_loop_wide_kernel<512, kStopRelative>, p, grid, threads, smem, stream_);
+    else
+      launch_cooperative(round_loop_wide_kernel<512, kStopAbsolute>, p, grid, threads, smem, stream_);
   } else if (vec4) {
     if (form == kFormInPlace)
       launch_by_stop<4, kFormInPlace>(stop, threads, p, grid, smem, stream_);
@@ -772,7 +808,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->launches = 1;
     res->loop_ms = loop_ms;
     res->grid = (uint32_t)grid;
-    res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : 1u;
+    res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : wide ? (uint32_t)kWideKernelId : 1u;
     res->threads = (uint32_t)threads;
     const uint64_t per_pass = (uint64_t)rows * dim * (bf16 ? 2u : sizeof(float));
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;

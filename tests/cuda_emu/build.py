@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "eigen_value_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SO = os.path.join(HERE, "libcuda_emu.so")
-KERNEL_SOURCES = ["kernels.cuh", "kernels_sc.cuh", "kernels_cluster.cuh", "launch_plan.hpp"]
+KERNEL_SOURCES = ["kernels.cuh", "kernels_sc.cuh", "kernels_wide.cuh", "kernels_cluster.cuh", "launch_plan.hpp"]
 OWN_SOURCES = ["cuda_emu.h", "ptx_emu.h", "emu_driver.cpp", os.path.join("fake_include", "cuda_runtime.h"),
                os.path.join("fake_include", "cooperative_groups.h")]
 

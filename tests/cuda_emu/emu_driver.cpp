@@ -10,6 +10,7 @@
 
 #include "kernels.cuh"
 #include "kernels_sc.cuh"
+#include "kernels_wide.cuh"
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
 
@@ -28,7 +29,7 @@ struct emu_opts
   int32_t dynamic; // -1: automatic (dim >= 8192), 0 static, 1 dynamic work units
   int32_t threads; // CTA size
   int32_t ctas;    // grid size per emulated GPU
-  int32_t kernel;  // 1 general, 10-13 resident-e, 20 cluster
+  int32_t kernel;  // 1 general, 2 wide, 10-13 resident-e, 20 cluster
   int32_t stop;    // 0 absolute, 1 relative
   int32_t bf16;    // matrix is bf16 storage
   int32_t world;   // emulated GPUs (row-block sharded)
@@ -52,6 +53,7 @@ struct Rank
   std::vector<float> vecs;    // S0 S1 (world == 1), E0 E1, OUT
   std::vector<float> partial; // chunk sums
   std::vector<unsigned> row_done;
+  std::vector<unsigned> phase_counter;
   std::vector<unsigned long long> ts;
   std::vector<unsigned char> work; // in-place working copy
   BarrierState* bar = nullptr;
@@ -214,6 +216,30 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.row_done = r.row_done.data();
         }
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
+      } else if (kid == 2) {
+        // wide kernel: windows of p.chunk_cols columns (kResidentCols; ST_EMU_WINDOW stages less so that several
+        // windows fit an emulated size), chunk sums + per-row counters + one unit counter per window
+        if (!vec4 || form != kFormReadOnly || bf16 || acc64)
+          throw std::string("wide kernel: read-only form, fp32, dim % 4 == 0");
+        uint32_t window = (uint32_t)kResidentCols;
+        if (const char* wv = getenv("ST_EMU_WINDOW"))
+          window = (uint32_t)std::max(kChunkCols, atoi(wv) / kChunkCols * kChunkCols);
+        window = std::min<uint32_t>(window, (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols * (uint32_t)kChunkCols);
+        r.grid = std::max(1u, std::min(want, (rows + warps - 1) / warps));
+        uint32_t moff = 0;
+        r.smem = sc_smem_bytes((int)r.threads, 1, std::min<uint32_t>(window, dim), &moff);
+        if (r.smem > kSmemLimit)
+          throw std::string("wide kernel does not fit shared memory");
+        p.mbar_offset = moff;
+        p.chunk_cols = window;
+        const uint32_t units = (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols;
+        r.partial.assign((size_t)rows * units, -3.f);
+        r.row_done.assign(rows, 0u);
+        r.phase_counter.assign(32u * (size_t)kWideMaxWindows, 0u);
+        p.partial = r.partial.data();
+        p.row_done = r.row_done.data();
+        p.phase_counter = r.phase_counter.data();
+        kernel = o->stop ? round_loop_wide_kernel<512, kStopRelative> : round_loop_wide_kernel<512, kStopAbsolute>;
       } else if (kid == 20) {
         if (!vec4 || form != kFormReadOnly || bf16 || world != 1 || dim > (uint32_t)kClusterCols)
           throw std::string("cluster kernel: one GPU, read-only form, fp32, dim % 4 == 0, dim <= 512");

@@ -99,6 +99,9 @@ main(int argc, char** argv)
     { "2 GPUs, general 200", 200, with(1, 64, 2, 2) },
     { "3 GPUs, resident-e 13 dynamic 320", 320, with(13, 64, 2, 3, 0, 0, 1) },
     { "resident-e 13, fp64 accumulation, 320", 320, [&] { emu_opts o = with(13, 64, 3); o.acc64 = 1; return o; }() },
+    { "wide kernel 2, dynamic units, 320", 320, with(2, 64, 3, 1, 0, 0, 1) },
+    { "2 GPUs, wide kernel 2, static units, 200", 200, with(2, 64, 2, 2, 0, 0, 0) },
+    { "wide kernel 2, three 8192-column windows (ST_EMU_WINDOW), 16400 x 2 rounds", 16400, [&] { setenv("ST_EMU_WINDOW", "8192", 1); return with(2, 64, 4, 1, 0, 0, 1, 0, 2u); }() },
   };
   int failures = 0;
   for (const Case& c : cases) {

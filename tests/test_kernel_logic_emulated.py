@@ -234,3 +234,38 @@ def test_general_loop_with_several_staged_windows_per_row(monkeypatch):
         same_bits(emu.solve(mat, 16400, kernel=1, threads=128, ctas=5, max_iter=2), want)
     monkeypatch.setenv("ST_EMU_WINDOW", "8192")
     same_bits(emu.solve(mat, 16400, kernel=1, threads=64, ctas=3, world=2, form=1, max_iter=2), expect(mat, 1, max_iter=2))
+
+
+# ---- wide kernel (kernel 2): unit-scheduled, the eigenvector staged one window at a time --------------------------
+@pytest.mark.parametrize("dim,threads,ctas,world,dynamic,sweep", [(520, 64, 3, 1, 1, 1), (520, 64, 3, 1, 0, 1), (1000, 128, 4, 1, 1, 0),
+                                                                  (36, 32, 2, 1, 1, 1), (4, 32, 1, 1, 0, 1), (1000, 64, 2, 3, 1, 1),
+                                                                  (640, 96, 5, 2, 0, 1)])
+def test_wide_kernel_one_window(dim, threads, ctas, world, dynamic, sweep):
+    mat = U(dim)
+    same_bits(emu.solve(mat, dim, kernel=2, threads=threads, ctas=ctas, world=world, dynamic=dynamic, sweep=sweep), expect(mat))
+
+
+def test_wide_kernel_stop_tests_and_round_cap():
+    mat = U(256)
+    for kw in (dict(eps=1e-2), dict(max_iter=5), dict(eps=0.0, max_iter=25), dict(eps=1e-6, stop=1, max_iter=60)):
+        okw = dict(kw)
+        if "stop" in okw:
+            okw["stop"] = oracle.STOP_RELATIVE
+        same_bits(emu.solve(mat, 256, kernel=2, threads=64, ctas=4, **kw), expect(mat, **okw))
+    bad = mat.copy()
+    bad[100, 21] = np.nan
+    assert emu.solve(bad, 256, kernel=2, threads=64, ctas=2, max_iter=30)[2] == 30
+
+
+def test_wide_kernel_several_windows_per_row(monkeypatch):
+    # 16400 columns = three 8192-column chunks (the last one 16 columns); windows of 8192 columns -> three phases per
+    # round (one chunk each), 16384 -> two phases (two chunks + one); every CTA walks them on its own, every window
+    # has its own unit counter.  Alternating sweep: odd rounds go through the windows backwards.
+    mat = U(16400)
+    want = expect(mat, max_iter=3)
+    for window, dyn in (("8192", 1), ("16384", 1), ("16384", 0), ("32768", 1)):
+        monkeypatch.setenv("ST_EMU_WINDOW", window)
+        same_bits(emu.solve(mat, 16400, kernel=2, threads=128, ctas=5, dynamic=dyn, max_iter=3), want)
+    monkeypatch.setenv("ST_EMU_WINDOW", "8192")
+    same_bits(emu.solve(mat, 16400, kernel=2, threads=64, ctas=3, world=2, dynamic=1, max_iter=2), expect(mat, max_iter=2))
+    same_bits(emu.solve(mat, 16400, kernel=2, threads=64, ctas=4, dynamic=1, sweep=0, max_iter=2), expect(mat, max_iter=2))

@@ -16,7 +16,7 @@ import emu  # noqa: E402
 
 @st.composite
 def cases(draw):
-    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 20]))
+    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 20, 2, 2]))
     dim = draw(st.integers(1, 1100))
     if kernel != 1:
         dim = max(4, dim - dim % 4)                       # vector kernels: dim % 4 == 0

@@ -44,18 +44,19 @@ def test_positive_control_missing_syncthreads_is_reported(tsan_exe):
 
 def test_round_kernels_are_race_free(tsan_exe):
     """general loop (both forms, scalar, relative stop), resident-e (prefetch, static / dynamic units, resident
-    rows, bf16, two units per row, fp64 accumulation), cluster kernel, 2 and 3 emulated GPUs (tsan_main.cpp)."""
+    rows, bf16, two units per row, fp64 accumulation), cluster kernel, wide kernel (one and three windows, 2 GPUs), 2 and 3
+    emulated GPUs (tsan_main.cpp)."""
     proc = run(tsan_exe)
     assert "ThreadSanitizer" not in proc.stderr, proc.stderr[:4000]
     assert proc.returncode == 0, proc.stdout
-    assert proc.stdout.count("rc=0") == 12 and "agree=0" not in proc.stdout
+    assert proc.stdout.count("rc=0") == 15 and "agree=0" not in proc.stdout
 
 
 MUTANTS = [
     # the barrier between rebuilding the eigenvector chunk in shared memory and the rows that read it
     ("general_chunk_barrier", "kernels.cuh",
-     "      __syncthreads();\n      for (uint32_t i = warp; i < nrows; i += kWarps) {",
-     "      for (uint32_t i = warp; i < nrows; i += kWarps) {"),
+     "      __syncthreads();\n      // the staged window holds up to four 8192-column chunks",
+     "      // the staged window holds up to four 8192-column chunks"),
     # the parity double-buffering of the row-sum vector: one barrier per round is only enough because a CTA
     # that runs one round ahead writes the OTHER buffer
     ("resident_e_single_buffered_s", "kernels_sc.cuh",

@@ -172,7 +172,7 @@ def test_relative_stop_with_nan_hits_the_cap_and_unknown_options_are_refused(sol
     assert info.iter_count == 50
     d = solver.hilbert(1024)
     with pytest.raises(Exception):
-        solver.solve_device(d, 1024, kernel=2, stop=STOP_RELATIVE)     # a kernel id that does not exist (round 1: TMA ring)
+        solver.solve_device(d, 1024, kernel=5, stop=STOP_RELATIVE)     # a kernel id that does not exist (round 1: TMA ring)
     with pytest.raises(Exception):
         solver.solve_device(d, 1024, stop=7)                           # unknown mode
     info, _ = solver.solve_device(d, 1024)                             # the handle stays usable
@@ -203,7 +203,7 @@ def test_fp64_accumulation_is_bit_identical_to_the_oracle(solver, dim):
 
 def test_fp64_accumulation_refusals(solver):
     d = solver.hilbert(256)
-    for bad in (dict(form=FORM_INPLACE), dict(kernel=2), dict(kernel=20), dict(kernel=11), dict(accumulate=5)):
+    for bad in (dict(form=FORM_INPLACE), dict(kernel=2), dict(kernel=20), dict(kernel=11), dict(accumulate=5)):   # 2: wide kernel, fp32 accumulators only
         kw = dict(accumulate=ACC_F64)
         kw.update(bad)
         with pytest.raises(Exception):
