@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       const uint32_t v = idx + rotv;
       return v < nv ? v : v - nv;
     };
-    constexpr int kTailBatch = 16;
+    constexpr int kTailBatch = 8;
     for (uint32_t v0 = 0; v0 < nv; v0 += (uint32_t)kTailBatch * THREADS) {
       float4 t4[kTailBatch];
       float nx[kTailBatch];

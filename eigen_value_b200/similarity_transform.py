@@ -121,14 +121,14 @@ class SolveInfo:
     kernel_id: int = 0
     threads: int = 0
 
-    KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_tma_kernel", 10: "st::round_loop_sc_kernel",
+    KERNEL_NAMES = {1: "st::round_loop_kernel", 2: "st::round_loop_wide_kernel", 10: "st::round_loop_sc_kernel",
                     20: "st::round_loop_cluster_kernel",
                     30: "st::sum_across_rows_kernel + tail kernels (streamed, host-driven rounds)"}
 
     @property
     def kernel_name(self) -> str:
         k = self.kernel_id
-        key = 30 if k >= 30 else 10 if 21 <= k <= 26 else 20 if k >= 20 else 10 if k >= 10 else 2 if k >= 2 else 1
+        key = 30 if k >= 30 else 20 if k >= 20 else 10 if k >= 10 else 2 if k == 2 else 1
         return self.KERNEL_NAMES[key]
 
     @classmethod

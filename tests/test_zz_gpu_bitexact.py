@@ -102,18 +102,29 @@ def test_multi_chunk_16384_bit_identical(solver):
     _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(oracle.hilbert(dim)), "hilbert-16384")
 
 
-def test_general_loop_beyond_the_resident_limit_bit_identical(solver):
-    # N > 32768 takes the general column-chunked loop (5 chunks here); capped at 3 rounds so the
-    # oracle needs ~10 s for the 6.25 GiB matrix
+def test_wide_and_general_loops_beyond_the_resident_limit_bit_identical(solver):
+    # N > 32768: the wide kernel (automatic; two windows of 32768 + 8192 columns, 5 chunks per row) and the general
+    # column-chunked loop (kernel 1); capped at 3 rounds so the oracle needs ~10 s for the 6.25 GiB matrix
     dim = 40960
     if solver.hbm_bytes < 16 * 2**30:
         pytest.skip("needs 6.25 GiB of device memory")
     d = solver.uniform(dim, 0x5EED0003)
     info, vec = solver.solve_device(d, dim, max_iter=3)
+    base, base_vec = solver.solve_device(d, dim, max_iter=3, kernel=1)
     d.free()
-    assert info.kernel_id == 1
-    mat = oracle.uniform(dim, 0x5EED0003)
-    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=3), "uniform-40960")
+    assert info.kernel_id == 2 and base.kernel_id == 1
+    want = oracle.similarity_transform_generated("uniform", dim, 0x5EED0003, max_itr=3)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), (want[0], want[1], want[3]), "uniform-40960 wide")
+    _assert_same_bits((base.eigen_val, base_vec, base.iter_count), (want[0], want[1], want[3]), "uniform-40960 general")
+
+
+@pytest.mark.parametrize("dim", [4, 520, 2048, 8200, 16384])
+def test_wide_kernel_at_sizes_the_resident_kernel_also_takes(solver, dim):
+    # explicit kernel 2 below the resident limit: one window, rows of one or two chunks -- the bits of every other kernel
+    mat = _matrix("uniform", dim)
+    info, vec = solver.solve_device(solver.upload(mat), dim, kernel=2, max_iter=8)
+    assert info.kernel_id == 2
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=8), f"wide {dim}")
 
 
 @pytest.mark.parametrize("dim", [7, 64, 1000, 2048, 8200])
