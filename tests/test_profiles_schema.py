@@ -8,7 +8,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_n1_hilbert8192.json"))
-               + glob.glob(os.path.join(ROOT, "profiles", "r1_scale_*.json")))
+               + glob.glob(os.path.join(ROOT, "profiles", "r1_scale_*.json"))
+               + glob.glob(os.path.join(ROOT, "profiles", "r2_bench_n*.json"))
+               + glob.glob(os.path.join(ROOT, "profiles", "r2_c8_bench_n2.json"))
+               + glob.glob(os.path.join(ROOT, "profiles", "r2_c9_bench_n[48].json")))
+LINES = [p for p in LINES if "reference_arm" not in p]
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
              "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e",
@@ -55,3 +59,22 @@ def test_there_is_a_committed_line_for_every_gpu_count():
         with open(path) as f:
             counts.add(json.loads(f.read())["n_gpus"])
     assert {1, 2, 4, 8} <= counts
+
+
+R2 = [p for p in LINES if os.path.basename(p).startswith("r2_")]
+
+
+@pytest.mark.parametrize("path", R2, ids=[os.path.basename(p) for p in R2])
+def test_round_2_lines_carry_a_parity_verdict_and_the_north_star_records(path):
+    with open(path) as f:
+        d = json.loads(f.read())
+    assert d["parity"]["bits_equal"] is True and d["parity"]["checked_against"].startswith("tests/golden/")
+    assert d["e2e_pageable"] is None or "pageable" in d["e2e_pageable"]["api"]
+    names = [r["workload"] for r in d["north_star"]]
+    assert "hilbert-131072" in names and "uniform-131072" in names
+    for r in d["north_star"]:
+        assert r["n_gpus"] == d["n_gpus"] and r["parity"]["bits_equal"] is True
+        assert abs(r["value"] - r["passes_per_step"] * 4.0 * r["N"] ** 2 / (r["ms_per_step"] * 1e-3) / 1e9) < 5e-3 * r["value"]
+        assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(r["clocks"]["reasons"])
+        if r["workload"] == "hilbert-131072":
+            assert r["rounds"] == 23                     # BASELINE.md section 5's prediction, the oracle's count
