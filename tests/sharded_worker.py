@@ -65,6 +65,28 @@ def main():
         d_full.free()
         sh.close()
 
+    # BASELINE configs 3 to 5 at full size, sharded: the wide kernel (N > 32768) and the resident-e kernel must return the
+    # bits the CPU oracle computed matrix-free (tests/golden/generated_expected.json: lambda, rounds, eigenvector digest)
+    import hashlib
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generated_expected.json")) as f:
+        expected = json.load(f)["cases"]
+    for name in ("hilbert-32768", "hilbert-65536", "uniform-65536", "hilbert-131072", "uniform-131072"):
+        e = expected[name]
+        dim = e["dim"]
+        if 4 * dim * dim // world > 0.8 * solver.hbm_bytes:
+            continue
+        sh = ShardedSolver(solver, dim, rank, world)
+        d_rows = sh.hilbert() if e["kind"] == "hilbert" else sh.uniform(e["seed"])
+        dist.barrier()
+        info, vec = sh.solve(d_rows, max_iter=e["max_iter"])
+        assert info.iter_count == e["iter_count"], (name, info.iter_count)
+        assert int(np.float32(info.eigen_val).view(np.uint32)) == e["eigen_val_bits"], (name, float(info.eigen_val))
+        assert hashlib.sha256(np.ascontiguousarray(vec).tobytes()).hexdigest() == e["eigen_vec_sha256"], name
+        report.append({"case": f"{name}-full-size-vs-cpu-oracle", "rounds": info.iter_count, "lambda": float(info.eigen_val),
+                       "kernel": info.kernel_id, "us_per_round": info.round_us_median})
+        d_rows.free()
+        sh.close()
+
     # ST_STOP_RELATIVE (extension): the decision is taken redundantly on every rank from identical
     # inputs, so the sharded solve stops in the same round with the same bits as one GPU
     for kind, dim in (("uniform", 4096), ("hilbert", 16384)):

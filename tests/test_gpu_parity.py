@@ -411,3 +411,31 @@ def test_concurrent_callers_on_one_handle_are_serialised(ev):
         t.join(timeout=300)
     for got, w in zip(out, want):
         assert got is not None and got[3] == w[3] and got[0] == w[0] and np.array_equal(got[1], w[1])
+
+
+# ---- BASELINE configs 3 to 5 at FULL size on one GPU against CPU-computed expected bits ---------------------------------
+@pytest.mark.parametrize("name", ["hilbert-16384", "hilbert-32768", "uniform-32768", "hilbert-65536", "uniform-65536",
+                                  "hilbert-131072", "uniform-131072"])
+def test_full_size_configs_return_the_bits_the_cpu_oracle_computed(solver, name):
+    """tests/golden/generated_expected.json holds lambda bits, round count and the sha256 of the raw eigenvector that the
+    oracle's matrix-free loop (ORACLE_SUM_CUDA order) computed on the CPU -- Hilbert to convergence, the uniform cases
+    (seeds of BASELINE configs 4 and 5) capped at 50 rounds.  The matrix is generated on the device: 16 GiB at 65536,
+    64 GiB at 131072 (the north-star size on ONE GPU, wide kernel)."""
+    import hashlib
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "generated_expected.json")) as f:
+        e = json.load(f)["cases"][name]
+    dim = e["dim"]
+    if 4 * dim * dim > 0.8 * solver.hbm_bytes:
+        pytest.skip("matrix does not fit this device")
+    d = solver.hilbert(dim) if e["kind"] == "hilbert" else solver.uniform(dim, e["seed"])
+    try:
+        info, vec = solver.solve_device(d, dim, max_iter=e["max_iter"])
+    finally:
+        d.free()
+    assert info.kernel_id == (2 if dim > 32768 else 13)
+    assert info.iter_count == e["iter_count"]
+    assert int(np.float32(info.eigen_val).view(np.uint32)) == e["eigen_val_bits"], float(info.eigen_val)
+    assert hashlib.sha256(np.ascontiguousarray(vec).tobytes()).hexdigest() == e["eigen_vec_sha256"]

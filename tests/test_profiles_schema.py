@@ -9,10 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_n1_hilbert8192.json"))
                + glob.glob(os.path.join(ROOT, "profiles", "r1_scale_*.json"))
-               + glob.glob(os.path.join(ROOT, "profiles", "r2_bench_n*.json"))
-               + glob.glob(os.path.join(ROOT, "profiles", "r2_c8_bench_n2.json"))
-               + glob.glob(os.path.join(ROOT, "profiles", "r2_c9_bench_n[48].json")))
-LINES = [p for p in LINES if "reference_arm" not in p]
+               + glob.glob(os.path.join(ROOT, "profiles", "r2_bench_n[1248].json")))      # the final build, driver-style lines
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
              "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e",
