@@ -45,31 +45,11 @@ ld_relaxed_gpu(const unsigned long long* p)
   return v;
 }
 
-__device__ __forceinline__ void
-st_release_gpu(unsigned int* p, unsigned int v)
-{
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __device__ __forceinline__ unsigned long long
 ld_acquire_sys(const unsigned long long* p)
 {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void
-st_release_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ unsigned long long
-ld_relaxed_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -201,24 +181,6 @@ bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
                  smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-__device__ __forceinline__ void
-bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar,
-               unsigned long long pol)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-               "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-               : "memory");
-}
-
-// Asks the memory system to pull [src_gmem, src_gmem + bytes) into L2 (no destination, no completion to
-// wait for; SASS UBLKPF.L2).  16-byte aligned address, size a multiple of 16.  A hint: never changes a result.
-__device__ __forceinline__ void
-l2_prefetch_bulk(const float* src_gmem, uint32_t bytes)
-{
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void

@@ -33,27 +33,11 @@ ld_relaxed_gpu(const unsigned long long* p)
 {
   return __atomic_load_n(p, EMU_RELAXED_LOAD);
 }
-inline void
-st_release_gpu(unsigned int* p, unsigned int v)
-{
-  __atomic_store_n(p, v, __ATOMIC_RELEASE);
-}
 inline unsigned long long
 ld_acquire_sys(const unsigned long long* p)
 {
   sched_yield();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
-}
-inline void
-st_release_sys(unsigned long long* p, unsigned long long v)
-{
-  __atomic_store_n(p, v, __ATOMIC_RELEASE);
-}
-inline unsigned long long
-ld_relaxed_sys(const unsigned long long* p)
-{
-  sched_yield();
-  return __atomic_load_n(p, EMU_RELAXED_LOAD);
 }
 inline void
 st_relaxed_sys(unsigned long long* p, unsigned long long v)
@@ -126,23 +110,6 @@ bulk_load(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar)
   memcpy(dst_smem, src_gmem, bytes);
   EMU_RELEASE(bar);
   emu_bump(bar);
-}
-inline void
-bulk_load_hint(float* dst_smem, const float* src_gmem, uint32_t bytes, uint64_t* bar, unsigned long long)
-{
-  bulk_load(dst_smem, src_gmem, bytes, bar);
-}
-inline void
-l2_prefetch_bulk(const float* src_gmem, uint32_t bytes)
-{
-  if (bytes == 0u || bytes % 16u != 0u || (reinterpret_cast<uintptr_t>(src_gmem) & 15u)) {
-    fprintf(stderr, "cuda_emu: L2 bulk prefetch with misaligned address or size (%u bytes)\n", bytes);
-    abort(); // the hardware would fault
-  }
-  // touch both ends so that an out-of-bounds hint is caught by the address sanitiser / a guard page
-  volatile float first = src_gmem[0], last = src_gmem[bytes / 4u - 1u];
-  (void)first;
-  (void)last;
 }
 inline void
 fence_mbarrier_init()
