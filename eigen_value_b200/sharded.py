@@ -113,6 +113,9 @@ class ShardedSolver:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             dist.barrier()
+            return
+        raise RuntimeError("ShardedSolver: scratch for these options had to be reserved (st_shard_prepare), which must be "
+                           "followed by a host barrier across the ranks; pass barrier=... when torch.distributed is not used")
 
     def close(self) -> None:
         if self._vec is not None:
