@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, first GPU call (one B200): the measurement backlog of round 1, ordered so that a cut-short call
-# still leaves the most useful numbers.   gpurun --timeout 1380 -- 'bash tools/r2_call1.sh'
+# still leaves the most useful numbers.   gpurun --timeout 1380 -- 'bash tools/gpu_calls/r2_call1.sh'
 set -u
 mkdir -p gpurun_out
 O=gpurun_out/r2c1
