@@ -462,8 +462,7 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
 //   wait    : EVERY CTA polls the local counter and, when sharded, the G - 1 flag words the peers wrote into
 //             this GPU's memory (acquire loads at system scope) -- no second hop through a generation word.
 //   result  : *s_m = max(0, max_r s[r]) over all GPUs = the reference's find_max (:154-227), so the vector
-//             tail needs a single pass over s (stop test and eigenvector update together).  (defer_local_max: the
-//             peers' part only; the caller folds in smax[parity] of its own GPU, see round_loop_sc_kernel.)
+//             tail needs a single pass over s (stop test and eigenvector update together).
 // Flags and smax are indexed by the parity of k + flip and tagged with a monotonic sequence number, so they
 // are never reset -- not between rounds, not between solves.  All waits are bounded by timeout_ns (checked
 // every 1024 polls) so that a missing rank turns into an error code instead of a hung GPU.  Returns false on
@@ -493,7 +492,7 @@ constexpr uint32_t kFlagSlots = 2u * (uint32_t)kMaxWorld; // 64-bit words in a r
 
 __device__ __forceinline__ bool
 round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned int* s_cta_max = nullptr,
-              volatile float* s_m = nullptr, bool defer_local_max = false)
+              volatile float* s_m = nullptr)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -533,9 +532,7 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned 
         break;
       }
     }
-    // defer_local_max: the caller reads this GPU's smax word itself, together with its first loads of s (one L2 round
-    // trip instead of two in a row); *s_m then carries the peers' maxima only
-    uint32_t bits = defer_local_max ? 0u : (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
+    uint32_t bits = (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
     if (p.world > 1) {
       const uint32_t want = p.seq_base + k + 1u;
       for (uint32_t g = 0; g < p.world && !fail; g++) {

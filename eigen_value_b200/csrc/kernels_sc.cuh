@@ -289,12 +289,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       stamp_phase(p, k, 0u);
 
     // the barrier's first __syncthreads orders the warps' atomicMax before thread 0 reads the CTA's max
-    if (!round_barrier(p, k, &s_abort, &s_cta_max, &s_m, true))
+    if (!round_barrier(p, k, &s_abort, &s_cta_max, &s_m))
       break;
     if (blockIdx.x == 0 && tid == 0)
       stamp_phase(p, k, 1u);
+    const float m_k = s_m; // max over every GPU's rows, carried by the barrier            :41
 
-    // ---- every CTA: circular stop test over the full s and the e update, ONE pass ----   :41-44
+    // ---- every CTA: circular stop test over the full s and the e update, ONE pass ----   :42-44
     // 128-bit L2 loads, all loads of a batch (8 per thread) issued before anything depends on them.  The
     // circular neighbour of a vector's last element is the next lane's first element (shuffle); only
     // lane 31 reads it from memory -- the reference does the same with shuffle_down + one global read
@@ -303,15 +304,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     const float4* S4 = reinterpret_cast<const float4*>(Scur);
     float4* e4_s = reinterpret_cast<float4*>(e_s);
     const uint32_t rotv = cb >> 2;
+    const float thr = STOP == kStopRelative ? p.eps * m_k : p.eps;
     int ok = 1;
     auto vec_index = [&](uint32_t idx) {
       const uint32_t v = idx + rotv;
       return v < nv ? v : v - nv;
     };
     constexpr int kTailBatch = 8;
-    float4 t4[kTailBatch];
-    float nx[kTailBatch];
-    auto load_batch = [&](uint32_t v0) {
+    for (uint32_t v0 = 0; v0 < nv; v0 += (uint32_t)kTailBatch * THREADS) {
+      float4 t4[kTailBatch];
+      float nx[kTailBatch];
 #pragma unroll
       for (int j = 0; j < kTailBatch; j++) {
         const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
@@ -321,17 +323,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         const bool edge = active && (lane == 31 || idx + 1u >= nv);
         nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
       }
-    };
-    // The first batch of s and this GPU's max word travel together: one L2 round trip after the barrier, not two.
-    load_batch(0u);
-    if (tid == 0) {
-      const uint32_t mine = (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
-      s_m = __uint_as_float(max(mine, __float_as_uint(s_m))); // s_m came out of the barrier with the peers' maxima
-    }
-    __syncthreads();
-    const float m_k = s_m; // max over every GPU's rows = find_max                          :41
-    const float thr = STOP == kStopRelative ? p.eps * m_k : p.eps;
-    auto process_batch = [&](uint32_t v0) {
 #pragma unroll
       for (int j = 0; j < kTailBatch; j++) {
         const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
@@ -356,11 +347,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           }
         }
       }
-    };
-    process_batch(0u);
-    for (uint32_t v0 = (uint32_t)kTailBatch * THREADS; v0 < nv; v0 += (uint32_t)kTailBatch * THREADS) {
-      load_batch(v0);
-      process_batch(v0);
     }
     if (blockIdx.x == 0 && tid == 0)
       stamp_round_end(p, k);
