@@ -115,6 +115,13 @@ struct RoundParams
   uint32_t seq_base;                      // (solve counter & 0xff) << 24: flags are never reset between solves
   uint32_t flip;                          // parity offset of this solve: round k uses buffer / flag set (k + flip) & 1, so that
                                           // a rank that starts the next solve early never touches what a slower peer still reads
+  // flat cross-GPU barrier (xbar == 1): every CTA of every GPU arrives at every GPU's counter itself
+  uint32_t xbar;                              // 0: per-GPU flags forwarded by the completing CTA; 1: flat
+  uint32_t xbar_sc_fence;                     // flat: 1 = sequentially consistent system fence before the arrivals (experiment)
+  unsigned long long* peer_arrive[kMaxWorld]; // monotonic arrival counter of every rank (kArriveUnits per GPU and round)
+  unsigned int* peer_smax3[kMaxWorld];        // max of the published row sums (float bits), three slots rotating by round
+  unsigned long long arrive_base;             // what this group's counters had reached before this solve
+  unsigned long long round_base;              // rounds this group ran before this solve (slot = (round_base + k) % 3)
   // results
   float* out_eigen_vec;  // N floats (device)
   float* out_eigen_val;  // 1 float  (device)
@@ -490,6 +497,20 @@ struct SpinClock
 
 constexpr uint32_t kFlagSlots = 2u * (uint32_t)kMaxWorld; // 64-bit words in a rank's flag array
 
+// Head of a rank's exchange block (mapped into every peer): the flag words of the forwarding protocol and the
+// words of the flat barrier, each on a line of its own; the two row-sum buffers follow.
+struct alignas(128) ExchangeHeader
+{
+  unsigned long long flags[kFlagSlots];
+  unsigned long long arrive; // flat barrier: + kArriveUnits per GPU and round, never reset
+  unsigned long long pad0[15];
+  unsigned int smax3[3];     // flat barrier: slot r % 3 holds round r's max; reset two rounds ahead of its next use
+  unsigned int pad1[29];
+};
+// A GPU's CTAs add up to exactly this much per round whatever its grid size is (ranks of tiny problems can run
+// different grids), so no rank needs to know another rank's launch shape.
+constexpr unsigned long long kArriveUnits = 4096ull;
+
 __device__ __forceinline__ bool
 round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned int* s_cta_max = nullptr,
               volatile float* s_m = nullptr)
@@ -508,6 +529,46 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned 
     const unsigned int target = (k + 1u) * gridDim.x;
     const unsigned long long tag = (unsigned long long)(k + 1u) << 32;
     SpinClock clk;
+    if (p.world > 1 && p.xbar == 1u) {
+      // ---- flat barrier: no completing CTA, no forwarding hop.  Every CTA folds its max into every GPU's slot of
+      // the round and then arrives at every GPU's counter (peers first: their stores have the longer way); ONE system
+      // fence in between orders the CTA's peer stores of s and the max before the arrivals.  A waiter polls one
+      // word in its own memory.  The slot of round r is cleared by this GPU's CTA 0 once barrier r + 1 has been
+      // passed (every reader of it has arrived there) and is next written in round r + 3, by CTAs that passed
+      // barrier r + 2 -- which CTA 0 only arrives at after the clear.
+      const unsigned long long r = p.round_base + k;
+      const uint32_t slot = (uint32_t)(r % 3ull);
+      if (cta_max_bits != 0u)
+        for (uint32_t i = 1; i <= p.world; i++) {
+          const uint32_t g = p.rank + i < p.world ? p.rank + i : p.rank + i - p.world;
+          red_relaxed_sys_max(p.peer_smax3[g] + slot, cta_max_bits);
+        }
+      if (p.xbar_sc_fence)
+        __threadfence_system();
+      else
+        fence_acq_rel_sys();
+      const unsigned long long inc =
+        kArriveUnits * (blockIdx.x + 1u) / gridDim.x - kArriveUnits * blockIdx.x / gridDim.x;
+      for (uint32_t i = 1; i <= p.world; i++) {
+        const uint32_t g = p.rank + i < p.world ? p.rank + i : p.rank + i - p.world;
+        red_relaxed_sys_add(p.peer_arrive[g], inc);
+      }
+      const unsigned long long want = p.arrive_base + (unsigned long long)(k + 1u) * p.world * kArriveUnits;
+      while (ld_acquire_sys(p.peer_arrive[p.rank]) < want) {
+        if (clk.expired(p.timeout_ns, &p.bar->error)) {
+          fail = 1;
+          break;
+        }
+      }
+      const uint32_t bits = ld_relaxed_sys(p.peer_smax3[p.rank] + slot);
+      if (blockIdx.x == 0)
+        st_relaxed_sys(p.peer_smax3[p.rank] + (slot + 2u) % 3u, 0u); // round r - 1's slot, next used in round r + 2
+      if (fail)
+        atomicExch(&p.bar->error, 1u);
+      if (s_m)
+        *s_m = __uint_as_float(bits);
+      *s_abort = fail;
+    } else {
     atomicMax(&p.bar->smax[par], tag | cta_max_bits);
     if (p.world == 1) {
       red_release_gpu_add(&p.bar->count, 1u);
@@ -554,6 +615,7 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned 
     if (s_m)
       *s_m = __uint_as_float(bits);
     *s_abort = fail;
+    }
   }
   __syncthreads();
   return *s_abort == 0;

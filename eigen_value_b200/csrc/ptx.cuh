@@ -65,6 +65,41 @@ red_release_gpu_add(unsigned int* p, unsigned int v)
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Flat cross-GPU barrier: fire-and-forget reductions at system scope, onto this GPU's or a peer's memory
+// (over NVLink the atomic is performed at the owner's L2, like a local one)
+__device__ __forceinline__ void
+red_relaxed_sys_add(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void
+red_relaxed_sys_max(unsigned int* p, unsigned int v)
+{
+  asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// release/acquire fence at system scope (MEMBAR.ALL.SYS); __threadfence_system() is the sequentially consistent one
+__device__ __forceinline__ void
+fence_acq_rel_sys()
+{
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
+__device__ __forceinline__ unsigned int
+ld_relaxed_sys(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void
+st_relaxed_sys(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---- matrix stream ------------------------------------------------------------------------------
 // Streaming 128-bit load of matrix data that is never written while the kernel runs: read-only
 // path, no L1 allocation (each byte is used exactly once per round).  The two-argument forms carry

@@ -137,6 +137,9 @@ private:
   std::vector<uint64_t> last_phase_ts_;
 };
 
+// bytes of the exchange block's head (kernels.cuh: ExchangeHeader -- flag words, arrival counter, max slots)
+constexpr size_t kExchangeHeaderBytes = 384;
+
 // Row-block shard: this rank's exchange block (two N-float row-sum buffers + flags) and the
 // mapped blocks of the peers.
 struct Shard
@@ -152,6 +155,8 @@ struct Shard
   bool linked = false;
   uint64_t solves = 0;
   uint32_t flip = 0; // parity offset of the next solve's exchange buffers and flag sets (RoundParams::flip)
+  uint64_t arrive_total = 0; // flat barrier: what every rank's arrival counter reads between solves
+  uint64_t rounds_total = 0; // flat barrier: rounds run so far (the max slots rotate by round)
 };
 
 } // namespace st

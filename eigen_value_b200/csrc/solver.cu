@@ -24,6 +24,8 @@
 #include "kernels_cluster.cuh"
 #include "launch_plan.hpp"
 
+static_assert(sizeof(st::ExchangeHeader) == st::kExchangeHeaderBytes, "exchange block header layout");
+
 // Triple-chevron launches go through two macros so that the host code of this file can also be built
 // for the CPU emulation harness (tests/cuda_emu), whose stand-in <cuda_runtime.h> defines them first:
 //   ST_LAUNCH              kernels whose threads cooperate (barriers, shuffles, shared memory)
@@ -588,6 +590,17 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     shard->solves += 1;
     p.seq_base = (uint32_t)(shard->solves & 0xffu) << 24;
     p.flip = shard->flip;
+    // flat barrier (default; st_options.sweep bit 4 selects the forwarding protocol of the first half of round 2):
+    // counters and max slots sit in the exchange blocks and are never reset, the group's totals carry over
+    p.xbar = (opt.sweep & 16) ? 0u : 1u;
+    p.xbar_sc_fence = (opt.sweep & 32) ? 1u : 0u;
+    for (uint32_t g = 0; g < shard->world; g++) {
+      ExchangeHeader* h = static_cast<ExchangeHeader*>(shard->peer_block[g]);
+      p.peer_arrive[g] = &h->arrive;
+      p.peer_smax3[g] = h->smax3;
+    }
+    p.arrive_base = shard->arrive_total;
+    p.round_base = shard->rounds_total;
     if (opt.max_iter >= (1u << 24) - 1u)
       throw std::invalid_argument("solve: a sharded solve supports max_iter below 2^24 - 1");
   }
@@ -790,8 +803,13 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     return ST_ERR_TIMEOUT;
   }
   const uint32_t passes = words[2];
-  if (shard)
+  if (shard) {
     shard->flip = (shard->flip + passes) & 1u; // every rank saw the same number of rounds
+    if (p.xbar == 1u) {
+      shard->arrive_total += (uint64_t)passes * shard->world * kArriveUnits;
+      shard->rounds_total += passes;
+    }
+  }
   const uint32_t stamped = std::min<uint32_t>(passes, p.ts_rounds);
   last_ts_.assign((size_t)stamped + 1, 0);
   ST_CUDA(cudaMemcpy(last_ts_.data(), d_ts_, sizeof(uint64_t) * ((size_t)stamped + 1),

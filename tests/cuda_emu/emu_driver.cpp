@@ -57,7 +57,7 @@ struct Rank
   std::vector<unsigned long long> ts;
   std::vector<unsigned char> work; // in-place working copy
   BarrierState* bar = nullptr;
-  unsigned char* xblock = nullptr; // exchange block: 128 B flags + 2 x N floats
+  unsigned char* xblock = nullptr; // exchange block: ExchangeHeader + 2 x N floats
   float scalars[16] = {};
   unsigned grid = 1, threads = 32;
   size_t smem = 0;
@@ -123,8 +123,9 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
     std::vector<Rank> R(world);
     for (uint32_t g = 0; g < world; g++) {
       Rank& r = R[g];
-      r.xblock = static_cast<unsigned char*>(aligned_alloc(128, 128 + 2 * nvec * sizeof(float)));
-      memset(r.xblock, 0, 128 + 2 * nvec * sizeof(float));
+      r.xblock = static_cast<unsigned char*>(aligned_alloc(128, sizeof(ExchangeHeader) + 2 * nvec * sizeof(float)));
+      memset(r.xblock, 0, sizeof(ExchangeHeader) + 2 * nvec * sizeof(float));
+      reinterpret_cast<ExchangeHeader*>(r.xblock)->arrive = 3ull * world * kArriveUnits; // == arrive_base below
       r.bar = static_cast<BarrierState*>(aligned_alloc(128, sizeof(BarrierState)));
       memset(r.bar, 0, sizeof(BarrierState));
     }
@@ -157,10 +158,18 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
       p.world = world;
       if (world > 1) {
         for (uint32_t h = 0; h < world; h++) {
-          p.peer_S[0][h] = reinterpret_cast<float*>(R[h].xblock + 128);
-          p.peer_S[1][h] = reinterpret_cast<float*>(R[h].xblock + 128) + nvec;
+          p.peer_S[0][h] = reinterpret_cast<float*>(R[h].xblock + sizeof(ExchangeHeader));
+          p.peer_S[1][h] = reinterpret_cast<float*>(R[h].xblock + sizeof(ExchangeHeader)) + nvec;
           p.peer_flags[h] = reinterpret_cast<unsigned long long*>(R[h].xblock);
+          ExchangeHeader* hd = reinterpret_cast<ExchangeHeader*>(R[h].xblock);
+          p.peer_arrive[h] = &hd->arrive;
+          p.peer_smax3[h] = hd->smax3;
         }
+        // flat barrier unless sweep bit 4 asks for the forwarding protocol; as if earlier solves had left the
+        // counters somewhere (every rank's counter starts from the same total, any round offset must work)
+        p.xbar = (o->sweep & 16) ? 0u : 1u;
+        p.round_base = 5ull + (o->max_iter % 3u);
+        p.arrive_base = 3ull * world * kArriveUnits;
         p.S[0] = p.peer_S[0][g];
         p.S[1] = p.peer_S[1][g];
         p.flags = p.peer_flags[g];

@@ -49,6 +49,33 @@ red_release_gpu_add(unsigned int* p, unsigned int v)
 {
   __atomic_fetch_add(p, v, __ATOMIC_RELEASE);
 }
+inline void
+red_relaxed_sys_add(unsigned long long* p, unsigned long long v)
+{
+  __atomic_fetch_add(p, v, EMU_RELAXED_STORE);
+}
+inline void
+red_relaxed_sys_max(unsigned int* p, unsigned int v)
+{
+  unsigned int cur = __atomic_load_n(p, EMU_RELAXED_LOAD);
+  while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, true, EMU_RELAXED_STORE, EMU_RELAXED_LOAD))
+    ;
+}
+inline void
+fence_acq_rel_sys()
+{
+  __atomic_thread_fence(__ATOMIC_ACQ_REL);
+}
+inline unsigned int
+ld_relaxed_sys(const unsigned int* p)
+{
+  return __atomic_load_n(p, EMU_RELAXED_LOAD);
+}
+inline void
+st_relaxed_sys(unsigned int* p, unsigned int v)
+{
+  __atomic_store_n(p, v, EMU_RELAXED_STORE);
+}
 
 inline float4 ld_stream(const float4* p) { return *p; }
 inline float ld_stream(const float* p) { return *p; }

@@ -162,12 +162,22 @@ def test_bf16_conversion_kernel():
 
 
 # ---- several emulated GPUs: the fused exchange and its flag barrier ---------------------------------------
+# sweep bit 4 selects the forwarding-flag protocol instead of the flat barrier (every CTA arrives at every GPU itself)
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kernel", [1, 13])
-def test_row_block_sharding_is_bit_identical_to_one_gpu(world, kernel):
+@pytest.mark.parametrize("sweep", [1, 17])
+def test_row_block_sharding_is_bit_identical_to_one_gpu(world, kernel, sweep):
     for dim, form in ((1000, 0), (640, 0)) + (((1001, 1),) if kernel == 1 else ()):
         mat = U(dim)
-        same_bits(emu.solve(mat, dim, kernel=kernel, threads=64, ctas=2, world=world, form=form), expect(mat, form))
+        same_bits(emu.solve(mat, dim, kernel=kernel, threads=64, ctas=2, world=world, form=form, sweep=sweep), expect(mat, form))
+
+
+def test_flat_barrier_with_unequal_grids():
+    # 33 rows on 2 GPUs: 16 and 17 rows, one warp per CTA -> the ranks run 16 and 17 CTAs; each GPU still adds
+    # exactly kArriveUnits per round.  Hilbert: a dozen rounds, so the three max slots go round several times.
+    H = oracle.hilbert(36)
+    same_bits(emu.solve(H, 36, kernel=13, threads=32, ctas=64, world=2), expect(H))
+    same_bits(emu.solve(H, 36, kernel=1, threads=32, ctas=64, world=3), expect(H))
 
 
 def test_sharded_extras():
