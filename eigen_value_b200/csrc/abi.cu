@@ -86,7 +86,7 @@ as_shard(void* p)
   return static_cast<Shard*>(p);
 }
 
-constexpr size_t kFlagBytes = st::kExchangeHeaderBytes; // flag words, arrival counter, max slots: one 128-byte line each
+constexpr size_t kFlagBytes = st::kExchangeHeaderBytes; // arrival counter, max slots: one 128-byte line each
 
 // ---- device group: several GPUs behind ONE handle --------------------------------------------------
 // st_group_attach (or ST_DEVICES in make_queue's environment) binds helper contexts on other GPUs to a

@@ -110,18 +110,12 @@ struct RoundParams
   // row-block sharding (world == 1: unused)
   uint32_t rank, world;
   float* peer_S[2][kMaxWorld];            // S buffers of every rank (own entry == S[b])
-  unsigned long long* peer_flags[kMaxWorld]; // flag array of every rank: 2 x kMaxWorld words, slot [parity][src rank]
-  unsigned long long* flags;              // this rank's flag array (written by the peers)
-  uint32_t seq_base;                      // (solve counter & 0xff) << 24: flags are never reset between solves
-  uint32_t flip;                          // parity offset of this solve: round k uses buffer / flag set (k + flip) & 1, so that
+  unsigned long long* peer_arrive[kMaxWorld]; // arrival counter of every rank (ExchangeHeader::arrive)
+  unsigned int* peer_smax3[kMaxWorld];        // max slots of every rank (ExchangeHeader::smax3)
+  unsigned long long arrive_base;         // what this group's counters had reached before this solve
+  unsigned long long round_base;          // rounds this group ran before this solve (slot = (round_base + k) % 3)
+  uint32_t flip;                          // parity offset of this solve: round k uses buffer set (k + flip) & 1, so that
                                           // a rank that starts the next solve early never touches what a slower peer still reads
-  // flat cross-GPU barrier (xbar == 1): every CTA of every GPU arrives at every GPU's counter itself
-  uint32_t xbar;                              // 0: per-GPU flags forwarded by the completing CTA; 1: flat
-  uint32_t xbar_sc_fence;                     // flat: 1 = sequentially consistent system fence before the arrivals (experiment)
-  unsigned long long* peer_arrive[kMaxWorld]; // monotonic arrival counter of every rank (kArriveUnits per GPU and round)
-  unsigned int* peer_smax3[kMaxWorld];        // max of the published row sums (float bits), three slots rotating by round
-  unsigned long long arrive_base;             // what this group's counters had reached before this solve
-  unsigned long long round_base;              // rounds this group ran before this solve (slot = (round_base + k) % 3)
   // results
   float* out_eigen_vec;  // N floats (device)
   float* out_eigen_val;  // 1 float  (device)
@@ -461,19 +455,25 @@ row_pass_inplace(const float* __restrict__ src, float* dst, const float* sc_s, f
 // Every CTA has written its row sums (locally and into every peer's S buffer) and knows the largest one it
 // published (*s_cta_max: the bits of a non-negative, non-NaN float, so unsigned order = numeric order; kernels
 // that compute the max in their own vector tail pass nullptr and ignore *s_m).
-//   arrive  : atomicMax of ((k + 1) << 32 | bits) into smax[parity], then one release-add on the monotonic
-//             arrival counter (preceded by a system fence when sharded: the CTA's peer stores come first).
-//   sharded : the CTA whose arrival completes the GPU forwards ONE 64-bit word per peer,
-//             (seq << 32) | bits of this GPU's max, with relaxed system-scope stores issued back to back
-//             (a release store per peer would serialise one NVLink round trip per peer).
-//   wait    : EVERY CTA polls the local counter and, when sharded, the G - 1 flag words the peers wrote into
-//             this GPU's memory (acquire loads at system scope) -- no second hop through a generation word.
+//   one GPU : atomicMax of ((k + 1) << 32 | bits) into smax[parity] -- the round tag makes the word monotonic, so it
+//             is never reset -- then one release-add on the monotonic arrival counter; every CTA polls the counter.
+//   sharded : a FLAT barrier over the CTAs of all GPUs.  Every CTA folds its max into every GPU's slot of the round
+//             and then arrives at every GPU's counter itself (fire-and-forget reductions over NVLink, peers first);
+//             ONE release/acquire system fence in between orders the CTA's peer stores of s (ordered before thread
+//             0 by the __syncthreads) and the max before the arrivals.  A waiter polls one word in its own memory:
+//             no completing CTA, no forwarding hop, no per-peer flag words.  The counters are never reset (a
+//             solve starts from the total its group has reached); the max slots rotate by round: the slot of round
+//             r is cleared by its GPU's CTA 0 once barrier r + 1 has been passed (every reader of it has arrived
+//             there) and is next written in round r + 3 by CTAs that passed barrier r + 2 -- which CTA 0 only
+//             arrives at after the clear.
 //   result  : *s_m = max(0, max_r s[r]) over all GPUs = the reference's find_max (:154-227), so the vector
 //             tail needs a single pass over s (stop test and eigenvector update together).
-// Flags and smax are indexed by the parity of k + flip and tagged with a monotonic sequence number, so they
-// are never reset -- not between rounds, not between solves.  All waits are bounded by timeout_ns (checked
-// every 1024 polls) so that a missing rank turns into an error code instead of a hung GPU.  Returns false on
-// timeout or when another CTA reported one.
+// S and E are indexed by the parity of k + flip.  All waits are bounded by timeout_ns (checked every 1024 polls)
+// so that a missing rank turns into an error code instead of a hung GPU.  Returns false on timeout or when
+// another CTA reported one.
+// Measured against the protocol it replaced (this GPU's last CTA forwards one flag word per peer, every CTA polls
+// G - 1 flags): 89.5 instead of 90.4 us per round at Hilbert 32768 on 8 GPUs, 84.7 instead of 85.8 at Hilbert
+// 16384 on 2 (profiles/r2_c21_ab_barrier_8gpu.json, r2_c20_ab_barrier_2gpu.json).
 
 struct SpinClock
 {
@@ -495,16 +495,13 @@ struct SpinClock
   }
 };
 
-constexpr uint32_t kFlagSlots = 2u * (uint32_t)kMaxWorld; // 64-bit words in a rank's flag array
-
-// Head of a rank's exchange block (mapped into every peer): the flag words of the forwarding protocol and the
-// words of the flat barrier, each on a line of its own; the two row-sum buffers follow.
+// Head of a rank's exchange block (mapped into every peer), each word group on a line of its own; the two
+// row-sum buffers follow.
 struct alignas(128) ExchangeHeader
 {
-  unsigned long long flags[kFlagSlots];
-  unsigned long long arrive; // flat barrier: + kArriveUnits per GPU and round, never reset
+  unsigned long long arrive; // + kArriveUnits per GPU and round, never reset
   unsigned long long pad0[15];
-  unsigned int smax3[3];     // flat barrier: slot r % 3 holds round r's max; reset two rounds ahead of its next use
+  unsigned int smax3[3];     // slot r % 3 holds round r's max (float bits); cleared two rounds ahead of its next use
   unsigned int pad1[29];
 };
 // A GPU's CTAs add up to exactly this much per round whatever its grid size is (ranks of tiny problems can run
@@ -525,28 +522,29 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned 
       cta_max_bits = *s_cta_max;
       *s_cta_max = 0u;
     }
-    const uint32_t par = (k + p.flip) & 1u;
-    const unsigned int target = (k + 1u) * gridDim.x;
-    const unsigned long long tag = (unsigned long long)(k + 1u) << 32;
     SpinClock clk;
-    if (p.world > 1 && p.xbar == 1u) {
-      // ---- flat barrier: no completing CTA, no forwarding hop.  Every CTA folds its max into every GPU's slot of
-      // the round and then arrives at every GPU's counter (peers first: their stores have the longer way); ONE system
-      // fence in between orders the CTA's peer stores of s and the max before the arrivals.  A waiter polls one
-      // word in its own memory.  The slot of round r is cleared by this GPU's CTA 0 once barrier r + 1 has been
-      // passed (every reader of it has arrived there) and is next written in round r + 3, by CTAs that passed
-      // barrier r + 2 -- which CTA 0 only arrives at after the clear.
+    uint32_t bits;
+    if (p.world == 1) {
+      const uint32_t par = (k + p.flip) & 1u;
+      const unsigned int target = (k + 1u) * gridDim.x;
+      atomicMax(&p.bar->smax[par], ((unsigned long long)(k + 1u) << 32) | cta_max_bits);
+      red_release_gpu_add(&p.bar->count, 1u);
+      while (ld_acquire_gpu(&p.bar->count) < target) {
+        if (clk.expired(p.timeout_ns, &p.bar->error)) {
+          fail = 1;
+          break;
+        }
+      }
+      bits = (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
+    } else {
       const unsigned long long r = p.round_base + k;
       const uint32_t slot = (uint32_t)(r % 3ull);
-      if (cta_max_bits != 0u)
+      if (cta_max_bits != 0u) // the slots start from 0 = the reference's zero-filled max cell (:169)
         for (uint32_t i = 1; i <= p.world; i++) {
           const uint32_t g = p.rank + i < p.world ? p.rank + i : p.rank + i - p.world;
           red_relaxed_sys_max(p.peer_smax3[g] + slot, cta_max_bits);
         }
-      if (p.xbar_sc_fence)
-        __threadfence_system();
-      else
-        fence_acq_rel_sys();
+      fence_acq_rel_sys();
       const unsigned long long inc =
         kArriveUnits * (blockIdx.x + 1u) / gridDim.x - kArriveUnits * blockIdx.x / gridDim.x;
       for (uint32_t i = 1; i <= p.world; i++) {
@@ -560,62 +558,15 @@ round_barrier(const RoundParams& p, uint32_t k, volatile int* s_abort, unsigned 
           break;
         }
       }
-      const uint32_t bits = ld_relaxed_sys(p.peer_smax3[p.rank] + slot);
+      bits = ld_relaxed_sys(p.peer_smax3[p.rank] + slot);
       if (blockIdx.x == 0)
         st_relaxed_sys(p.peer_smax3[p.rank] + (slot + 2u) % 3u, 0u); // round r - 1's slot, next used in round r + 2
-      if (fail)
-        atomicExch(&p.bar->error, 1u);
-      if (s_m)
-        *s_m = __uint_as_float(bits);
-      *s_abort = fail;
-    } else {
-    atomicMax(&p.bar->smax[par], tag | cta_max_bits);
-    if (p.world == 1) {
-      red_release_gpu_add(&p.bar->count, 1u);
-    } else {
-      __threadfence_system(); // this CTA's peer stores (ordered before here by the __syncthreads) come before its arrival
-      const unsigned int prev = atomicAdd(&p.bar->count, 1u);
-      if (prev + 1u == target) {
-        // ONE system fence orders every CTA's peer stores (observed through the arrival counter) before the
-        // flag stores; the flags carry this GPU's max along
-        __threadfence_system();
-        const unsigned long long mine = atomicMax(&p.bar->smax[par], 0ull); // atomic read
-        const unsigned long long word =
-          ((unsigned long long)(p.seq_base + k + 1u) << 32) | (mine & 0xffffffffull);
-        for (uint32_t g = 0; g < p.world; g++)
-          if (g != p.rank)
-            st_relaxed_sys(p.peer_flags[g] + par * (uint32_t)kMaxWorld + p.rank, word);
-      }
-    }
-    while (ld_acquire_gpu(&p.bar->count) < target) {
-      if (clk.expired(p.timeout_ns, &p.bar->error)) {
-        fail = 1;
-        break;
-      }
-    }
-    uint32_t bits = (uint32_t)(ld_relaxed_gpu(&p.bar->smax[par]) & 0xffffffffull);
-    if (p.world > 1) {
-      const uint32_t want = p.seq_base + k + 1u;
-      for (uint32_t g = 0; g < p.world && !fail; g++) {
-        if (g == p.rank)
-          continue;
-        unsigned long long v;
-        // sequence numbers compare modulo 2^32 (the solve counter wraps after 256 solves)
-        while ((int32_t)((uint32_t)((v = ld_acquire_sys(p.flags + par * (uint32_t)kMaxWorld + g)) >> 32) - want) < 0) {
-          if (clk.expired(p.timeout_ns, &p.bar->error)) {
-            fail = 1;
-            break;
-          }
-        }
-        bits = max(bits, (uint32_t)(v & 0xffffffffull));
-      }
     }
     if (fail)
       atomicExch(&p.bar->error, 1u);
     if (s_m)
       *s_m = __uint_as_float(bits);
     *s_abort = fail;
-    }
   }
   __syncthreads();
   return *s_abort == 0;

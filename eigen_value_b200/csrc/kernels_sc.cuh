@@ -82,11 +82,17 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return (float)warp_sum(acc[0]);
 }
 
-template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float>
+// VEC = 1: dim % 4 != 0 (or a matrix that is not 16-byte aligned).  Rows then start on 4-byte boundaries, the unit of
+// the evaluation order is a single float (element j of a chunk -> lane j % 32, accumulator (j / 32) % 8: the order
+// round_loop_kernel<1, ...> and the oracle's SUM_CUDA already use for these dimensions), the matrix is streamed with
+// 32 scalar loads in flight per lane, there are no prefetch slots (bulk copies need 16-byte alignment) and the vector
+// tail reads s with 4-byte loads.  Everything else -- units, scheduling, publication, barrier -- is shared.
+template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float, int VEC = 4>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
   constexpr int LD = kUnroll; // independent 128-bit loads in flight per lane (16 measured no better, profiles/r1_sweep_resident_e_variants.txt)
   static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
+  static_assert(VEC == 4 || (VEC == 1 && PF_BATCHES == 0 && sizeof(T) == 4), "scalar units: fp32 storage, no prefetch slots");
   // bf16 storage (p.A points to bf16 data, N % 8 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -224,7 +230,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
             npre = seg_nv; // landed before round 0 and never evicted
           }
           float t;
-          if (kBf16) {
+          if (VEC == 1) {
+            t = row_dot_readonly<1, false, ACC>(p.A + (size_t)rl * N + (size_t)ch * kChunkCols, e_s + (size_t)ch * kChunkCols,
+                                                min((uint32_t)kChunkCols, N - ch * (uint32_t)kChunkCols), lane);
+          } else if (kBf16) {
             // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
             const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +
                                  ch * (kChunkVec >> 1);
@@ -306,32 +315,47 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     const uint32_t rotv = cb >> 2;
     const float thr = STOP == kStopRelative ? p.eps * m_k : p.eps;
     int ok = 1;
+    // scalar units (N % 4 != 0) scan s in 128-bit vectors too -- s and e are this kernel's own, 16-byte aligned and
+    // padded buffers; only the LAST vector is partial (N - 4 (nvt - 1) valid elements, see below)
+    const uint32_t nvt = VEC == 4 ? nv : (N + 3u) >> 2;
     auto vec_index = [&](uint32_t idx) {
       const uint32_t v = idx + rotv;
-      return v < nv ? v : v - nv;
+      return v < nvt ? v : v - nvt;
     };
     constexpr int kTailBatch = 8;
-    for (uint32_t v0 = 0; v0 < nv; v0 += (uint32_t)kTailBatch * THREADS) {
+    for (uint32_t v0 = 0; v0 < nvt; v0 += (uint32_t)kTailBatch * THREADS) {
       float4 t4[kTailBatch];
       float nx[kTailBatch];
 #pragma unroll
       for (int j = 0; j < kTailBatch; j++) {
         const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-        const bool active = idx < nv;
+        const bool active = idx < nvt;
         const uint32_t vi = vec_index(idx);
         t4[j] = active ? ld_cg(S4 + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool edge = active && (lane == 31 || idx + 1u >= nv);
-        nx[j] = edge ? ld_cg(Scur + (vi + 1u == nv ? 0u : 4u * (vi + 1u))) : 0.f;
+        const bool edge = active && (lane == 31 || idx + 1u >= nvt);
+        nx[j] = edge ? ld_cg(Scur + (vi + 1u == nvt ? 0u : 4u * (vi + 1u))) : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < kTailBatch; j++) {
         const uint32_t idx = v0 + tid + (uint32_t)j * THREADS;
-        if (v0 + (uint32_t)j * THREADS < nv) { // warp-uniform
+        if (v0 + (uint32_t)j * THREADS < nvt) { // warp-uniform
           float nxt = __shfl_down_sync(0xffffffffu, t4[j].x, 1);
-          if (lane == 31 || idx + 1u >= nv)
+          if (lane == 31 || idx + 1u >= nvt)
             nxt = nx[j];
-          if (idx < nv) {
-            const float4 v = t4[j];
+          if (idx < nvt) {
+            float4 v = t4[j];
+            if (VEC == 1 && vec_index(idx) == nvt - 1u) {
+              // partial last vector: its circular successor is s[0] (= nxt here: the next vector is vector 0).  The
+              // padding takes that value, so the pairs past the last element compare s[0] with itself -- they pass
+              // exactly when the wrap pair's s[0] is not NaN -- and the padding of e is updated but never read.
+              const uint32_t valid = N - 4u * (nvt - 1u);
+              if (valid < 2u)
+                v.y = nxt;
+              if (valid < 3u)
+                v.z = nxt;
+              if (valid < 4u)
+                v.w = nxt;
+            }
             // strict <, wrap pair included (:413-421).  Relative test: every pair below eps * m is the same
             // statement as "the largest difference is below eps * m" (a NaN difference fails either way)
             ok &= (fabsf(v.x - v.y) < thr) & (fabsf(v.y - v.z) < thr) & (fabsf(v.z - v.w) < thr) &

@@ -54,18 +54,12 @@ ld_acquire_sys(const unsigned long long* p)
 }
 
 __device__ __forceinline__ void
-st_relaxed_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ void
 red_release_gpu_add(unsigned int* p, unsigned int v)
 {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Flat cross-GPU barrier: fire-and-forget reductions at system scope, onto this GPU's or a peer's memory
+// Cross-GPU barrier: fire-and-forget reductions at system scope, onto this GPU's or a peer's memory
 // (over NVLink the atomic is performed at the owner's L2, like a local one)
 __device__ __forceinline__ void
 red_relaxed_sys_add(unsigned long long* p, unsigned long long v)
@@ -79,7 +73,8 @@ red_relaxed_sys_max(unsigned int* p, unsigned int v)
   asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// release/acquire fence at system scope (MEMBAR.ALL.SYS); __threadfence_system() is the sequentially consistent one
+// release/acquire fence at system scope (MEMBAR.ALL.SYS; the sequentially consistent __threadfence_system()
+// measured the same, profiles/r2_c21_ab_barrier_8gpu.json)
 __device__ __forceinline__ void
 fence_acq_rel_sys()
 {
@@ -177,6 +172,44 @@ f32_to_bf16_rn(float x)
   unsigned short h;
   asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
   return h;
+}
+
+// ---- fp8 (e4m3) storage of the matrix ---------------------------------------------------------------
+// Four consecutive elements (lowest address = lowest byte of the word) -> fp32.  e4m3 -> f16 -> f32 is exact at
+// both steps (4 exponent / 3 mantissa bits fit f16's 5 / 10), subnormals included.
+__device__ __forceinline__ float4
+fp8x4_to_float4(uint32_t w)
+{
+  uint32_t h0, h1;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "cvt.rn.f16x2.e4m3x2 %0, lo;\n\t"
+      "cvt.rn.f16x2.e4m3x2 %1, hi;\n\t}"
+      : "=r"(h0), "=r"(h1)
+      : "r"(w));
+  float4 f;
+  asm("{\n\t.reg .b16 a, b;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "cvt.f32.f16 %0, a;\n\t"
+      "cvt.f32.f16 %1, b;\n\t}"
+      : "=f"(f.x), "=f"(f.y)
+      : "r"(h0));
+  asm("{\n\t.reg .b16 a, b;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "cvt.f32.f16 %0, a;\n\t"
+      "cvt.f32.f16 %1, b;\n\t}"
+      : "=f"(f.z), "=f"(f.w)
+      : "r"(h1));
+  return f;
+}
+
+// two floats -> two e4m3 codes, round to nearest even, saturating at +-448 (NaN -> 0x7f); `lo` lands in the low byte
+__device__ __forceinline__ unsigned short
+f32x2_to_fp8x2(float lo, float hi)
+{
+  unsigned short r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // ---- TMA bulk copies and their mbarriers ----------------------------------------------------------

@@ -137,10 +137,10 @@ private:
   std::vector<uint64_t> last_phase_ts_;
 };
 
-// bytes of the exchange block's head (kernels.cuh: ExchangeHeader -- flag words, arrival counter, max slots)
-constexpr size_t kExchangeHeaderBytes = 384;
+// bytes of the exchange block's head (kernels.cuh: ExchangeHeader -- arrival counter and max slots of the round barrier)
+constexpr size_t kExchangeHeaderBytes = 256;
 
-// Row-block shard: this rank's exchange block (two N-float row-sum buffers + flags) and the
+// Row-block shard: this rank's exchange block (barrier words + two N-float row-sum buffers) and the
 // mapped blocks of the peers.
 struct Shard
 {
@@ -154,9 +154,9 @@ struct Shard
   bool peer_is_ipc[ST_MAX_WORLD] = {};
   bool linked = false;
   uint64_t solves = 0;
-  uint32_t flip = 0; // parity offset of the next solve's exchange buffers and flag sets (RoundParams::flip)
-  uint64_t arrive_total = 0; // flat barrier: what every rank's arrival counter reads between solves
-  uint64_t rounds_total = 0; // flat barrier: rounds run so far (the max slots rotate by round)
+  uint32_t flip = 0; // parity offset of the next solve's exchange buffers (RoundParams::flip)
+  uint64_t arrive_total = 0; // what every rank's arrival counter reads between solves (never reset)
+  uint64_t rounds_total = 0; // rounds run so far (the barrier's max slots rotate by round)
 };
 
 } // namespace st

@@ -580,27 +580,18 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       char* base = static_cast<char*>(shard->peer_block[g]);
       p.peer_S[0][g] = reinterpret_cast<float*>(base + shard->s_offset[0]);
       p.peer_S[1][g] = reinterpret_cast<float*>(base + shard->s_offset[1]);
-      p.peer_flags[g] = reinterpret_cast<unsigned long long*>(base);
-    }
-    p.S[0] = p.peer_S[0][shard->rank];
-    p.S[1] = p.peer_S[1][shard->rank];
-    p.flags = p.peer_flags[shard->rank];
-    // flags are never reset: their sequence numbers carry the solve counter in the top 8 bits (compared modulo
-    // 2^32) and the round in the low 24; buffers and flag sets start from the parity the last solve did NOT end on
-    shard->solves += 1;
-    p.seq_base = (uint32_t)(shard->solves & 0xffu) << 24;
-    p.flip = shard->flip;
-    // flat barrier (default; st_options.sweep bit 4 selects the forwarding protocol of the first half of round 2):
-    // counters and max slots sit in the exchange blocks and are never reset, the group's totals carry over
-    p.xbar = (opt.sweep & 16) ? 0u : 1u;
-    p.xbar_sc_fence = (opt.sweep & 32) ? 1u : 0u;
-    for (uint32_t g = 0; g < shard->world; g++) {
-      ExchangeHeader* h = static_cast<ExchangeHeader*>(shard->peer_block[g]);
+      ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(base);
       p.peer_arrive[g] = &h->arrive;
       p.peer_smax3[g] = h->smax3;
     }
+    p.S[0] = p.peer_S[0][shard->rank];
+    p.S[1] = p.peer_S[1][shard->rank];
+    // the barrier words are never reset: a solve starts from the totals its group has reached; S buffers start from
+    // the parity the last solve did NOT end on
+    shard->solves += 1;
     p.arrive_base = shard->arrive_total;
     p.round_base = shard->rounds_total;
+    p.flip = shard->flip;
     if (opt.max_iter >= (1u << 24) - 1u)
       throw std::invalid_argument("solve: a sharded solve supports max_iter below 2^24 - 1");
   }
@@ -647,25 +638,29 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     grid = cluster_ctas;
     threads = kClusterThreads;
   }
+  // scalar units (dim % 4 != 0 or a matrix off the 16-byte grid): the resident-e kernel without prefetch slots
+  // (configuration 11) streams them with 4-byte loads in the order the general loop uses for these dimensions
+  const bool readonly1 = !vec4 && form == kFormReadOnly && !bf16 && !acc64;
   if (!cluster_ctas && (is_sc_kernel_id(opt.kernel) ||
-                        (opt.kernel == 0 && readonly4 && dim <= (uint32_t)kResidentCols))) {
-    if (!readonly4 || dim > (uint32_t)kResidentCols)
-      throw std::invalid_argument("solve: resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
+                        (opt.kernel == 0 && (readonly4 || readonly1) && dim <= (uint32_t)kResidentCols))) {
+    if (!(readonly4 || (readonly1 && (opt.kernel == 0 || opt.kernel == kScBf16Id))) || dim > (uint32_t)kResidentCols)
+      throw std::invalid_argument("solve: resident-e kernel needs the read-only form and dim <= 32768; dim % 4 != 0 "
+                                  "runs on configuration 11 (fp32 storage and accumulation)");
     // Automatic slot size: one 4 KB batch per warp, unless a whole row fits a 2- or 3-batch slot
     // and no warp would own more than one row -- then the rows stay in shared memory for the
     // whole solve (matrix resident on chip, N <= ~2368 on 148 SMs).
     int want_pf = 1;
     if (opt.kernel == 0 && dim > 1024u && dim <= 3072u && (uint64_t)rows <= (uint64_t)sm_count_ * 16u)
       want_pf = (int)((dim + 1023u) / 1024u);
-    if (bf16)
-      want_pf = 0; // bf16 storage is built without prefetch slots (configuration 11)
+    if (bf16 || readonly1)
+      want_pf = 0; // bf16 storage and scalar units are built without prefetch slots (configuration 11)
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
       if (opt.kernel == 0 && pinned > c.max_threads)
         continue;
-      if (bf16 && c.id != kScBf16Id)
-        continue; // bf16 storage is built for configuration 11 only
+      if ((bf16 || readonly1) && c.id != kScBf16Id)
+        continue; // bf16 storage and scalar units are built for configuration 11 only
       if (opt.kernel == 0 && !bf16 && acc64 && c.id == kScBf16Id)
         continue; // fp64 accumulation is built for the configurations with prefetch slots
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
@@ -765,6 +760,11 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_cluster<kStopRelative>(p, cluster_ctas, smem, stream_);
     else
       launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
+  } else if (sc && readonly1) {
+    if (stop == kStopRelative)
+      launch_cooperative(round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>, p, grid, threads, smem, stream_);
+    else
+      launch_cooperative(round_loop_sc_kernel<512, 0, kStopAbsolute, float, float, 1>, p, grid, threads, smem, stream_);
   } else if (sc) {
     launch_sc(sc->id, stop, p, grid, threads, smem, stream_);
   } else if (wide) {
@@ -805,10 +805,8 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const uint32_t passes = words[2];
   if (shard) {
     shard->flip = (shard->flip + passes) & 1u; // every rank saw the same number of rounds
-    if (p.xbar == 1u) {
-      shard->arrive_total += (uint64_t)passes * shard->world * kArriveUnits;
-      shard->rounds_total += passes;
-    }
+    shard->arrive_total += (uint64_t)passes * shard->world * kArriveUnits;
+    shard->rounds_total += passes;
   }
   const uint32_t stamped = std::min<uint32_t>(passes, p.ts_rounds);
   last_ts_.assign((size_t)stamped + 1, 0);

@@ -107,9 +107,7 @@ typedef struct st_options
   int32_t sweep;     /* bit 0: alternate the row order every round so the tail of one pass is
                         the L2-resident head of the next (default on); bit 1 / bit 2: force
                         static / dynamic work-unit scheduling in the unit-scheduled kernels; bit 3:
-                        no in-kernel time stamps; bit 4: sharded solves cross the round barrier with
-                        per-GPU flags forwarded by the last CTA instead of the flat barrier (every
-                        rank must pass the same value)                                           */
+                        no in-kernel time stamps                                                 */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
   int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, one GPU), resident-e

@@ -160,20 +160,16 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         for (uint32_t h = 0; h < world; h++) {
           p.peer_S[0][h] = reinterpret_cast<float*>(R[h].xblock + sizeof(ExchangeHeader));
           p.peer_S[1][h] = reinterpret_cast<float*>(R[h].xblock + sizeof(ExchangeHeader)) + nvec;
-          p.peer_flags[h] = reinterpret_cast<unsigned long long*>(R[h].xblock);
           ExchangeHeader* hd = reinterpret_cast<ExchangeHeader*>(R[h].xblock);
           p.peer_arrive[h] = &hd->arrive;
           p.peer_smax3[h] = hd->smax3;
         }
-        // flat barrier unless sweep bit 4 asks for the forwarding protocol; as if earlier solves had left the
-        // counters somewhere (every rank's counter starts from the same total, any round offset must work)
-        p.xbar = (o->sweep & 16) ? 0u : 1u;
+        // as if earlier solves had left the barrier words somewhere (every rank's counter starts from the same total,
+        // any round offset must work)
         p.round_base = 5ull + (o->max_iter % 3u);
         p.arrive_base = 3ull * world * kArriveUnits;
         p.S[0] = p.peer_S[0][g];
         p.S[1] = p.peer_S[1][g];
-        p.flags = p.peer_flags[g];
-        p.seq_base = 1u << 24;
         p.flip = (uint32_t)(o->max_iter & 1u); // either parity offset must work
       }
       p.out_eigen_val = r.scalars;
@@ -200,8 +196,9 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         r.smem = sizeof(float) * ((size_t)p.chunk_cols + cap);
         kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64);
       } else if (kid >= 10 && kid <= 13) {
-        if (!vec4 || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
-          throw std::string("resident-e kernel needs the read-only form, dim % 4 == 0, dim <= 32768");
+        const bool scalar_units = !vec4 && kid == 11 && !bf16 && !acc64; // dim % 4 != 0: configuration 11, 4-byte units
+        if ((!vec4 && !scalar_units) || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
+          throw std::string("resident-e kernel needs the read-only form, dim <= 32768 and dim % 4 == 0 (configuration 11: any dim)");
         int pf = -1;
         for (const ScConfig& c : kScConfigs)
           if (c.id == kid)
@@ -225,6 +222,9 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.row_done = r.row_done.data();
         }
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
+        if (scalar_units)
+          kernel = o->stop ? round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>
+                           : round_loop_sc_kernel<512, 0, kStopAbsolute, float, float, 1>;
       } else if (kid == 2) {
         // wide kernel: windows of p.chunk_cols columns (kResidentCols; ST_EMU_WINDOW stages less so that several
         // windows fit an emulated size), chunk sums + per-row counters + one unit counter per window

@@ -40,11 +40,6 @@ ld_acquire_sys(const unsigned long long* p)
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
 inline void
-st_relaxed_sys(unsigned long long* p, unsigned long long v)
-{
-  __atomic_store_n(p, v, EMU_RELAXED_STORE);
-}
-inline void
 red_release_gpu_add(unsigned int* p, unsigned int v)
 {
   __atomic_fetch_add(p, v, __ATOMIC_RELEASE);
@@ -94,6 +89,58 @@ f32_to_bf16_rn(float x)
   if ((u & 0x7fffffffu) > 0x7f800000u)
     return 0x7fffu;
   return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+// e4m3 (fn variant: no infinities, 0x7f / 0xff = NaN): value of one code
+inline float
+emu_fp8_value(unsigned char c)
+{
+  const int e = (c >> 3) & 15, m = c & 7;
+  float v;
+  if (e == 15 && m == 7)
+    v = NAN;
+  else if (e == 0)
+    v = ldexpf((float)m, -9);
+  else
+    v = ldexpf(1.f + (float)m / 8.f, e - 7);
+  return (c & 0x80) ? -v : v;
+}
+inline float4
+fp8x4_to_float4(uint32_t w)
+{
+  return make_float4(emu_fp8_value((unsigned char)w), emu_fp8_value((unsigned char)(w >> 8)),
+                     emu_fp8_value((unsigned char)(w >> 16)), emu_fp8_value((unsigned char)(w >> 24)));
+}
+// cvt.rn.satfinite.e4m3x2.f32: nearest code, ties to the even code, saturating at 448; NaN -> 0x7f
+inline unsigned char
+emu_f32_to_fp8(float x)
+{
+  if (x != x)
+    return 0x7f;
+  const unsigned char sign = std::signbit(x) ? 0x80 : 0x00;
+  const float a = fabsf(x);
+  if (a >= 448.f)
+    return sign | 0x7e;
+  unsigned char lo = 0, hi = 0x7e; // largest code <= a, by bisection over the monotonic code values
+  while (lo < hi) {
+    const unsigned char mid = (unsigned char)((lo + hi + 1) / 2);
+    if (emu_fp8_value(mid) <= a)
+      lo = mid;
+    else
+      hi = (unsigned char)(mid - 1);
+  }
+  unsigned char best = lo;
+  if (lo < 0x7e) {
+    const float dl = a - emu_fp8_value(lo), dh = emu_fp8_value((unsigned char)(lo + 1)) - a;
+    if (dh < dl || (dh == dl && (lo & 1)))
+      best = (unsigned char)(lo + 1);
+  }
+  return sign | best;
+}
+inline unsigned short
+f32x2_to_fp8x2(float lo, float hi)
+{
+  return (unsigned short)(emu_f32_to_fp8(lo) | (emu_f32_to_fp8(hi) << 8));
 }
 
 inline uint32_t

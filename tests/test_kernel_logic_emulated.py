@@ -103,6 +103,29 @@ def test_rows_of_several_work_units(kernel, dynamic):
               expect(mat, max_iter=4))
 
 
+# ---- resident-e kernel on scalar units: dim % 4 != 0 (configuration 11, 4-byte loads, scalar vector tail) -----
+@pytest.mark.parametrize("dim,threads,ctas,dynamic", [(1, 32, 1, 0), (2, 32, 1, 1), (3, 32, 1, 0), (5, 32, 2, 1), (31, 64, 2, 0),
+                                                      (257, 96, 4, 1), (1001, 128, 3, 0), (1023, 64, 4, 1), (1030, 512, 2, 1)])
+def test_resident_e_kernel_on_scalar_units(dim, threads, ctas, dynamic):
+    mat = A3 if dim == 3 else U(dim)
+    want = expect(mat)
+    same_bits(emu.solve(mat, dim, kernel=11, threads=threads, ctas=ctas, dynamic=dynamic), want)
+    same_bits(emu.solve(mat, dim, kernel=1, threads=threads, ctas=ctas), want)       # the general loop's order, bit for bit
+
+
+def test_resident_e_kernel_on_scalar_units_extras():
+    mat = U(8195)                                                            # two units per row: 8192 + 3 columns
+    same_bits(emu.solve(mat, 8195, kernel=11, threads=128, ctas=6, dynamic=1, max_iter=3), expect(mat, max_iter=3))
+    same_bits(emu.solve(mat, 8195, kernel=11, threads=128, ctas=3, world=2, max_iter=3), expect(mat, max_iter=3))
+    mat = U(1001)                                                            # sharded, ranks of 333 / 334 / 334 rows
+    same_bits(emu.solve(mat, 1001, kernel=11, threads=64, ctas=3, world=3), expect(mat))
+    kw = dict(stop=1, eps=1e-6, max_iter=40)                                 # relative stop test
+    same_bits(emu.solve(mat, 1001, kernel=11, threads=64, ctas=2, **kw), expect(mat, **kw))
+    H = oracle.hilbert(1022)                                                 # a dozen rounds, alternating sweep on and off
+    for sweep in (0, 1):
+        same_bits(emu.solve(H, 1022, kernel=11, threads=96, ctas=5, sweep=sweep), expect(H))
+
+
 # ---- on-chip cluster kernel ---------------------------------------------------------
 @pytest.mark.parametrize("dim", [4, 8, 100, 128, 384, 512])
 def test_cluster_kernel_distributed_shared_memory(dim):
@@ -161,15 +184,13 @@ def test_bf16_conversion_kernel():
     assert np.array_equal(emu.convert_bf16(base[1:]), oracle.to_bf16(base[1:])[1])
 
 
-# ---- several emulated GPUs: the fused exchange and its flag barrier ---------------------------------------
-# sweep bit 4 selects the forwarding-flag protocol instead of the flat barrier (every CTA arrives at every GPU itself)
+# ---- several emulated GPUs: the fused exchange and its flat barrier ---------------------------------------
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kernel", [1, 13])
-@pytest.mark.parametrize("sweep", [1, 17])
-def test_row_block_sharding_is_bit_identical_to_one_gpu(world, kernel, sweep):
+def test_row_block_sharding_is_bit_identical_to_one_gpu(world, kernel):
     for dim, form in ((1000, 0), (640, 0)) + (((1001, 1),) if kernel == 1 else ()):
         mat = U(dim)
-        same_bits(emu.solve(mat, dim, kernel=kernel, threads=64, ctas=2, world=world, form=form, sweep=sweep), expect(mat, form))
+        same_bits(emu.solve(mat, dim, kernel=kernel, threads=64, ctas=2, world=world, form=form), expect(mat, form))
 
 
 def test_flat_barrier_with_unequal_grids():

@@ -46,8 +46,8 @@ def ev():
     return EigenValue()
 
 
-# on-chip cluster kernel (dim % 4 == 0, <= 512), resident-e kernel (dim % 4 == 0, <= 32768), general
-# loop with scalar loads (dim % 4 != 0); 8196 / 12288: rows of two work units
+# on-chip cluster kernel (dim % 4 == 0, <= 512), resident-e kernel (dim <= 32768; dim % 4 != 0 on its scalar-unit
+# build, configuration 11); 8196 / 12288: rows of two work units
 DIMS = [1, 2, 3, 4, 5, 31, 33, 100, 128, 257, 512, 640, 1000, 1023, 1024, 2048, 4100, 8192, 8196, 12288]
 
 
@@ -93,6 +93,21 @@ def test_every_kernel_family_is_bit_identical_to_the_oracle(solver, kernel):
     mat = _matrix("uniform", dim)
     info, vec = solver.solve_device(solver.upload(mat), dim, kernel=kernel, max_iter=8)
     _assert_same_bits((info.eigen_val, vec, info.iter_count), _oracle(mat, max_itr=8), f"kernel {kernel}")
+
+
+@pytest.mark.parametrize("dim", [5, 1001, 4099, 8191, 8195])
+def test_ragged_dims_run_on_the_resident_e_kernel_and_match_the_general_loop(solver, dim):
+    # dim % 4 != 0: automatic = resident-e configuration 11 on scalar units (dynamic work units, e in shared memory);
+    # the general loop (kernel 1) is the other kernel built for these dimensions -- same order, same bits, = the oracle
+    mat = _matrix("uniform", dim)
+    cap = 6 if dim > 4100 else 1000
+    d = solver.upload(mat)
+    info, vec = solver.solve_device(d, dim, max_iter=cap)
+    base, base_vec = solver.solve_device(d, dim, max_iter=cap, kernel=1)
+    assert info.kernel_id == 11 and base.kernel_id == 1
+    want = _oracle(mat, max_itr=cap)
+    _assert_same_bits((info.eigen_val, vec, info.iter_count), want, f"ragged {dim} resident-e")
+    _assert_same_bits((base.eigen_val, base_vec, base.iter_count), want, f"ragged {dim} general")
 
 
 def test_multi_chunk_16384_bit_identical(solver):

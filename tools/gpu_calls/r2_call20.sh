@@ -1,6 +1,8 @@
 #!/bin/bash
 # Round 2, call 20 (--gpus 2): the flat cross-GPU barrier (every CTA arrives at every GPU's counter itself) against the
 # forwarding-flag protocol (--sweep 17), same build, same box: sharded / group tests, A/B at three sizes, a short soak.
+# (Ran at commit d2515d7: the forwarding-flag protocol, its --sweep 17 switch and tools/ab_barrier.py were removed after this
+# measurement; check that commit out to repeat it.)
 set -u
 O=gpurun_out/r2c20; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_sharded.py tests/test_zzzz_gpu_group.py -m gpu -q -rs -x > $O/multigpu_pytest.txt 2>&1
