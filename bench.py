@@ -52,7 +52,7 @@ def parse_args():
                          "relative = extension, max adjacent diff < eps * max(s)")
     ap.add_argument("--accumulate", default="f32", choices=["f32", "f64"],
                     help="f32 = like the reference (default); f64 = opt-in fp64 accumulators, same evaluation order")
-    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16", "fp8"],
                     help="f32 = the reference's matrix format (default, the headline); bf16 = opt-in bfloat16 storage "
                          "of the matrix with fp32 accumulation (changes results; bytes counted at 2 per element)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto; 1 general loop; 2-9 TMA ring; 10-19 resident-e variants; 21-23 resident-e + L2 prefetch across the barrier")
@@ -386,8 +386,17 @@ def main():
     d_rows = solver.hilbert(dim, row0, rows) if kind == "hilbert" else solver.uniform(dim, seed, row0, rows)
     d_vec = solver.alloc(4 * dim)
     solver.synchronize()
+    fp8 = args.storage == "fp8"
+    d_scale = None
+    if fp8:
+        # opt-in storage format: e4m3 codes + one power-of-two scale per row, converted on the device (dim % 16 == 0)
+        d8, d_scale = solver.to_fp8(d_rows, rows, dim)
+        solver.synchronize()
+        d_rows.free()
+        d_rows = d8
+        args.no_e2e = True
     bf16 = args.storage == "bf16"
-    elem_bytes = 2 if bf16 else 4
+    elem_bytes = 1 if fp8 else 2 if bf16 else 4
     if bf16:
         # opt-in storage format: convert this rank's rows on the device, keep only the 2-byte copy
         d16 = solver.to_bf16(d_rows, rows * dim)
@@ -398,9 +407,9 @@ def main():
 
     def step():
         if sh is None:
-            info, _ = solver.solve_device(d_rows, dim, d_eigen_vec=d_vec, bf16=bf16, **opts)
+            info, _ = solver.solve_device(d_rows, dim, d_eigen_vec=d_vec, bf16=bf16, fp8_scale=d_scale, **opts)
         else:
-            info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, bf16=bf16, **opts)
+            info, _ = sh.solve(d_rows, d_eigen_vec=d_vec, bf16=bf16, fp8_scale=d_scale, **opts)
         return info
 
     # L2 hygiene: the shard is larger than L2 for the default workloads; smaller ones get a flush
@@ -465,7 +474,7 @@ def main():
     round_us = statistics.median(i.round_us_median for i in infos)
 
     # ---- parity verdict on the timed solves' result (default options only) ----
-    default_opts = (args.form == 0 and args.eps == 1e-3 and args.stop == "absolute" and not bf16
+    default_opts = (args.form == 0 and args.eps == 1e-3 and args.stop == "absolute" and not bf16 and not fp8
                     and args.accumulate == "f32")
     parity = None
     if default_opts and rank == 0:
@@ -550,7 +559,7 @@ def main():
     # (the driver's default N=1 call measures configs[1]'s roofline point, Hilbert 8192; its N>1 calls measure
     # configs[2], Hilbert 32768 row-block sharded -- this puts the 1-GPU figure of THAT workload in the same line)
     scale_base = None
-    if world == 1 and args.scale_base_dim > 0 and not args.no_sweep_table and not bf16:
+    if world == 1 and args.scale_base_dim > 0 and not args.no_sweep_table and not bf16 and not fp8:
         n = args.scale_base_dim
         d = solver.hilbert(n)
         d_v = solver.alloc(4 * n)
@@ -646,7 +655,8 @@ def main():
         peak, peak_src = measured_peak()
         agg_peak = peak * world
         line = {
-            "metric": ("per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside" if not bf16 else
+            "metric": ("per-round algorithmic HBM GB/s on fp8 storage (passes * N^2 B / loop time); ms_to_converge alongside" if fp8 else
+                       "per-round algorithmic HBM GB/s (passes * 4*N^2 B / loop time); ms_to_converge alongside" if not bf16 else
                        "per-round algorithmic HBM GB/s on bf16 storage (passes * 2*N^2 B / loop time); ms_to_converge alongside"),
             "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 5),
@@ -668,7 +678,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(value, 3), "peak": round(agg_peak, 1), "unit": "GB/s",
                          "frac": round(value / agg_peak, 4),
                          # the ncu captures are single-GPU launches; no capture exists for a shard
-                         "traffic": recorded_traffic(workload) if world == 1 and not bf16 else None,
+                         "traffic": recorded_traffic(workload) if world == 1 and not bf16 and not fp8 else None,
                          "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                          "kernel": f"{last.kernel_name} id {last.kernel_id}, {last.threads} threads x {last.grid} CTAs "
                                    "(one launch = one whole solve)",

@@ -104,6 +104,9 @@ SYMBOLS = {
     "st_convert_f32_to_bf16": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "st_solve_device_bf16": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP,
                                             ctypes.POINTER(StResult)]),
+    "st_convert_f32_to_fp8": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_uint32, ctypes.c_uint32]),
+    "st_solve_device_fp8": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_uint32, ctypes.POINTER(StOptions), _VP,
+                                           ctypes.POINTER(StResult)]),
     "st_round_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
     "st_phase_timestamps": (ctypes.c_int, [_VP, _VP, ctypes.c_uint32, c_u32p]),
     "st_timer_start": (ctypes.c_int, [_VP]),
@@ -125,6 +128,7 @@ SYMBOLS = {
     "st_shard_rows": (ctypes.c_int, [_VP, c_u32p, c_u32p]),
     "st_shard_solve": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(StOptions), _VP, ctypes.POINTER(StResult)]),
     "st_shard_solve_bf16": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(StOptions), _VP, ctypes.POINTER(StResult)]),
+    "st_shard_solve_fp8": (ctypes.c_int, [_VP, _VP, _VP, ctypes.POINTER(StOptions), _VP, ctypes.POINTER(StResult)]),
     "st_shard_destroy": (None, [_VP]),
 }
 

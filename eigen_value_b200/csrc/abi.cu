@@ -700,6 +700,35 @@ st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const st_op
 }
 
 int
+st_convert_f32_to_fp8(void* ctx, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows, uint32_t dim)
+{
+  return guarded([&] {
+    if (!d_src || !d_dst || !d_row_scale || rows == 0 || dim == 0 || dim % 16u != 0u ||
+        (reinterpret_cast<uintptr_t>(d_src) & 15u) != 0 || (reinterpret_cast<uintptr_t>(d_dst) & 15u) != 0)
+      throw std::invalid_argument("st_convert_f32_to_fp8: needs dim % 16 == 0 and 16-byte aligned buffers");
+    return convert_to_fp8(*as_ctx(ctx), d_src, d_dst, d_row_scale, rows, dim);
+  });
+}
+
+int
+st_solve_device_fp8(void* ctx, const uint8_t* d_mat, const float* d_row_scale, uint32_t dim, const st_options* opt,
+                    float* d_eigen_vec, st_result* res)
+{
+  return guarded([&] {
+    Context* c = as_ctx(ctx);
+    if (!d_mat || !d_row_scale)
+      throw std::invalid_argument("st_solve_device_fp8: null matrix or row scales");
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(c->mutex());
+    return c->solve(reinterpret_cast<const float*>(d_mat), dim, o, nullptr, d_eigen_vec, res, false, d_row_scale);
+  });
+}
+
+int
 st_round_timestamps(void* ctx, uint64_t* out, uint32_t capacity, uint32_t* count)
 {
   return guarded([&] {
@@ -995,6 +1024,24 @@ st_shard_solve_bf16(void* shard, const uint16_t* d_rows, const st_options* opt, 
       st_default_options(&o);
     std::lock_guard<std::mutex> lock(s->ctx->mutex());
     return s->ctx->solve(reinterpret_cast<const float*>(d_rows), s->dim, o, s, d_eigen_vec, res, true);
+  });
+}
+
+int
+st_shard_solve_fp8(void* shard, const uint8_t* d_rows, const float* d_row_scale, const st_options* opt, float* d_eigen_vec,
+                   st_result* res)
+{
+  return guarded([&] {
+    Shard* s = as_shard(shard);
+    if (!d_rows || !d_row_scale)
+      throw std::invalid_argument("st_shard_solve_fp8: null rows or row scales");
+    st_options o;
+    if (opt)
+      o = *opt;
+    else
+      st_default_options(&o);
+    std::lock_guard<std::mutex> lock(s->ctx->mutex());
+    return s->ctx->solve(reinterpret_cast<const float*>(d_rows), s->dim, o, s, d_eigen_vec, res, false, d_row_scale);
   });
 }
 

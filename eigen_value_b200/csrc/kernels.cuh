@@ -89,6 +89,7 @@ struct alignas(128) BarrierState
 struct RoundParams
 {
   const float* A; // this GPU's rows of the input: rows x N, row-major (never written)
+  const float* row_scale; // fp8 storage only: one power-of-two scale per owned row
   float* W;       // in-place form only: working copy, rows x N
   uint32_t N;     // matrix dimension
   uint32_t row0;  // first global row owned by this GPU
@@ -316,6 +317,70 @@ row_dot_bf16(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lan
     const uint32_t j = i + 32u * u;
     if (j < nu)
       acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[2u * j], es[2u * j + 1u], acc[u % kUnroll]);
+  }
+#pragma unroll
+  for (int s = kUnroll / 2; s >= 1; s >>= 1)
+#pragma unroll
+    for (int u = 0; u < s; u++)
+      acc[u] += acc[u + s];
+  return warp_sum(acc[0]);
+}
+
+// ---- fp8 STORAGE of the matrix (opt-in, outside reference parity) -----------
+// One byte per element (e4m3: 4 exponent bits, 3 mantissa bits, no infinities) and ONE power-of-two scale per row:
+// A[r][c] ~= row_scale[r] * q[r][c], with the scale chosen so that the row's largest magnitude lands in (224, 448]
+// (st_convert_f32_to_fp8).  A quarter of the HBM bytes per round; e, s and every accumulation stay fp32.  e4m3 -> fp32
+// is exact and the scale is a power of two, so the solve returns exactly the bits of an fp32 solve of the dequantised
+// matrix evaluated in this order: the unit is one 128-bit load = 16 consecutive elements, folded into its accumulator
+// with 16 sequential FMAs; unit j -> lane j % 32, accumulator (j / 32) % 8 as for fp32; the row's sum is multiplied
+// by its scale once, before the division by e[r] (oracle: ORACLE_SUM_CUDA_FP8 on oracle.to_fp8_rows(mat)).
+struct fp8_t
+{
+  unsigned char bits;
+};
+
+__device__ __forceinline__ float
+dot_acc_fp8(uint4 a, const float4* e, float acc)
+{
+  const uint32_t w[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float4 q = fp8x4_to_float4(w[i]);
+    const float4 ev = e[i];
+    acc = fmaf(q.x, ev.x, acc);
+    acc = fmaf(q.y, ev.y, acc);
+    acc = fmaf(q.z, ev.z, acc);
+    acc = fmaf(q.w, ev.w, acc);
+  }
+  return acc;
+}
+
+// One row segment of fp8 storage, one warp: `nu` units of 16 elements starting at `a`; the matching eigenvector
+// entries are es[4 j .. 4 j + 3] (float4, shared memory).  Same loop shape as row_dot_bf16.
+template<int LD>
+__device__ __forceinline__ float
+row_dot_fp8(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lane)
+{
+  static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
+  float acc[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; u++)
+    acc[u] = 0.f;
+  uint32_t i = (uint32_t)lane;
+  for (; i + 32u * (LD - 1) < nu; i += 32u * LD) {
+    uint4 v[LD];
+#pragma unroll
+    for (int u = 0; u < LD; u++)
+      v[u] = ld_stream(a + i + 32u * u);
+#pragma unroll
+    for (int u = 0; u < LD; u++)
+      acc[u % kUnroll] = dot_acc_fp8(v[u], es + 4u * (i + 32u * u), acc[u % kUnroll]);
+  }
+#pragma unroll
+  for (int u = 0; u < LD; u++) {
+    const uint32_t j = i + 32u * u;
+    if (j < nu)
+      acc[u % kUnroll] = dot_acc_fp8(ld_stream(a + j), es + 4u * j, acc[u % kUnroll]);
   }
 #pragma unroll
   for (int s = kUnroll / 2; s >= 1; s >>= 1)
@@ -581,6 +646,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
   static_assert(sizeof(ACC) == 4 || (sizeof(T) == 4 && FORM == kFormReadOnly), "fp64 accumulation: fp32 storage, read-only form");
   constexpr bool kBf16 = sizeof(T) == 2; // p.A then points to bf16 storage (read-only form, N % 8 == 0)
   static_assert(!kBf16 || (VEC == 4 && FORM == kFormReadOnly), "bf16 storage: read-only form, vector loads");
+  constexpr bool kFp8 = sizeof(T) == 1; // p.A points to e4m3 storage, p.row_scale to the row scales (read-only form, N % 16 == 0)
+  static_assert(!kFp8 || (VEC == 4 && FORM == kFormReadOnly && sizeof(ACC) == 4), "fp8 storage: read-only form, vector loads, fp32 accumulation");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
   extern __shared__ __align__(16) float smem[];
   float* scale_s = smem;               // chunk_cols floats: e (read-only) or s_prev (in-place)
@@ -692,7 +759,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
           const size_t off = (size_t)(rb + rl) * N + c0 + s0;
           const float* sc = scale_s + s0;
           float t;
-          if (kBf16) {
+          if (kFp8) {
+            const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const fp8_t*>(p.A) + off);
+            t = row_dot_fp8<kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 4, lane);
+          } else if (kBf16) {
             const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
             t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 3, lane);
           } else if (FORM == kFormReadOnly) {
@@ -721,6 +791,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
     for (uint32_t r = tid; r < nrows; r += THREADS) {
       const uint32_t gr = p.row0 + rb + r;
       float s = part_s[r];
+      if (kFp8)
+        s = s * p.row_scale[rb + r];
       if (FORM == kFormReadOnly && !first)
         s = s / (ld_cg(Eprev + gr) * (ld_cg(Sprev + gr) / m_prev));
       if (p.world > 1) {
@@ -1090,6 +1162,50 @@ __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restri
   }
   for (size_t i = done + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = f32_to_bf16_rn(src[i]);
+}
+
+// fp32 -> fp8 storage, one warp per row (dim % 16 == 0, 16-byte aligned rows): the row's largest magnitude a gives the
+// scale 2^k with a / 2^k in (224, 448] (k clamped to +-118; an all-zero or non-finite row keeps scale 1), every element
+// is divided by it -- exact -- and rounded to the nearest e4m3 code, ties to even, saturating.
+__device__ __forceinline__ float
+fp8_row_scale(float amax)
+{
+  if (!(amax > 0.f) || !(amax < __uint_as_float(0x7f800000u)))
+    return 1.f;
+  int e;
+  const float m = frexpf(amax, &e); // amax = m * 2^e, m in [0.5, 1)
+  int k = (m <= 0.875f) ? e - 9 : e - 8;
+  k = max(-118, min(118, k));
+  return ldexpf(1.f, k);
+}
+
+__global__ void __launch_bounds__(256) convert_fp8_rows_kernel(const float* __restrict__ src, unsigned char* __restrict__ dst,
+                                                               float* __restrict__ row_scale, uint32_t rows, uint32_t dim)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nv = dim >> 2;
+  for (uint32_t r = gw; r < rows; r += warps) {
+    const float4* row = reinterpret_cast<const float4*>(src + (size_t)r * dim);
+    float amax = 0.f;
+    for (uint32_t i = lane; i < nv; i += 32u) {
+      const float4 v = row[i];
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float scale = fp8_row_scale(amax);
+    const float inv = 1.f / scale; // a power of two: exact
+    if (lane == 0)
+      row_scale[r] = scale;
+    uint32_t* out = reinterpret_cast<uint32_t*>(dst + (size_t)r * dim);
+    for (uint32_t i = lane; i < nv; i += 32u) {
+      const float4 v = row[i];
+      out[i] = (uint32_t)f32x2_to_fp8x2(v.x * inv, v.y * inv) | ((uint32_t)f32x2_to_fp8x2(v.z * inv, v.w * inv) << 16);
+    }
+  }
 }
 
 // Philox-4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): counter (ctr, 0), key = seed.

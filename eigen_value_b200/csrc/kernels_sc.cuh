@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
   static_assert(!kBf16 || PF_BATCHES == 0, "bf16 storage: no prefetch slots");
+  // fp8 storage (p.A points to e4m3 codes, p.row_scale to the row scales, N % 16 == 0): a work unit is 8 KB
+  constexpr bool kFp8 = sizeof(T) == 1;
+  static_assert(!kFp8 || (PF_BATCHES == 0 && sizeof(ACC) == 4 && VEC == 4), "fp8 storage: no prefetch slots, fp32 accumulation");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (a multiple of 32, <= MAX_THREADS)
   const uint32_t kWarps = THREADS >> 5;
   constexpr uint32_t kPfFloats = PF_BATCHES * 1024u; // prefetch slot per warp
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
       // publish s[r] = (A.e)[r] / e[r] -- to every rank when sharded
       auto publish = [&](uint32_t rl, float t) {
         const uint32_t gr = p.row0 + rl;
-        const float s = t / e_s[gr];
+        const float s = (kFp8 ? t * p.row_scale[rl] : t) / e_s[gr];
         wmax = fmaxf(wmax, s); // find_max, reference :154-227 (fmaxf drops NaNs, like the running max of the old scan)
         if (p.world > 1) {
           for (uint32_t g = 0; g < p.world; g++)
@@ -233,6 +236,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           if (VEC == 1) {
             t = row_dot_readonly<1, false, ACC>(p.A + (size_t)rl * N + (size_t)ch * kChunkCols, e_s + (size_t)ch * kChunkCols,
                                                 min((uint32_t)kChunkCols, N - ch * (uint32_t)kChunkCols), lane);
+          } else if (kFp8) {
+            // 16 columns per fp8 unit; seg_nv counts float4 of the eigenvector chunk
+            const uint4* seg8 = reinterpret_cast<const uint4*>(reinterpret_cast<const fp8_t*>(p.A) + (size_t)rl * N) +
+                                ch * (kChunkVec >> 2);
+            t = row_dot_fp8<LD>(seg8, reinterpret_cast<const float4*>(e_s) + ch * kChunkVec, seg_nv >> 2, lane);
           } else if (kBf16) {
             // seg_nv counts float4 of the eigenvector chunk = 4 columns each; 8 columns per bf16 unit
             const uint4* seg16 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + (size_t)rl * N) +

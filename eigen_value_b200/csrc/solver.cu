@@ -502,7 +502,7 @@ aligned16(const void* p)
 
 int
 Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
-               float* d_eigen_vec, st_result* res, bool bf16)
+               float* d_eigen_vec, st_result* res, bool bf16, const float* d_row_scale)
 {
   if (!d_rows || dim == 0 || opt.max_iter == 0 || !(opt.eps >= 0.f))
     throw std::invalid_argument("solve: bad argument");
@@ -538,6 +538,17 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != 10 && opt.kernel != 12 && opt.kernel != 13)
       throw std::invalid_argument("solve: fp64 accumulation is built for kernel 0 (automatic), 1, 10, 12 and 13");
   }
+  // fp8 storage: d_rows points to e4m3 codes, d_row_scale to one power-of-two scale per owned row
+  const bool fp8 = d_row_scale != nullptr;
+  const bool narrow = bf16 || fp8; // storage below fp32: configuration 11 or the general loop
+  if (fp8) {
+    if (bf16 || acc64 || form != kFormReadOnly || dim % 16u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
+      throw std::invalid_argument("solve: fp8 storage needs the read-only form, fp32 accumulation, dim % 16 == 0 and a 16-byte aligned matrix");
+    if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != kScBf16Id)
+      throw std::invalid_argument("solve: fp8 storage is built for kernel 0 (automatic), 1 (general loop) and 11 (resident-e)");
+    if (opt.kernel == kScBf16Id && dim > (uint32_t)kResidentCols)
+      throw std::invalid_argument("solve: resident-e kernel needs dim <= 32768");
+  }
   if (bf16) {
     // d_rows points to bfloat16 storage: 128-bit loads of 8 elements, fp32 everywhere else
     if (form != kFormReadOnly || dim % 8u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
@@ -550,6 +561,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
 
   RoundParams p{};
   p.A = d_rows;
+  p.row_scale = d_row_scale;
   p.W = nullptr;
   if (form == kFormInPlace)
     p.W = d_work_;
@@ -629,7 +641,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const ScConfig* sc = nullptr;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
-  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !bf16 && !acc64 && dim <= (uint32_t)kClusterCols)) {
+  if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !narrow && !acc64 && dim <= (uint32_t)kClusterCols)) {
     if (!readonly4 || shard || dim > (uint32_t)kClusterCols)
       throw std::invalid_argument("solve: on-chip kernel needs one GPU, the read-only form, dim % 4 == 0, dim <= 512");
     cluster_ctas = cluster_ctas_for(dim, &smem);
@@ -640,7 +652,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   }
   // scalar units (dim % 4 != 0 or a matrix off the 16-byte grid): the resident-e kernel without prefetch slots
   // (configuration 11) streams them with 4-byte loads in the order the general loop uses for these dimensions
-  const bool readonly1 = !vec4 && form == kFormReadOnly && !bf16 && !acc64;
+  const bool readonly1 = !vec4 && form == kFormReadOnly && !narrow && !acc64;
   if (!cluster_ctas && (is_sc_kernel_id(opt.kernel) ||
                         (opt.kernel == 0 && (readonly4 || readonly1) && dim <= (uint32_t)kResidentCols))) {
     if (!(readonly4 || (readonly1 && (opt.kernel == 0 || opt.kernel == kScBf16Id))) || dim > (uint32_t)kResidentCols)
@@ -652,16 +664,16 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     int want_pf = 1;
     if (opt.kernel == 0 && dim > 1024u && dim <= 3072u && (uint64_t)rows <= (uint64_t)sm_count_ * 16u)
       want_pf = (int)((dim + 1023u) / 1024u);
-    if (bf16 || readonly1)
-      want_pf = 0; // bf16 storage and scalar units are built without prefetch slots (configuration 11)
+    if (narrow || readonly1)
+      want_pf = 0; // bf16 / fp8 storage and scalar units are built without prefetch slots (configuration 11)
     for (const ScConfig& c : kScConfigs) {
       if (opt.kernel >= 10 && c.id != opt.kernel)
         continue;
       if (opt.kernel == 0 && pinned > c.max_threads)
         continue;
-      if ((bf16 || readonly1) && c.id != kScBf16Id)
-        continue; // bf16 storage and scalar units are built for configuration 11 only
-      if (opt.kernel == 0 && !bf16 && acc64 && c.id == kScBf16Id)
+      if ((narrow || readonly1) && c.id != kScBf16Id)
+        continue; // bf16 / fp8 storage and scalar units are built for configuration 11 only
+      if (opt.kernel == 0 && !narrow && acc64 && c.id == kScBf16Id)
         continue; // fp64 accumulation is built for the configurations with prefetch slots
       if (opt.kernel == 0 && !pinned && (c.pf_batches != want_pf || c.max_threads != 512))
         continue;
@@ -693,9 +705,9 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   // wide kernel (kernel 2): unit-scheduled like the resident-e kernel, the eigenvector staged one 32768-column window at
   // a time.  Automatic above the resident limit for the default form / storage / accumulator; explicit for any dim % 4 == 0.
   bool wide = false;
-  if (!sc && !cluster_ctas && (opt.kernel == kWideKernelId || (opt.kernel == 0 && readonly4 && !bf16 && !acc64 &&
+  if (!sc && !cluster_ctas && (opt.kernel == kWideKernelId || (opt.kernel == 0 && readonly4 && !narrow && !acc64 &&
                                                                 dim > (uint32_t)kResidentCols && pinned <= 512))) {
-    if (!readonly4 || bf16 || acc64)
+    if (!readonly4 || narrow || acc64)
       throw std::invalid_argument("solve: the wide kernel needs the read-only form, fp32 storage and accumulation, dim % 4 == 0");
     const uint32_t window = std::min<uint32_t>((uint32_t)kResidentCols, (dim + (uint32_t)kChunkCols - 1u) / (uint32_t)kChunkCols * (uint32_t)kChunkCols);
     if ((dim + window - 1u) / window > (uint32_t)kWideMaxWindows)
@@ -743,6 +755,22 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_general_acc64<1, kStopRelative>(threads, p, grid, smem, stream_);
     else
       launch_general_acc64<1, kStopAbsolute>(threads, p, grid, smem, stream_);
+  } else if (fp8 && sc) {
+    if (sc->id != kScBf16Id)
+      throw std::invalid_argument("solve: fp8 storage needs resident-e configuration 11");
+    if (stop == kStopRelative)
+      launch_cooperative(round_loop_sc_kernel<512, 0, kStopRelative, fp8_t>, p, grid, threads, smem, stream_);
+    else
+      launch_cooperative(round_loop_sc_kernel<512, 0, kStopAbsolute, fp8_t>, p, grid, threads, smem, stream_);
+  } else if (fp8) {
+    if (threads <= 512 && stop == kStopRelative)
+      launch_cooperative(round_loop_kernel<4, kFormReadOnly, 512, kStopRelative, fp8_t>, p, grid, threads, smem, stream_);
+    else if (threads <= 512)
+      launch_cooperative(round_loop_kernel<4, kFormReadOnly, 512, kStopAbsolute, fp8_t>, p, grid, threads, smem, stream_);
+    else if (stop == kStopRelative)
+      launch_cooperative(round_loop_kernel<4, kFormReadOnly, 1024, kStopRelative, fp8_t>, p, grid, threads, smem, stream_);
+    else
+      launch_cooperative(round_loop_kernel<4, kFormReadOnly, 1024, kStopAbsolute, fp8_t>, p, grid, threads, smem, stream_);
   } else if (bf16 && sc) {
     if (sc->id != kScBf16Id)
       throw std::invalid_argument("solve: bf16 storage needs resident-e configuration 11");
@@ -826,7 +854,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
     res->grid = (uint32_t)grid;
     res->kernel_id = cluster_ctas ? (uint32_t)kClusterKernelId : sc ? (uint32_t)sc->id : wide ? (uint32_t)kWideKernelId : 1u;
     res->threads = (uint32_t)threads;
-    const uint64_t per_pass = (uint64_t)rows * dim * (bf16 ? 2u : sizeof(float));
+    const uint64_t per_pass = (uint64_t)rows * dim * (fp8 ? 1u : bf16 ? 2u : sizeof(float));
     res->bytes_per_round = form == kFormInPlace ? 2 * per_pass : per_pass;
     std::vector<float> dt;
     for (uint32_t k = 0; k < stamped; k++)
@@ -1128,6 +1156,17 @@ convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t coun
   const size_t work = (count + 3) / 4;
   const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)q.sm_count() * 16);
   ST_LAUNCH_ELEMENTWISE(convert_bf16_kernel, std::max(1, grid), 256, 0, q.stream(), d_src, d_dst, count);
+  ST_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int
+convert_to_fp8(st::Context& q, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows, uint32_t dim)
+{
+  q.activate();
+  const int grid = (int)std::min<uint32_t>((rows + 7u) / 8u, (uint32_t)q.sm_count() * 8u);
+  ST_LAUNCH(convert_fp8_rows_kernel, std::max(1, grid), 256, 0, q.stream(), d_src, reinterpret_cast<unsigned char*>(d_dst),
+            d_row_scale, rows, dim);
   ST_CUDA(cudaGetLastError());
   return ST_OK;
 }

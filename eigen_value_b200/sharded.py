@@ -79,7 +79,7 @@ class ShardedSolver:
         return self.solver.uniform(self.dim, seed, self.row0, self.rows)
 
     def solve(self, d_rows: DeviceBuffer, d_eigen_vec: Optional[DeviceBuffer] = None,
-              bf16: bool = False, **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
+              bf16: bool = False, fp8_scale: Optional[DeviceBuffer] = None, **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
         """Collective: every rank calls it with its own rows.  Every rank gets the full
         eigenvector and identical (lambda, iter_count).  The eigenvector is downloaded only
         when no device output buffer is supplied."""
@@ -99,8 +99,12 @@ class ShardedSolver:
             self.solver.synchronize()
             self._host_barrier()
         vec = self._vec if own else d_eigen_vec
-        fn = self.lib.st_shard_solve_bf16 if bf16 else self.lib.st_shard_solve   # bf16: rows in bfloat16 storage
-        check(fn(self.shard, d_rows.ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res)), "st_shard_solve")
+        if fp8_scale is not None:                                                 # rows in fp8 storage + their row scales
+            check(self.lib.st_shard_solve_fp8(self.shard, d_rows.ptr, fp8_scale.ptr, ctypes.byref(o), vec.ptr,
+                                              ctypes.byref(res)), "st_shard_solve_fp8")
+        else:
+            fn = self.lib.st_shard_solve_bf16 if bf16 else self.lib.st_shard_solve   # bf16: rows in bfloat16 storage
+            check(fn(self.shard, d_rows.ptr, ctypes.byref(o), vec.ptr, ctypes.byref(res)), "st_shard_solve")
         out = vec.download(np.float32, self.dim) if own else None
         return SolveInfo.from_c(res), out
 

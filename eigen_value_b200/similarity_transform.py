@@ -247,22 +247,36 @@ class Solver:
         check(self.lib.st_convert_f32_to_bf16(self.ctx, d_src.ptr, out.ptr, count), "st_convert_f32_to_bf16")
         return out
 
+    def to_fp8(self, d_src: DeviceBuffer, rows: int, dim: int) -> Tuple[DeviceBuffer, DeviceBuffer]:
+        """fp32 -> fp8 (e4m3) storage with one power-of-two scale per row, on the device: (codes, row scales), the
+        storage for solve_device(..., fp8_scale=...).  dim % 16 == 0."""
+        codes, scale = self.alloc(rows * dim), self.alloc(4 * rows)
+        check(self.lib.st_convert_f32_to_fp8(self.ctx, d_src.ptr, codes.ptr, scale.ptr, rows, dim), "st_convert_f32_to_fp8")
+        return codes, scale
+
     def synchronize(self) -> None:
         check(self.lib.st_synchronize(self.ctx), "st_synchronize")
 
     # ---- the round loop -------------------------------------------------------------------
     def solve_device(self, d_mat: DeviceBuffer, dim: int, d_eigen_vec: Optional[DeviceBuffer] = None,
-                     bf16: bool = False, **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
+                     bf16: bool = False, fp8_scale: Optional[DeviceBuffer] = None,
+                     **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
         """similarity_transform() on a device-resident matrix.  Returns (info, eigen_vec);
         eigen_vec is downloaded only when no device output buffer was supplied.  bf16=True: d_mat
-        holds bfloat16 storage (see to_bf16; opt-in, changes results, dim % 8 == 0)."""
+        holds bfloat16 storage (see to_bf16; opt-in, changes results, dim % 8 == 0).  fp8_scale=<row scales>: d_mat
+        holds fp8 storage (see to_fp8; opt-in, changes results, dim % 16 == 0)."""
         o = make_options(self.lib, **opts)
         res = StResult()
         own = d_eigen_vec is None
         vec = self.alloc(4 * dim) if own else d_eigen_vec
-        fn, what = (self.lib.st_solve_device_bf16, "st_solve_device_bf16") if bf16 else \
-                   (self.lib.st_solve_device, "st_solve_device")
-        check(fn(self.ctx, d_mat.ptr, dim, ctypes.byref(o), vec.ptr, ctypes.byref(res)), what)
+        if fp8_scale is not None:
+            assert not bf16
+            check(self.lib.st_solve_device_fp8(self.ctx, d_mat.ptr, fp8_scale.ptr, dim, ctypes.byref(o), vec.ptr,
+                                               ctypes.byref(res)), "st_solve_device_fp8")
+        else:
+            fn, what = (self.lib.st_solve_device_bf16, "st_solve_device_bf16") if bf16 else \
+                       (self.lib.st_solve_device, "st_solve_device")
+            check(fn(self.ctx, d_mat.ptr, dim, ctypes.byref(o), vec.ptr, ctypes.byref(res)), what)
         out = vec.download(np.float32, dim) if own else None
         if own:
             vec.free()

@@ -198,6 +198,17 @@ int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options*
 int st_convert_f32_to_bf16(void* ctx, const float* d_src, uint16_t* d_dst, size_t count);
 int st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const st_options* opt,
                          float* d_eigen_vec, st_result* res);
+/* fp8 STORAGE of the matrix (opt-in; changes results, so outside reference parity): one byte per element (e4m3)
+ * plus ONE power-of-two fp32 scale per row, A[r][c] ~= d_row_scale[r] * q[r][c] -- a quarter of the HBM bytes per
+ * round -- while the eigenvector, the row sums and every accumulation stay fp32.  st_convert_f32_to_fp8 picks each
+ * row's scale so that its largest magnitude lands in (224, 448] and rounds to the nearest code, ties to even.
+ * e4m3 -> fp32 is exact and the scales are powers of two, so the result is bit-identical to an fp32 solve of the
+ * dequantised matrix evaluated in 16-element units.  Read-only form, fp32 accumulation; dim % 16 == 0; kernels 0
+ * (automatic), 1 and 11.  Entries below 2^-18 of their row's largest one round to zero. */
+int st_convert_f32_to_fp8(void* ctx, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows,
+                          uint32_t dim);
+int st_solve_device_fp8(void* ctx, const uint8_t* d_mat, const float* d_row_scale, uint32_t dim,
+                        const st_options* opt, float* d_eigen_vec, st_result* res);
 /* Streamed solve: the same round loop for a HOST matrix that does not fit the device (or the share of
  * it the caller grants).  The step before the path in the reference is the host copy-in of the whole
  * matrix (similarity_transform.cpp:14-19); here the device holds a direct-mapped cache of `slots` row
@@ -307,6 +318,9 @@ int st_shard_solve(void* shard, const float* d_rows, const st_options* opt, floa
 /* st_shard_solve on bf16 storage of this rank's rows (see st_solve_device_bf16). */
 int st_shard_solve_bf16(void* shard, const uint16_t* d_rows, const st_options* opt, float* d_eigen_vec,
                         st_result* res);
+/* st_shard_solve on fp8 storage of this rank's rows and their row scales (see st_solve_device_fp8). */
+int st_shard_solve_fp8(void* shard, const uint8_t* d_rows, const float* d_row_scale, const st_options* opt,
+                       float* d_eigen_vec, st_result* res);
 void st_shard_destroy(void* shard);
 
 #ifdef __cplusplus

@@ -26,6 +26,7 @@ SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
 SUM_CUDA = 4   # the CUDA kernels' evaluation order: bit-identical to the GPU (tests/test_zz_gpu_bitexact.py)
 SUM_CUDA_F64 = 6    # SUM_CUDA's order with fp64 accumulators (st_options.accumulate = ST_ACC_F64)
 SUM_CUDA_BF16 = 5   # the same with 8-element units: the kernels' order on bf16 storage (feed to_bf16(mat)[0])
+SUM_CUDA_FP8 = 7    # the same with 16-element units: the kernels' order on fp8 storage (feed to_fp8_rows(mat)[0])
 STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # the reference's stop test | extension: threshold eps * max(s)
 
 
@@ -129,6 +130,45 @@ def to_bf16(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         bits[i:i + step] = r
         back[i:i + step] = (r.astype(np.uint32) << np.uint32(16)).view(np.float32)
     return back.reshape(a.shape), bits.reshape(a.shape)
+
+
+def fp8_e4m3_values() -> np.ndarray:
+    """Value of every e4m3 code 0x00..0x7e (the fn variant: no infinities, 0x7f = NaN), ascending."""
+    c = np.arange(127)
+    e, m = c >> 3, c & 7
+    return np.where(e == 0, np.ldexp(m.astype(np.float64), -9), np.ldexp(1.0 + m / 8.0, e - 7)).astype(np.float32)
+
+
+def to_fp8_rows(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """fp32 -> fp8 (e4m3) storage with one power-of-two scale per row: what st_convert_f32_to_fp8 does.
+    Per row: a = max |x|, scale = 2^k with a / 2^k in (224, 448] (k clamped to +-118; 1 for an all-zero or
+    non-finite row); every element divided by the scale (exact) and rounded to the nearest code, ties to the
+    even code, saturating at 448 (cvt.rn.satfinite.e4m3x2.f32; NaN -> 0x7f).
+    Returns (the dequantised matrix scale[r] * q[r][c] as fp32 -- exact --, the uint8 codes, the fp32 scales)."""
+    a = np.ascontiguousarray(mat, dtype=np.float32)
+    rows = a.shape[0]
+    vals = fp8_e4m3_values()
+    amax = np.max(np.abs(np.where(np.isnan(a), np.float32(0), a)), axis=1)
+    m, e = np.frexp(amax)                                    # amax = m * 2^e, m in [0.5, 1)
+    k = np.clip(np.where(m <= np.float32(0.875), e - 9, e - 8), -118, 118)
+    scale = np.where((amax > 0) & np.isfinite(amax), np.ldexp(np.float32(1), k), np.float32(1)).astype(np.float32)
+    codes = np.empty(a.shape, dtype=np.uint8)
+    back = np.empty(a.shape, dtype=np.float32)
+    for r in range(rows):
+        x = a[r] / scale[r]                                    # exact: a power of two
+        mag = np.minimum(np.abs(x), np.float32(448))
+        lo = np.clip(np.searchsorted(vals, mag, side="right") - 1, 0, 126)     # largest code <= |x|
+        hi = np.minimum(lo + 1, 126)
+        dl, dh = mag - vals[lo], vals[hi] - mag
+        up = (hi > lo) & ((dh < dl) | ((dh == dl) & ((lo & 1) == 1)))
+        c = np.where(up, hi, lo).astype(np.uint8)
+        nan = np.isnan(x)
+        c[nan] = 0x7F
+        sign = np.signbit(x) & ~nan
+        codes[r] = c | (sign.astype(np.uint8) << 7)
+        v = np.where(nan, np.float32(np.nan), vals[np.minimum(c, 126)])
+        back[r] = np.where(sign, -v, v) * scale[r]
+    return back, codes, scale
 
 
 def philox_block(ctr: int, key: int) -> np.ndarray:

@@ -66,10 +66,16 @@ enum
   ORACLE_SUM_CUDA_F64 = 6,   /* ORACLE_SUM_CUDA's order with fp64 accumulators (ST_ACC_F64): products are
                                 exact in double, every add rounds once in double, the chunk sum is
                                 rounded to fp32 once; chunk sums of a row are added in fp32 */
-  ORACLE_SUM_CUDA_BF16 = 5   /* the same order with 8-element units: what the CUDA kernels do on
+  ORACLE_SUM_CUDA_BF16 = 5,  /* the same order with 8-element units: what the CUDA kernels do on
                                 bf16 STORAGE of the matrix (one 128-bit load = 8 elements).  Feed
                                 the oracle the bf16-rounded matrix (as fp32): bf16 -> fp32 is
                                 exact, so the bits must match the GPU's bf16-storage solve */
+  ORACLE_SUM_CUDA_FP8 = 7    /* the same order with 16-element units: fp8 (e4m3) STORAGE with one
+                                power-of-two scale per row (one 128-bit load = 16 elements).  Feed
+                                the oracle the dequantised matrix scale[r] * q[r][c] (as fp32):
+                                e4m3 -> fp32 is exact and multiplying a row by a power of two
+                                commutes with every rounding of its sum, so the bits must match
+                                the GPU's fp8-storage solve */
 };
 
 int
@@ -128,7 +134,7 @@ reduce16(const float* acc)
 static float
 row_dot_cuda_order(const float* row, const float* scale, size_t n, size_t unit)
 {
-  /* unit == 0: fp32 storage (float4 when n % 4 == 0, else scalar); unit == 8: bf16 storage */
+  /* unit == 0: fp32 storage (float4 when n % 4 == 0, else scalar); unit == 8: bf16 storage; unit == 16: fp8 storage */
   const size_t vec = unit ? unit : ((n % 4 == 0) ? 4 : 1);
   float total = 0.f;
   for (size_t c0 = 0; c0 < n; c0 += ORACLE_CUDA_CHUNK) {
@@ -224,6 +230,8 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
     return row_dot_cuda_order_f64(row, scale, n);
   if (sum_mode == ORACLE_SUM_CUDA_BF16)
     return row_dot_cuda_order(row, scale, n, 8); /* n % 8 == 0 required, like the kernels */
+  if (sum_mode == ORACLE_SUM_CUDA_FP8)
+    return row_dot_cuda_order(row, scale, n, 16); /* n % 16 == 0 required, like the kernels */
   if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {
     const size_t wg = (size_t)(sum_mode >> 8);
     float cell = 0.f; /* the zero-filled global cell (:85-93) */

@@ -31,9 +31,10 @@ struct emu_opts
   int32_t ctas;    // grid size per emulated GPU
   int32_t kernel;  // 1 general, 2 wide, 10-13 resident-e, 20 cluster
   int32_t stop;    // 0 absolute, 1 relative
-  int32_t bf16;    // matrix is bf16 storage
+  int32_t bf16;    // 1: matrix is bf16 storage; 2: fp8 (e4m3) storage with row scales
   int32_t world;   // emulated GPUs (row-block sharded)
   int32_t acc64;   // fp64 accumulation (read-only form, fp32 storage; kernels 1, 10, 12, 13)
+  const float* row_scale; // fp8 storage: one power-of-two scale per row of the whole matrix
 };
 
 static thread_local std::string g_err;
@@ -65,11 +66,13 @@ struct Rank
 };
 
 template<int STOP>
-void (*general_kernel(bool vec4, int form, bool bf16, bool acc64))(const RoundParams)
+void (*general_kernel(bool vec4, int form, bool bf16, bool acc64, bool fp8 = false))(const RoundParams)
 {
   if (acc64)
     return vec4 ? round_loop_kernel<4, kFormReadOnly, 512, STOP, float, double>
                 : round_loop_kernel<1, kFormReadOnly, 512, STOP, float, double>;
+  if (fp8)
+    return round_loop_kernel<4, kFormReadOnly, 512, STOP, fp8_t>;
   if (bf16)
     return round_loop_kernel<4, kFormReadOnly, 512, STOP, bf16_t>;
   if (vec4)
@@ -80,7 +83,7 @@ void (*general_kernel(bool vec4, int form, bool bf16, bool acc64))(const RoundPa
 }
 
 template<int STOP>
-void (*sc_kernel(int pf, bool bf16, bool acc64))(const RoundParams)
+void (*sc_kernel(int pf, bool bf16, bool acc64, bool fp8 = false))(const RoundParams)
 {
   if (acc64) {
     switch (pf) {
@@ -89,6 +92,8 @@ void (*sc_kernel(int pf, bool bf16, bool acc64))(const RoundParams)
       default: return round_loop_sc_kernel<512, 3, STOP, float, double>;
     }
   }
+  if (fp8)
+    return round_loop_sc_kernel<512, 0, STOP, fp8_t>;
   if (bf16)
     return round_loop_sc_kernel<512, 0, STOP, bf16_t>;
   switch (pf) {
@@ -110,14 +115,17 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
     if (!mat || dim == 0 || world > (uint32_t)kMaxWorld || world > dim || o->max_iter == 0)
       throw std::string("bad argument");
     const int form = o->form ? kFormInPlace : kFormReadOnly;
-    const bool bf16 = o->bf16 != 0;
+    const bool fp8 = o->bf16 == 2;
+    const bool bf16 = o->bf16 == 1;
     const bool acc64 = o->acc64 != 0;
     const bool vec4 = dim % 4u == 0u;
     if (acc64 && (bf16 || form != kFormReadOnly || !(o->kernel == 1 || o->kernel == 10 || o->kernel == 12 || o->kernel == 13)))
       throw std::string("fp64 accumulation: fp32 storage, read-only form, kernels 1, 10, 12, 13");
     if (bf16 && (dim % 8u != 0u || form != kFormReadOnly))
       throw std::string("bf16 storage needs dim % 8 == 0 and the read-only form");
-    const size_t elem = bf16 ? 2 : 4;
+    if (fp8 && (dim % 16u != 0u || form != kFormReadOnly || acc64 || !o->row_scale || !(o->kernel == 1 || o->kernel == 11)))
+      throw std::string("fp8 storage needs dim % 16 == 0, the read-only form, row scales, kernel 1 or 11");
+    const size_t elem = fp8 ? 1 : bf16 ? 2 : 4;
     const size_t nvec = ((size_t)dim + 31) & ~(size_t)31;
 
     std::vector<Rank> R(world);
@@ -138,6 +146,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
       p.N = dim;
       p.row0 = row0;
       p.rows = rows;
+      p.row_scale = fp8 ? o->row_scale + row0 : nullptr;
       r.vecs.assign(5 * nvec, -7.f);
       p.S[0] = r.vecs.data();
       p.S[1] = r.vecs.data() + nvec;
@@ -194,17 +203,17 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         r.grid = std::max(1u, std::min(want, (rows + warps - 1) / warps));
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
         r.smem = sizeof(float) * ((size_t)p.chunk_cols + cap);
-        kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64);
+        kernel = o->stop ? general_kernel<kStopRelative>(vec4, form, bf16, acc64, fp8) : general_kernel<kStopAbsolute>(vec4, form, bf16, acc64, fp8);
       } else if (kid >= 10 && kid <= 13) {
-        const bool scalar_units = !vec4 && kid == 11 && !bf16 && !acc64; // dim % 4 != 0: configuration 11, 4-byte units
+        const bool scalar_units = !vec4 && kid == 11 && !bf16 && !fp8 && !acc64; // dim % 4 != 0: configuration 11, 4-byte units
         if ((!vec4 && !scalar_units) || form != kFormReadOnly || dim > (uint32_t)kResidentCols)
           throw std::string("resident-e kernel needs the read-only form, dim <= 32768 and dim % 4 == 0 (configuration 11: any dim)");
         int pf = -1;
         for (const ScConfig& c : kScConfigs)
           if (c.id == kid)
             pf = c.pf_batches;
-        if (bf16 && pf != 0)
-          throw std::string("bf16 storage is built for configuration 11");
+        if ((bf16 || fp8) && pf != 0)
+          throw std::string("bf16 / fp8 storage is built for configuration 11");
         r.grid = std::max(1u, std::min(want, (rows + warps - 1) / warps));
         const uint32_t cap = (rows + r.grid - 1) / r.grid + 1;
         uint32_t moff = 0;
@@ -221,14 +230,14 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.partial = r.partial.data();
           p.row_done = r.row_done.data();
         }
-        kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64) : sc_kernel<kStopAbsolute>(pf, bf16, acc64);
+        kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64, fp8) : sc_kernel<kStopAbsolute>(pf, bf16, acc64, fp8);
         if (scalar_units)
           kernel = o->stop ? round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>
                            : round_loop_sc_kernel<512, 0, kStopAbsolute, float, float, 1>;
       } else if (kid == 2) {
         // wide kernel: windows of p.chunk_cols columns (kResidentCols; ST_EMU_WINDOW stages less so that several
         // windows fit an emulated size), chunk sums + per-row counters + one unit counter per window
-        if (!vec4 || form != kFormReadOnly || bf16 || acc64)
+        if (!vec4 || form != kFormReadOnly || bf16 || fp8 || acc64)
           throw std::string("wide kernel: read-only form, fp32, dim % 4 == 0");
         uint32_t window = (uint32_t)kResidentCols;
         if (const char* wv = getenv("ST_EMU_WINDOW"))
@@ -250,7 +259,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         p.phase_counter = r.phase_counter.data();
         kernel = o->stop ? round_loop_wide_kernel<512, kStopRelative> : round_loop_wide_kernel<512, kStopAbsolute>;
       } else if (kid == 20) {
-        if (!vec4 || form != kFormReadOnly || bf16 || world != 1 || dim > (uint32_t)kClusterCols)
+        if (!vec4 || form != kFormReadOnly || bf16 || fp8 || world != 1 || dim > (uint32_t)kClusterCols)
           throw std::string("cluster kernel: one GPU, read-only form, fp32, dim % 4 == 0, dim <= 512");
         size_t smem = 0;
         const int c = cluster_ctas_for(dim, &smem);
@@ -333,6 +342,16 @@ emu_convert_bf16(const float* src, unsigned short* dst, size_t n, unsigned ctas)
   struct P { const float* s; unsigned short* d; size_t n; };
   P p{ src, dst, n };
   auto g = emu::launch_async<P>([](const P q) { convert_bf16_kernel(q.s, q.d, q.n); }, ctas, 256, 0, p);
+  emu::join(*g);
+  return 0;
+}
+
+extern "C" int
+emu_convert_fp8(const float* src, unsigned char* dst, float* row_scale, uint32_t rows, uint32_t dim, unsigned ctas)
+{
+  struct P { const float* s; unsigned char* d; float* sc; uint32_t rows, dim; };
+  P p{ src, dst, row_scale, rows, dim };
+  auto g = emu::launch_async<P>([](const P q) { convert_fp8_rows_kernel(q.s, q.d, q.sc, q.rows, q.dim); }, ctas, 256, 0, p);
   emu::join(*g);
   return 0;
 }

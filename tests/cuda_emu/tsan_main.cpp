@@ -14,6 +14,7 @@ struct emu_opts
   float eps;
   uint32_t max_iter;
   int32_t form, sweep, dynamic, threads, ctas, kernel, stop, bf16, world, acc64;
+  const float* row_scale;
 };
 int emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, float* eigen_vec,
               uint32_t* iter_count, uint32_t* passes, uint32_t* ranks_agree);
@@ -99,6 +100,8 @@ main(int argc, char** argv)
     { "2 GPUs, general 200", 200, with(1, 64, 2, 2) },
     { "3 GPUs, resident-e 13 dynamic 320", 320, with(13, 64, 2, 3, 0, 0, 1) },
     { "resident-e 13, fp64 accumulation, 320", 320, [&] { emu_opts o = with(13, 64, 3); o.acc64 = 1; return o; }() },
+    { "resident-e 11 on scalar units, dynamic, 321", 321, with(11, 64, 3, 1, 0, 0, 1) },
+    { "2 GPUs, resident-e 11 on scalar units, two units per row, 8195 x 2 rounds", 8195, with(11, 64, 3, 2, 0, 0, 1, 0, 2u) },
     { "wide kernel 2, dynamic units, 320", 320, with(2, 64, 3, 1, 0, 0, 1) },
     { "2 GPUs, wide kernel 2, static units, 200", 200, with(2, 64, 2, 2, 0, 0, 0) },
     { "wide kernel 2, three 8192-column windows (ST_EMU_WINDOW), 16400 x 2 rounds", 16400, [&] { setenv("ST_EMU_WINDOW", "8192", 1); return with(2, 64, 4, 1, 0, 0, 1, 0, 2u); }() },

@@ -26,10 +26,11 @@ def test_gpu_test_files_pass_on_the_emulated_library():
     """Every `-m gpu` test file, cases up to N = 4200: the drop-in boundary (golden, 4-byte iter_cnt slot, bad
     arguments, NaN input running to the cap), per-kernel entry points against the reference's unit fixtures, device
     generators, options, both forms, kernel variants, the world == 1 shard path and the in-process sharded solve on
-    2 and 4 pretend GPUs, the timeout when a peer never arrives, bit-exact parity with the oracle, relative stop, fp64 accumulation, bf16 storage, the streamed solve (block cache, file-backed input), the device group behind one handle (st_group_attach, ST_DEVICES), and 200 random option
+    2 and 4 pretend GPUs, the timeout when a peer never arrives, bit-exact parity with the oracle, relative stop, fp64 accumulation, bf16 and fp8 storage, the streamed solve (block cache, file-backed input), the device group behind one handle (st_group_attach, ST_DEVICES), and 200 random option
     combinations through the launch planner (refused cleanly or bit-exact)."""
     proc = run_emulated(["tests/test_gpu_parity.py", "tests/test_gpu_sharded.py", "tests/test_zz_gpu_bitexact.py",
                          "tests/test_zz_gpu_options_property.py", "tests/test_zzz_gpu_bf16_storage.py",
+                         "tests/test_zzz_gpu_fp8_storage.py",
                          "tests/test_zzzz_gpu_streamed.py", "tests/test_zzzz_gpu_group.py"],
                         max_dim=4200)
     assert proc.returncode == 0, proc.stdout[-4000:]

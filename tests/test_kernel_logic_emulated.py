@@ -184,6 +184,49 @@ def test_bf16_conversion_kernel():
     assert np.array_equal(emu.convert_bf16(base[1:]), oracle.to_bf16(base[1:])[1])
 
 
+# ---- fp8 (e4m3) storage with one power-of-two scale per row --------------------------------------------------
+def test_fp8_conversion_kernel():
+    rng = np.random.default_rng(8)
+    x = (rng.random((37, 64)) * np.exp(rng.normal(0, 6, (37, 1)))).astype(np.float32)     # rows of very different magnitude
+    x[3] = 0                                                                              # an all-zero row keeps scale 1
+    x[5, :4] = [448.0, -448.0, 1e-9, -3.0]                                                # saturation edge, underflow, sign
+    x[7, 9] = np.nan
+    x[11] *= np.float32(1e30)
+    x[12] *= np.float32(1e-30)
+    back, codes, scale = oracle.to_fp8_rows(x)
+    got_codes, got_scale = emu.convert_fp8(x)
+    assert np.array_equal(got_scale, scale) and np.array_equal(got_codes, codes)
+    fin = np.isfinite(x)
+    assert np.all(np.abs(back - x)[fin] <= np.abs(x)[fin] / 16 + (scale[:, None] * np.float32(2.0 ** -10) * np.ones_like(x))[fin])
+    # every code value survives the round trip: 0x00..0x7e and their negatives, in one row with the largest at 448
+    vals = oracle.fp8_e4m3_values()
+    row = np.concatenate([vals, -vals, np.zeros(2, np.float32)])[None, :].astype(np.float32)
+    b2, c2, s2 = oracle.to_fp8_rows(row)
+    assert s2[0] == 1 and np.array_equal(b2, row) and np.array_equal(emu.convert_fp8(row)[0], c2)
+
+
+@pytest.mark.parametrize("kernel,dim,threads,ctas,world", [(11, 16, 32, 1, 1), (11, 640, 64, 3, 1), (11, 1008, 128, 4, 2),
+                                                           (1, 640, 64, 3, 1), (1, 1008, 96, 2, 3)])
+def test_fp8_storage(kernel, dim, threads, ctas, world):
+    back, codes, scale = oracle.to_fp8_rows(U(dim))
+    same_bits(emu.solve(codes, dim, kernel=kernel, threads=threads, ctas=ctas, world=world, fp8_scale=scale),
+              expect(back, sum_mode=oracle.SUM_CUDA_FP8))
+
+
+def test_fp8_storage_extras():
+    back, codes, scale = oracle.to_fp8_rows(U(8208))                         # two units per row: 8192 + 16 columns
+    for kernel in (11, 1):
+        same_bits(emu.solve(codes, 8208, kernel=kernel, threads=128, ctas=6, max_iter=3, fp8_scale=scale),
+                  expect(back, sum_mode=oracle.SUM_CUDA_FP8, max_iter=3))
+    H = oracle.hilbert(512)                                                  # Hilbert: entries down to 1/1023 of the row's first
+    back, codes, scale = oracle.to_fp8_rows(H)
+    kw = dict(stop=1, eps=1e-5, max_iter=60)
+    same_bits(emu.solve(codes, 512, kernel=11, threads=64, ctas=4, fp8_scale=scale, **kw),
+              expect(back, sum_mode=oracle.SUM_CUDA_FP8, **kw))
+    val = emu.solve(codes, 512, kernel=11, threads=64, ctas=4, fp8_scale=scale)[0]
+    assert abs(val - expect(H)[0]) < 0.02 * expect(H)[0]                     # the storage format moves lambda by ~1 %
+
+
 # ---- several emulated GPUs: the fused exchange and its flat barrier ---------------------------------------
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kernel", [1, 13])

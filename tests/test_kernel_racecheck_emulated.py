@@ -44,12 +44,12 @@ def test_positive_control_missing_syncthreads_is_reported(tsan_exe):
 
 def test_round_kernels_are_race_free(tsan_exe):
     """general loop (both forms, scalar, relative stop), resident-e (prefetch, static / dynamic units, resident
-    rows, bf16, two units per row, fp64 accumulation), cluster kernel, wide kernel (one and three windows, 2 GPUs), 2 and 3
+    rows, bf16, two units per row, fp64 accumulation, scalar units for dim % 4 != 0 on one and two GPUs), cluster kernel, wide kernel (one and three windows, 2 GPUs), 2 and 3
     emulated GPUs (tsan_main.cpp)."""
     proc = run(tsan_exe)
     assert "ThreadSanitizer" not in proc.stderr, proc.stderr[:4000]
     assert proc.returncode == 0, proc.stdout
-    assert proc.stdout.count("rc=0") == 15 and "agree=0" not in proc.stdout
+    assert proc.stdout.count("rc=0") == 17 and "agree=0" not in proc.stdout
 
 
 MUTANTS = [

@@ -216,6 +216,65 @@ def test_bf16_storage_solve_is_an_fp32_solve_of_the_rounded_matrix():
     assert np.max(np.abs(low[1] / low[1].max() - same_matrix_fp32_order[1] / same_matrix_fp32_order[1].max())) <= 1e-4
 
 
+# ---- fp8 STORAGE of the matrix with one power-of-two scale per row (opt-in extension) ----
+@pytest.mark.parametrize("dim", [16, 64, 272, 1008, 8192, 8208, 16400])
+def test_fp8_storage_order_matches_the_numpy_restatement(dim):
+    rng = np.random.default_rng(dim)
+    rows = min(3, dim)
+    mat = np.zeros((dim, dim), dtype=np.float32)
+    mat[:rows] = oracle.to_fp8_rows((rng.random((rows, dim)) + 0.25).astype(np.float32))[0]
+    got = oracle.sum_across_rows(mat, oracle.SUM_CUDA_FP8)[:rows]
+    ones = np.ones(dim, dtype=np.float32)
+    want = np.array([row_dot_cuda_order_numpy(mat[r], ones, unit=16) for r in range(rows)], dtype=np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_to_fp8_rows_rounds_to_the_nearest_code_like_the_hardware_conversion():
+    import torch
+    vals = oracle.fp8_e4m3_values()
+    assert len(vals) == 127 and vals[0] == 0 and vals[1] == 2.0 ** -9 and vals[8] == 2.0 ** -6 and vals[-1] == 448
+    # torch's float8_e4m3fn conversion is round-to-nearest-even on the same grid (it does not saturate: stay below 448)
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.random(50000) * 400, rng.random(50000) * 0.05, vals, (vals[:-1] + vals[1:]) / 2]).astype(np.float32)
+    x = np.concatenate([x, -x, np.zeros((-2 * len(x)) % 16, np.float32)])
+    row = np.concatenate([x, np.full(16, 448, np.float32)])[None, :]             # the row's largest magnitude: scale 1
+    back, codes, scale = oracle.to_fp8_rows(row)
+    assert scale[0] == 1
+    t = torch.from_numpy(row[0]).to(torch.float8_e4m3fn)
+    assert np.array_equal(t.view(torch.uint8).numpy(), codes[0])
+    assert np.array_equal(t.to(torch.float32).numpy(), back[0])
+    # ties go to the even code: half way between 16 (0x58) and 18 (0x59) -> 16; between 18 and 20 (0x5a) -> 20
+    r = np.zeros((1, 16), np.float32)
+    r[0, :3] = [448, 17, 19]
+    assert list(oracle.to_fp8_rows(r)[0][0, 1:3]) == [16, 20]
+    # scales: the largest magnitude of a row lands in (224, 448]; powers of two; all-zero rows keep 1
+    m = (rng.random((64, 32)) * np.exp(rng.normal(0, 8, (64, 1)))).astype(np.float32)
+    m[5] = 0
+    b, c, sc = oracle.to_fp8_rows(m)
+    top = np.max(np.abs(m), axis=1) / sc
+    assert sc[5] == 1 and np.all((top[np.arange(64) != 5] > 224) & (top[np.arange(64) != 5] <= 448))
+    assert np.all(np.frexp(sc)[0] == 0.5)
+    assert np.all(np.abs(b - m) <= np.abs(m) / 16 + sc[:, None] * 2.0 ** -10)
+
+
+def test_fp8_storage_solve_is_an_fp32_solve_of_the_dequantised_matrix():
+    H = oracle.hilbert(1024)
+    Hq, codes, scale = oracle.to_fp8_rows(H)
+    assert np.all(Hq > 0)                                 # 1/(r+c+1) spans a factor <= 2047 per row: nothing rounds to zero
+    full = oracle.similarity_transform(H, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    low = oracle.similarity_transform(Hq, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA_FP8)
+    same_matrix_fp32_order = oracle.similarity_transform(Hq, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA)
+    # the storage format moves lambda by the rounding of the entries (<= 2^-4 relative each, mostly cancelling) ...
+    assert 1e-4 < abs(float(low[0]) - float(full[0])) / float(full[0]) < 0.03
+    # ... while the 16-element order alone is within the usual summation-order tolerance
+    assert abs(low[3] - same_matrix_fp32_order[3]) <= 1
+    assert abs(float(low[0]) - float(same_matrix_fp32_order[0])) <= 1e-5 * float(low[0])
+    # multiplying a row by its power-of-two scale commutes with the rounding of its sum: scaling every row of the
+    # CODES' values by the row scale before or after the reduction gives the same bits
+    q = Hq / scale[:, None]
+    assert np.array_equal(oracle.sum_across_rows(q, oracle.SUM_CUDA_FP8) * scale, oracle.sum_across_rows(Hq, oracle.SUM_CUDA_FP8))
+
+
 # ---- fp64 accumulation (opt-in extension; ST_ACC_F64 / SUM_CUDA_F64) -------------------------------------------
 def row_dot_cuda_order_f64_numpy(row, scale):
     """SUM_CUDA's order with double accumulators: the product of two floats is exact in double, every add
