@@ -703,9 +703,9 @@ int
 st_convert_f32_to_fp8(void* ctx, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows, uint32_t dim)
 {
   return guarded([&] {
-    if (!d_src || !d_dst || !d_row_scale || rows == 0 || dim == 0 || dim % 16u != 0u ||
+    if (!d_src || !d_dst || !d_row_scale || rows == 0 || dim == 0 || dim % 4u != 0u ||
         (reinterpret_cast<uintptr_t>(d_src) & 15u) != 0 || (reinterpret_cast<uintptr_t>(d_dst) & 15u) != 0)
-      throw std::invalid_argument("st_convert_f32_to_fp8: needs dim % 16 == 0 and 16-byte aligned buffers");
+      throw std::invalid_argument("st_convert_f32_to_fp8: needs dim % 4 == 0 and 16-byte aligned buffers");
     return convert_to_fp8(*as_ctx(ctx), d_src, d_dst, d_row_scale, rows, dim);
   });
 }

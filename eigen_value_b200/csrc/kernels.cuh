@@ -253,14 +253,16 @@ warp_sum(double v)
 // The matrix is held as bfloat16 (2 bytes per element: half the HBM bytes per round); everything
 // else -- the eigenvector, the row sums, every accumulation -- stays fp32.  bf16 -> fp32 is exact
 // (the 16 bits become the high half of the float), so a solve on bf16 storage returns exactly the
-// bits an fp32-storage solve returns on the bf16-rounded matrix, evaluated in this order: the unit
-// is one 128-bit load = 8 consecutive elements, folded into its accumulator with 8 sequential FMAs;
-// unit j -> lane j % 32, accumulator (j / 32) % 8, as for fp32 (oracle: ORACLE_SUM_CUDA_BF16).
+// bits an fp32-storage solve returns on the bf16-rounded matrix, in the fp32 kernels' own order: the unit
+// is one 64-bit load = FOUR consecutive elements, folded into its accumulator with four sequential FMAs;
+// unit j -> lane j % 32, accumulator (j / 32) % 8 (oracle: ORACLE_SUM_CUDA on oracle.to_bf16(mat)).
+// (The first build loaded 128 bits = 8 elements per lane: a lane then needs two float4 of e, 32 bytes apart from
+// its neighbour's -- a 2-way bank conflict on every LDS.128, 6.0 TB/s of bf16 bytes.  With 64-bit loads the 32
+// lanes read 32 consecutive float4 of e, and 16 loads in flight per lane keep the same 4 KB per warp on its way.)
 struct bf16_t
 {
   unsigned short bits;
 };
-
 
 // little-endian: the element at the lower address is the low half of the 32-bit word
 __device__ __forceinline__ float
@@ -275,48 +277,42 @@ bf16_hi(uint32_t w)
 }
 
 __device__ __forceinline__ float
-dot_acc(uint4 a, float4 e0, float4 e1, float acc)
+dot_acc(uint2 a, float4 e, float acc)
 {
-  acc = fmaf(bf16_lo(a.x), e0.x, acc);
-  acc = fmaf(bf16_hi(a.x), e0.y, acc);
-  acc = fmaf(bf16_lo(a.y), e0.z, acc);
-  acc = fmaf(bf16_hi(a.y), e0.w, acc);
-  acc = fmaf(bf16_lo(a.z), e1.x, acc);
-  acc = fmaf(bf16_hi(a.z), e1.y, acc);
-  acc = fmaf(bf16_lo(a.w), e1.z, acc);
-  acc = fmaf(bf16_hi(a.w), e1.w, acc);
+  acc = fmaf(bf16_lo(a.x), e.x, acc);
+  acc = fmaf(bf16_hi(a.x), e.y, acc);
+  acc = fmaf(bf16_lo(a.y), e.z, acc);
+  acc = fmaf(bf16_hi(a.y), e.w, acc);
   return acc;
 }
 
-// One row segment of bf16 storage, one warp: `nu` units of 8 elements starting at `a`; the matching
-// eigenvector entries are es[2 j], es[2 j + 1] (float4, shared memory).  Same loop shape as
-// row_dot_readonly; LD = independent 128-bit loads in flight per lane.
-template<int LD>
+// One row segment of bf16 storage, one warp: `nu` units of 4 elements starting at `a`; the matching
+// eigenvector entries are es[j] (float4, shared memory).  Same loop shape as row_dot_readonly; LDN = independent
+// 64-bit loads in flight per lane.
+template<int LDN>
 __device__ __forceinline__ float
-row_dot_bf16(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lane)
+row_dot_bf16(const uint2* __restrict__ a, const float4* es, uint32_t nu, int lane)
 {
-  static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
+  static_assert(LDN % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
   float acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
     acc[u] = 0.f;
   uint32_t i = (uint32_t)lane;
-  for (; i + 32u * (LD - 1) < nu; i += 32u * LD) {
-    uint4 v[LD];
+  for (; i + 32u * (LDN - 1) < nu; i += 32u * LDN) {
+    uint2 v[LDN];
 #pragma unroll
-    for (int u = 0; u < LD; u++)
+    for (int u = 0; u < LDN; u++)
       v[u] = ld_stream(a + i + 32u * u);
 #pragma unroll
-    for (int u = 0; u < LD; u++) {
-      const uint32_t j = i + 32u * u;
-      acc[u % kUnroll] = dot_acc(v[u], es[2u * j], es[2u * j + 1u], acc[u % kUnroll]);
-    }
+    for (int u = 0; u < LDN; u++)
+      acc[u % kUnroll] = dot_acc(v[u], es[i + 32u * u], acc[u % kUnroll]);
   }
 #pragma unroll
-  for (int u = 0; u < LD; u++) {
+  for (int u = 0; u < LDN; u++) {
     const uint32_t j = i + 32u * u;
     if (j < nu)
-      acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[2u * j], es[2u * j + 1u], acc[u % kUnroll]);
+      acc[u % kUnroll] = dot_acc(ld_stream(a + j), es[j], acc[u % kUnroll]);
   }
 #pragma unroll
   for (int s = kUnroll / 2; s >= 1; s >>= 1)
@@ -331,56 +327,77 @@ row_dot_bf16(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lan
 // A[r][c] ~= row_scale[r] * q[r][c], with the scale chosen so that the row's largest magnitude lands in (224, 448]
 // (st_convert_f32_to_fp8).  A quarter of the HBM bytes per round; e, s and every accumulation stay fp32.  e4m3 -> fp32
 // is exact and the scale is a power of two, so the solve returns exactly the bits of an fp32 solve of the dequantised
-// matrix evaluated in this order: the unit is one 128-bit load = 16 consecutive elements, folded into its accumulator
-// with 16 sequential FMAs; unit j -> lane j % 32, accumulator (j / 32) % 8 as for fp32; the row's sum is multiplied
-// by its scale once, before the division by e[r] (oracle: ORACLE_SUM_CUDA_FP8 on oracle.to_fp8_rows(mat)).
+// matrix in the fp32 kernels' own order: the unit is one 32-bit word = FOUR consecutive elements, folded into its
+// accumulator with four sequential FMAs; unit j -> lane j % 32, accumulator (j / 32) % 8; the row's sum is multiplied
+// by its scale once, before the division by e[r] (oracle: ORACLE_SUM_CUDA on oracle.to_fp8_rows(mat)).  A row
+// that holds a NaN gets the scale NaN: its sum is NaN in every round, as it would be in fp32.
+//
+// Why 4-byte loads: with one 128-bit load per lane (16 elements; the first build) a lane needs FOUR float4 of e from
+// shared memory per load, 64 bytes apart from its neighbour's -- a 4-way bank conflict on every LDS.128, which capped
+// the kernel at 2.0 TB/s of fp8 bytes whatever the decode cost (profiles/r2_c23_storage_fp8_cvt_decode.json,
+// r2_c24_storage_fp8_integer_decode.json).  With one word per lane the 32 lanes read 32 consecutive float4 of e
+// (conflict-free) and a warp request is still a full 128-byte line; 32 loads in flight per lane keep 4 KB per warp
+// on its way, as in every other build.
 struct fp8_t
 {
   unsigned char bits;
 };
 
+// Decode without the conversion pipe: the 7 magnitude bits of a code, moved to bits 26..20 of a float, ARE the code's
+// value times 2^-120 -- normal codes land on normal floats with the exponent field e (value 2^(e-127) (1 + m/8)
+// instead of 2^(e-7) (1 + m/8)), subnormal codes on subnormal floats (m 2^-129 instead of m 2^-9), and FFMA takes
+// subnormal inputs at full speed.  So the kernels keep the eigenvector they multiply with PRE-SCALED by 2^120 (exact),
+// and fmaf(raw, e * 2^120, acc) rounds the same real number as fmaf(q, e, acc).  Two or three integer operations per
+// element: byte i to the top of the word, arithmetic shift right by 4 (the sign stays in bit 31), one mask.  The code
+// 0x7f is therefore the finite value 480, not a NaN: st_convert_f32_to_fp8 never emits it for finite input and marks a
+// row that holds a NaN through its scale instead.
+constexpr float kFp8EigenScale = 0x1p120f;
+constexpr float kFp8EigenUnscale = 0x1p-120f;
+
 __device__ __forceinline__ float
-dot_acc_fp8(uint4 a, const float4* e, float acc)
+fp8_raw(uint32_t w, int byte)
 {
-  const uint32_t w[4] = { a.x, a.y, a.z, a.w };
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const float4 q = fp8x4_to_float4(w[i]);
-    const float4 ev = e[i];
-    acc = fmaf(q.x, ev.x, acc);
-    acc = fmaf(q.y, ev.y, acc);
-    acc = fmaf(q.z, ev.z, acc);
-    acc = fmaf(q.w, ev.w, acc);
-  }
+  const int32_t top = (int32_t)(w << (24 - 8 * byte));
+  return __uint_as_float((uint32_t)(top >> 4) & 0x87f00000u);
+}
+
+// e: the matching four eigenvector entries, pre-scaled by 2^120
+__device__ __forceinline__ float
+dot_acc_fp8(uint32_t w, float4 e, float acc)
+{
+  acc = fmaf(fp8_raw(w, 0), e.x, acc);
+  acc = fmaf(fp8_raw(w, 1), e.y, acc);
+  acc = fmaf(fp8_raw(w, 2), e.z, acc);
+  acc = fmaf(fp8_raw(w, 3), e.w, acc);
   return acc;
 }
 
-// One row segment of fp8 storage, one warp: `nu` units of 16 elements starting at `a`; the matching eigenvector
-// entries are es[4 j .. 4 j + 3] (float4, shared memory).  Same loop shape as row_dot_bf16.
-template<int LD>
+// One row segment of fp8 storage, one warp: `nw` words of four elements starting at `a`; the matching eigenvector
+// entries are es[j] (float4, shared memory, pre-scaled).  Same loop shape as row_dot_readonly<1>: LDN 4-byte loads in flight.
+template<int LDN>
 __device__ __forceinline__ float
-row_dot_fp8(const uint4* __restrict__ a, const float4* es, uint32_t nu, int lane)
+row_dot_fp8(const uint32_t* __restrict__ a, const float4* es, uint32_t nw, int lane)
 {
-  static_assert(LD % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
+  static_assert(LDN % kUnroll == 0, "loads in flight must be a multiple of the accumulator count");
   float acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++)
     acc[u] = 0.f;
   uint32_t i = (uint32_t)lane;
-  for (; i + 32u * (LD - 1) < nu; i += 32u * LD) {
-    uint4 v[LD];
+  for (; i + 32u * (LDN - 1) < nw; i += 32u * LDN) {
+    uint32_t v[LDN];
 #pragma unroll
-    for (int u = 0; u < LD; u++)
+    for (int u = 0; u < LDN; u++)
       v[u] = ld_stream(a + i + 32u * u);
 #pragma unroll
-    for (int u = 0; u < LD; u++)
-      acc[u % kUnroll] = dot_acc_fp8(v[u], es + 4u * (i + 32u * u), acc[u % kUnroll]);
+    for (int u = 0; u < LDN; u++)
+      acc[u % kUnroll] = dot_acc_fp8(v[u], es[i + 32u * u], acc[u % kUnroll]);
   }
 #pragma unroll
-  for (int u = 0; u < LD; u++) {
+  for (int u = 0; u < LDN; u++) {
     const uint32_t j = i + 32u * u;
-    if (j < nu)
-      acc[u % kUnroll] = dot_acc_fp8(ld_stream(a + j), es + 4u * j, acc[u % kUnroll]);
+    if (j < nw)
+      acc[u % kUnroll] = dot_acc_fp8(ld_stream(a + j), es[j], acc[u % kUnroll]);
   }
 #pragma unroll
   for (int s = kUnroll / 2; s >= 1; s >>= 1)
@@ -644,9 +661,9 @@ template<int VEC, int FORM, int MAX_THREADS, int STOP = kStopAbsolute, typename 
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundParams p)
 {
   static_assert(sizeof(ACC) == 4 || (sizeof(T) == 4 && FORM == kFormReadOnly), "fp64 accumulation: fp32 storage, read-only form");
-  constexpr bool kBf16 = sizeof(T) == 2; // p.A then points to bf16 storage (read-only form, N % 8 == 0)
+  constexpr bool kBf16 = sizeof(T) == 2; // p.A then points to bf16 storage (read-only form, N % 4 == 0)
   static_assert(!kBf16 || (VEC == 4 && FORM == kFormReadOnly), "bf16 storage: read-only form, vector loads");
-  constexpr bool kFp8 = sizeof(T) == 1; // p.A points to e4m3 storage, p.row_scale to the row scales (read-only form, N % 16 == 0)
+  constexpr bool kFp8 = sizeof(T) == 1; // p.A points to e4m3 storage, p.row_scale to the row scales (read-only form, N % 4 == 0)
   static_assert(!kFp8 || (VEC == 4 && FORM == kFormReadOnly && sizeof(ACC) == 4), "fp8 storage: read-only form, vector loads, fp32 accumulation");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (multiple of 32, <= MAX_THREADS)
   extern __shared__ __align__(16) float smem[];
@@ -729,6 +746,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
                 v.z = ep[j].z * (sp[j].z / m_prev);
                 v.w = ep[j].w * (sp[j].w / m_prev);
               }
+              if (kFp8) { // fp8 storage multiplies with e * 2^120 (dot_acc_fp8)
+                v.x *= kFp8EigenScale;
+                v.y *= kFp8EigenScale;
+                v.z *= kFp8EigenScale;
+                v.w *= kFp8EigenScale;
+              }
               sc4[vi] = v;
             }
           }
@@ -760,11 +783,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
           const float* sc = scale_s + s0;
           float t;
           if (kFp8) {
-            const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const fp8_t*>(p.A) + off);
-            t = row_dot_fp8<kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 4, lane);
+            const uint32_t* seg = reinterpret_cast<const uint32_t*>(reinterpret_cast<const fp8_t*>(p.A) + off);
+            t = row_dot_fp8<4 * kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 2, lane);
           } else if (kBf16) {
-            const uint4* seg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.A) + off);
-            t = row_dot_bf16<kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 3, lane);
+            const uint2* seg = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16_t*>(p.A) + off);
+            t = row_dot_bf16<2 * kUnroll>(seg, reinterpret_cast<const float4*>(sc), slen >> 2, lane);
           } else if (FORM == kFormReadOnly) {
             if (sizeof(ACC) == 8)
               t = row_dot_readonly<VEC, false, ACC>(p.A + off, sc, slen, lane);
@@ -1164,7 +1187,7 @@ __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restri
     dst[i] = f32_to_bf16_rn(src[i]);
 }
 
-// fp32 -> fp8 storage, one warp per row (dim % 16 == 0, 16-byte aligned rows): the row's largest magnitude a gives the
+// fp32 -> fp8 storage, one warp per row (dim % 4 == 0, 16-byte aligned source rows): the row's largest magnitude a gives the
 // scale 2^k with a / 2^k in (224, 448] (k clamped to +-118; an all-zero or non-finite row keeps scale 1), every element
 // is divided by it -- exact -- and rounded to the nearest e4m3 code, ties to even, saturating.
 __device__ __forceinline__ float
@@ -1189,17 +1212,22 @@ __global__ void __launch_bounds__(256) convert_fp8_rows_kernel(const float* __re
   for (uint32_t r = gw; r < rows; r += warps) {
     const float4* row = reinterpret_cast<const float4*>(src + (size_t)r * dim);
     float amax = 0.f;
+    float has_nan = 0.f;
     for (uint32_t i = lane; i < nv; i += 32u) {
       const float4 v = row[i];
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      if ((v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w))
+        has_nan = 1.f;
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1)
+    for (int o = 16; o >= 1; o >>= 1) {
       amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      has_nan = fmaxf(has_nan, __shfl_xor_sync(0xffffffffu, has_nan, o));
+    }
     const float scale = fp8_row_scale(amax);
     const float inv = 1.f / scale; // a power of two: exact
     if (lane == 0)
-      row_scale[r] = scale;
+      row_scale[r] = has_nan != 0.f ? __uint_as_float(0x7fc00000u) : scale; // the codes cannot carry a NaN (fp8_raw): the scale does
     uint32_t* out = reinterpret_cast<uint32_t*>(dst + (size_t)r * dim);
     for (uint32_t i = lane; i < nv; i += 32u) {
       const float4 v = row[i];

@@ -149,6 +149,24 @@ ld_stream(const uint4* p)
   return v;
 }
 
+// one 64-bit word of bf16 storage (four elements)
+__device__ __forceinline__ uint2
+ld_stream(const uint2* p)
+{
+  uint2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// one 32-bit word of fp8 storage (four elements)
+__device__ __forceinline__ uint32_t
+ld_stream(const uint32_t* p)
+{
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ unsigned long long
 l2_policy_evict_last()
 {
@@ -175,34 +193,6 @@ f32_to_bf16_rn(float x)
 }
 
 // ---- fp8 (e4m3) storage of the matrix ---------------------------------------------------------------
-// Four consecutive elements (lowest address = lowest byte of the word) -> fp32.  e4m3 -> f16 -> f32 is exact at
-// both steps (4 exponent / 3 mantissa bits fit f16's 5 / 10), subnormals included.
-__device__ __forceinline__ float4
-fp8x4_to_float4(uint32_t w)
-{
-  uint32_t h0, h1;
-  asm("{\n\t.reg .b16 lo, hi;\n\t"
-      "mov.b32 {lo, hi}, %2;\n\t"
-      "cvt.rn.f16x2.e4m3x2 %0, lo;\n\t"
-      "cvt.rn.f16x2.e4m3x2 %1, hi;\n\t}"
-      : "=r"(h0), "=r"(h1)
-      : "r"(w));
-  float4 f;
-  asm("{\n\t.reg .b16 a, b;\n\t"
-      "mov.b32 {a, b}, %2;\n\t"
-      "cvt.f32.f16 %0, a;\n\t"
-      "cvt.f32.f16 %1, b;\n\t}"
-      : "=f"(f.x), "=f"(f.y)
-      : "r"(h0));
-  asm("{\n\t.reg .b16 a, b;\n\t"
-      "mov.b32 {a, b}, %2;\n\t"
-      "cvt.f32.f16 %0, a;\n\t"
-      "cvt.f32.f16 %1, b;\n\t}"
-      : "=f"(f.z), "=f"(f.w)
-      : "r"(h1));
-  return f;
-}
-
 // two floats -> two e4m3 codes, round to nearest even, saturating at +-448 (NaN -> 0x7f); `lo` lands in the low byte
 __device__ __forceinline__ unsigned short
 f32x2_to_fp8x2(float lo, float hi)

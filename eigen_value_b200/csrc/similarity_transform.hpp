@@ -48,8 +48,8 @@ public:
   CUstream_st* stream() const { return stream_; }
 
   // Whole round loop on device-resident rows.  shard == nullptr: single GPU (rows == dim).
-  // bf16 == true: d_rows points to bfloat16 storage (read-only form, dim % 8 == 0); d_row_scale != nullptr: d_rows
-  // points to fp8 (e4m3) storage with one power-of-two scale per owned row (read-only form, dim % 16 == 0); fp32 otherwise.
+  // bf16 == true: d_rows points to bfloat16 storage (read-only form, dim % 4 == 0); d_row_scale != nullptr: d_rows
+  // points to fp8 (e4m3) storage with one power-of-two scale per owned row (read-only form, dim % 4 == 0); fp32 otherwise.
   int solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* shard,
             float* d_eigen_vec, st_result* res, bool bf16 = false, const float* d_row_scale = nullptr);
   // shard != nullptr (device group): h_mat is still the whole matrix; this context uploads and solves
@@ -191,7 +191,7 @@ int generate_uniform_matrix(st::Context& q, float* d_rows, const uint dim, uint6
                             const uint row0 = 0, const uint rows = 0);
 // fp32 -> bf16 (round to nearest even) on the device, for the bf16-storage solves
 int convert_to_bf16(st::Context& q, const float* d_src, uint16_t* d_dst, size_t count);
-// fp32 -> fp8 (e4m3) storage with one power-of-two scale per row, on the device (dim % 16 == 0, 16-byte aligned rows)
+// fp32 -> fp8 (e4m3) storage with one power-of-two scale per row, on the device (dim % 4 == 0, 16-byte aligned rows)
 int convert_to_fp8(st::Context& q, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows, uint32_t dim);
 
 namespace st {

@@ -399,7 +399,7 @@ launch_sc(int id, int stop, const RoundParams& p, int grid, int threads, size_t 
   }
 }
 
-// ---- bf16 storage (read-only form, N % 8 == 0): resident-e kernel without prefetch slots for
+// ---- bf16 storage (read-only form, N % 4 == 0): resident-e kernel without prefetch slots for
 // N <= 32768, the general chunked loop above it --------------------------------------------------
 constexpr int kScBf16Id = 11; // {512 threads, no prefetch}: the one resident-e configuration built for bf16
 
@@ -542,17 +542,17 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   const bool fp8 = d_row_scale != nullptr;
   const bool narrow = bf16 || fp8; // storage below fp32: configuration 11 or the general loop
   if (fp8) {
-    if (bf16 || acc64 || form != kFormReadOnly || dim % 16u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
-      throw std::invalid_argument("solve: fp8 storage needs the read-only form, fp32 accumulation, dim % 16 == 0 and a 16-byte aligned matrix");
+    if (bf16 || acc64 || form != kFormReadOnly || dim % 4u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
+      throw std::invalid_argument("solve: fp8 storage needs the read-only form, fp32 accumulation, dim % 4 == 0 and a 16-byte aligned matrix");
     if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != kScBf16Id)
       throw std::invalid_argument("solve: fp8 storage is built for kernel 0 (automatic), 1 (general loop) and 11 (resident-e)");
     if (opt.kernel == kScBf16Id && dim > (uint32_t)kResidentCols)
       throw std::invalid_argument("solve: resident-e kernel needs dim <= 32768");
   }
   if (bf16) {
-    // d_rows points to bfloat16 storage: 128-bit loads of 8 elements, fp32 everywhere else
-    if (form != kFormReadOnly || dim % 8u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
-      throw std::invalid_argument("solve: bf16 storage needs the read-only form, dim % 8 == 0 and a 16-byte aligned matrix");
+    // d_rows points to bfloat16 storage: 64-bit loads of 4 elements, fp32 everywhere else
+    if (form != kFormReadOnly || dim % 4u != 0u || (reinterpret_cast<uintptr_t>(d_rows) & 15u) != 0)
+      throw std::invalid_argument("solve: bf16 storage needs the read-only form, dim % 4 == 0 and a 16-byte aligned matrix");
     if (opt.kernel != 0 && opt.kernel != 1 && opt.kernel != kScBf16Id)
       throw std::invalid_argument("solve: bf16 storage is built for kernel 0 (automatic), 1 (general loop) and 11 (resident-e)");
     if (opt.kernel == kScBf16Id && dim > (uint32_t)kResidentCols)
@@ -639,6 +639,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   uint32_t rows_cap = 0;
   size_t smem = 0;
   const ScConfig* sc = nullptr;
+  bool sc_ring = false;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
   if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !narrow && !acc64 && dim <= (uint32_t)kClusterCols)) {
@@ -680,7 +681,19 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       int g, t;
       uint32_t cap, moff = 0;
       shape(c.max_threads, false, &g, &t, &cap);
-      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, &moff);
+      size_t need = sc_smem_bytes(t, c.pf_batches, dim, &moff);
+      // scalar units: through the per-warp ring of bulk copies when the matrix is 16-byte aligned and the ring fits
+      // next to e under the carve-out step (N <= ~15800 at 512 threads); st_options.sweep bit 4 keeps the 4-byte loads
+      sc_ring = false;
+      if (readonly1 && aligned16(d_rows) && !(opt.sweep & 16)) {
+        uint32_t rmoff = 0;
+        const size_t rneed = sc_smem_bytes(t, 0, dim, &rmoff, kScalarRingSlots);
+        if (rneed <= kScalarRingSmemLimit) {
+          sc_ring = true;
+          need = rneed;
+          moff = rmoff;
+        }
+      }
       if (need <= kSmemLimit) {
         sc = &c;
         grid = g;
@@ -788,6 +801,11 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_cluster<kStopRelative>(p, cluster_ctas, smem, stream_);
     else
       launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
+  } else if (sc && readonly1 && sc_ring) {
+    if (stop == kStopRelative)
+      launch_cooperative(round_loop_sc_kernel<512, kScalarRingSlots, kStopRelative, float, float, 1>, p, grid, threads, smem, stream_);
+    else
+      launch_cooperative(round_loop_sc_kernel<512, kScalarRingSlots, kStopAbsolute, float, float, 1>, p, grid, threads, smem, stream_);
   } else if (sc && readonly1) {
     if (stop == kStopRelative)
       launch_cooperative(round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>, p, grid, threads, smem, stream_);

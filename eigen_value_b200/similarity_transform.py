@@ -249,7 +249,7 @@ class Solver:
 
     def to_fp8(self, d_src: DeviceBuffer, rows: int, dim: int) -> Tuple[DeviceBuffer, DeviceBuffer]:
         """fp32 -> fp8 (e4m3) storage with one power-of-two scale per row, on the device: (codes, row scales), the
-        storage for solve_device(..., fp8_scale=...).  dim % 16 == 0."""
+        storage for solve_device(..., fp8_scale=...).  dim % 4 == 0."""
         codes, scale = self.alloc(rows * dim), self.alloc(4 * rows)
         check(self.lib.st_convert_f32_to_fp8(self.ctx, d_src.ptr, codes.ptr, scale.ptr, rows, dim), "st_convert_f32_to_fp8")
         return codes, scale
@@ -263,8 +263,8 @@ class Solver:
                      **opts) -> Tuple[SolveInfo, Optional[np.ndarray]]:
         """similarity_transform() on a device-resident matrix.  Returns (info, eigen_vec);
         eigen_vec is downloaded only when no device output buffer was supplied.  bf16=True: d_mat
-        holds bfloat16 storage (see to_bf16; opt-in, changes results, dim % 8 == 0).  fp8_scale=<row scales>: d_mat
-        holds fp8 storage (see to_fp8; opt-in, changes results, dim % 16 == 0)."""
+        holds bfloat16 storage (see to_bf16; opt-in, changes results, dim % 4 == 0).  fp8_scale=<row scales>: d_mat
+        holds fp8 storage (see to_fp8; opt-in, changes results, dim % 4 == 0)."""
         o = make_options(self.lib, **opts)
         res = StResult()
         own = d_eigen_vec is None

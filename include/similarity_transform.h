@@ -192,7 +192,7 @@ int st_solve_host(void* ctx, const float* h_mat, uint32_t dim, const st_options*
 /* bf16 STORAGE of the matrix (opt-in; changes results, so outside reference parity): the matrix is
  * held as bfloat16 -- half the HBM bytes per round -- while the eigenvector, the row sums and every
  * accumulation stay fp32.  bf16 -> fp32 is exact, so the result is bit-identical to an fp32 solve of
- * the bf16-rounded matrix evaluated in 8-element units.  Read-only form only; dim % 8 == 0; kernels 0
+ * the bf16-rounded matrix in the fp32 kernels' own evaluation order.  Read-only form only; dim % 4 == 0; kernels 0
  * (automatic), 1 and 11.  st_convert_f32_to_bf16 rounds to nearest even on the device; `count`
  * elements, d_dst 2-byte elements. */
 int st_convert_f32_to_bf16(void* ctx, const float* d_src, uint16_t* d_dst, size_t count);
@@ -203,7 +203,7 @@ int st_solve_device_bf16(void* ctx, const uint16_t* d_mat, uint32_t dim, const s
  * round -- while the eigenvector, the row sums and every accumulation stay fp32.  st_convert_f32_to_fp8 picks each
  * row's scale so that its largest magnitude lands in (224, 448] and rounds to the nearest code, ties to even.
  * e4m3 -> fp32 is exact and the scales are powers of two, so the result is bit-identical to an fp32 solve of the
- * dequantised matrix evaluated in 16-element units.  Read-only form, fp32 accumulation; dim % 16 == 0; kernels 0
+ * dequantised matrix in the fp32 kernels' own evaluation order.  Read-only form, fp32 accumulation; dim % 4 == 0; kernels 0
  * (automatic), 1 and 11.  Entries below 2^-18 of their row's largest one round to zero. */
 int st_convert_f32_to_fp8(void* ctx, const float* d_src, uint8_t* d_dst, float* d_row_scale, uint32_t rows,
                           uint32_t dim);

@@ -25,8 +25,8 @@ FORM_INPLACE, FORM_READONLY = 0, 1
 SUM_SEQUENTIAL, SUM_LANES16, SUM_SUBGROUP32 = 0, 1, 2
 SUM_CUDA = 4   # the CUDA kernels' evaluation order: bit-identical to the GPU (tests/test_zz_gpu_bitexact.py)
 SUM_CUDA_F64 = 6    # SUM_CUDA's order with fp64 accumulators (st_options.accumulate = ST_ACC_F64)
-SUM_CUDA_BF16 = 5   # the same with 8-element units: the kernels' order on bf16 storage (feed to_bf16(mat)[0])
-SUM_CUDA_FP8 = 7    # the same with 16-element units: the kernels' order on fp8 storage (feed to_fp8_rows(mat)[0])
+SUM_CUDA_BF16 = SUM_CUDA  # bf16 storage reduces 4-element words in the fp32 kernels' order (feed to_bf16(mat)[0])
+SUM_CUDA_FP8 = SUM_CUDA   # fp8 storage reduces 4-element words in the fp32 kernels' order (feed to_fp8_rows(mat)[0])
 STOP_ABSOLUTE, STOP_RELATIVE = 0, 1   # the reference's stop test | extension: threshold eps * max(s)
 
 
@@ -143,7 +143,7 @@ def to_fp8_rows(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """fp32 -> fp8 (e4m3) storage with one power-of-two scale per row: what st_convert_f32_to_fp8 does.
     Per row: a = max |x|, scale = 2^k with a / 2^k in (224, 448] (k clamped to +-118; 1 for an all-zero or
     non-finite row); every element divided by the scale (exact) and rounded to the nearest code, ties to the
-    even code, saturating at 448 (cvt.rn.satfinite.e4m3x2.f32; NaN -> 0x7f).
+    even code, saturating at 448 (cvt.rn.satfinite.e4m3x2.f32; NaN -> 0x7f, and the row's scale becomes NaN).
     Returns (the dequantised matrix scale[r] * q[r][c] as fp32 -- exact --, the uint8 codes, the fp32 scales)."""
     a = np.ascontiguousarray(mat, dtype=np.float32)
     rows = a.shape[0]
@@ -152,6 +152,7 @@ def to_fp8_rows(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     m, e = np.frexp(amax)                                    # amax = m * 2^e, m in [0.5, 1)
     k = np.clip(np.where(m <= np.float32(0.875), e - 9, e - 8), -118, 118)
     scale = np.where((amax > 0) & np.isfinite(amax), np.ldexp(np.float32(1), k), np.float32(1)).astype(np.float32)
+    has_nan = np.isnan(a).any(axis=1)
     codes = np.empty(a.shape, dtype=np.uint8)
     back = np.empty(a.shape, dtype=np.float32)
     for r in range(rows):
@@ -168,6 +169,10 @@ def to_fp8_rows(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         codes[r] = c | (sign.astype(np.uint8) << 7)
         v = np.where(nan, np.float32(np.nan), vals[np.minimum(c, 126)])
         back[r] = np.where(sign, -v, v) * scale[r]
+    # the kernels read a code's 7 magnitude bits as a number (0x7f would be 480), so a NaN travels in the row's scale:
+    # the whole row sum is NaN in every round, as it is in an fp32 solve of a matrix with a NaN in that row
+    scale[has_nan] = np.nan
+    back[has_nan] = np.nan
     return back, codes, scale
 
 

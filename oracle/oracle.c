@@ -63,19 +63,12 @@ enum
   ORACLE_SUM_CUDA = 4,       /* the evaluation order of the CUDA round kernels (lane / accumulator /
                                 fold / shuffle tree, FMA): with ORACLE_FORM_READONLY the oracle
                                 then matches the GPU bit for bit (row_dot_cuda_order below) */
-  ORACLE_SUM_CUDA_F64 = 6,   /* ORACLE_SUM_CUDA's order with fp64 accumulators (ST_ACC_F64): products are
+  ORACLE_SUM_CUDA_F64 = 6    /* ORACLE_SUM_CUDA's order with fp64 accumulators (ST_ACC_F64): products are
                                 exact in double, every add rounds once in double, the chunk sum is
                                 rounded to fp32 once; chunk sums of a row are added in fp32 */
-  ORACLE_SUM_CUDA_BF16 = 5,  /* the same order with 8-element units: what the CUDA kernels do on
-                                bf16 STORAGE of the matrix (one 128-bit load = 8 elements).  Feed
-                                the oracle the bf16-rounded matrix (as fp32): bf16 -> fp32 is
-                                exact, so the bits must match the GPU's bf16-storage solve */
-  ORACLE_SUM_CUDA_FP8 = 7    /* the same order with 16-element units: fp8 (e4m3) STORAGE with one
-                                power-of-two scale per row (one 128-bit load = 16 elements).  Feed
-                                the oracle the dequantised matrix scale[r] * q[r][c] (as fp32):
-                                e4m3 -> fp32 is exact and multiplying a row by a power of two
-                                commutes with every rounding of its sum, so the bits must match
-                                the GPU's fp8-storage solve */
+  /* bf16 and fp8 STORAGE of the matrix need no mode of their own: their kernels reduce 4-element words (one
+     64-bit / one 32-bit load) in ORACLE_SUM_CUDA's order, and bf16 -> fp32 / e4m3 -> fp32 are exact: feed the
+     oracle the rounded (dequantised) matrix as fp32 and the bits must match the GPU's solve. */
 };
 
 int
@@ -132,10 +125,9 @@ reduce16(const float* acc)
  * scale == NULL behaves like a vector of ones (fmaf(a, 1, acc) == a + acc exactly). */
 #define ORACLE_CUDA_CHUNK 8192
 static float
-row_dot_cuda_order(const float* row, const float* scale, size_t n, size_t unit)
+row_dot_cuda_order(const float* row, const float* scale, size_t n)
 {
-  /* unit == 0: fp32 storage (float4 when n % 4 == 0, else scalar); unit == 8: bf16 storage; unit == 16: fp8 storage */
-  const size_t vec = unit ? unit : ((n % 4 == 0) ? 4 : 1);
+  const size_t vec = (n % 4 == 0) ? 4 : 1;
   float total = 0.f;
   for (size_t c0 = 0; c0 < n; c0 += ORACLE_CUDA_CHUNK) {
     const size_t clen = n - c0 < ORACLE_CUDA_CHUNK ? n - c0 : ORACLE_CUDA_CHUNK;
@@ -225,13 +217,9 @@ row_dot(const float* row, const float* scale, size_t n, int sum_mode)
     return acc;
   }
   if (sum_mode == ORACLE_SUM_CUDA)
-    return row_dot_cuda_order(row, scale, n, 0);
+    return row_dot_cuda_order(row, scale, n);
   if (sum_mode == ORACLE_SUM_CUDA_F64)
     return row_dot_cuda_order_f64(row, scale, n);
-  if (sum_mode == ORACLE_SUM_CUDA_BF16)
-    return row_dot_cuda_order(row, scale, n, 8); /* n % 8 == 0 required, like the kernels */
-  if (sum_mode == ORACLE_SUM_CUDA_FP8)
-    return row_dot_cuda_order(row, scale, n, 16); /* n % 16 == 0 required, like the kernels */
   if ((sum_mode & 0xff) == ORACLE_SUM_WORKGROUP) {
     const size_t wg = (size_t)(sum_mode >> 8);
     float cell = 0.f; /* the zero-filled global cell (:85-93) */

@@ -77,6 +77,8 @@ inline float ld_stream(const float* p) { return *p; }
 inline float4 ld_stream(const float4* p, unsigned long long) { return *p; }
 inline float ld_stream(const float* p, unsigned long long) { return *p; }
 inline uint4 ld_stream(const uint4* p) { return *p; }
+inline uint32_t ld_stream(const uint32_t* p) { return *p; }
+inline uint2 ld_stream(const uint2* p) { return *p; }
 inline unsigned long long l2_policy_evict_last() { return 0ull; }
 inline unsigned long long l2_policy_evict_first() { return 0ull; }
 
@@ -104,12 +106,6 @@ emu_fp8_value(unsigned char c)
   else
     v = ldexpf(1.f + (float)m / 8.f, e - 7);
   return (c & 0x80) ? -v : v;
-}
-inline float4
-fp8x4_to_float4(uint32_t w)
-{
-  return make_float4(emu_fp8_value((unsigned char)w), emu_fp8_value((unsigned char)(w >> 8)),
-                     emu_fp8_value((unsigned char)(w >> 16)), emu_fp8_value((unsigned char)(w >> 24)));
 }
 // cvt.rn.satfinite.e4m3x2.f32: nearest code, ties to the even code, saturating at 448; NaN -> 0x7f
 inline unsigned char
@@ -160,8 +156,12 @@ emu_bump(uint64_t* bar)
   *bar += 1;
 }
 inline void
-mbar_arrive_expect_tx(uint64_t*, uint32_t)
+mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
+  if (bytes == 0u) { // nothing to wait for: the arrival itself completes the phase (count 1, no pending bytes)
+    EMU_RELEASE(bar);
+    emu_bump(bar);
+  }
 }
 EMU_NO_TSAN inline bool
 mbar_try_wait(uint64_t* bar, uint32_t parity)

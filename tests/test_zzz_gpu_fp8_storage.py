@@ -3,8 +3,8 @@
 The matrix is held as one byte per element (e4m3) plus ONE power-of-two fp32 scale per row -- a quarter of the HBM
 bytes per round -- while the eigenvector, the row sums and every accumulation stay fp32.  It changes results, so it
 is outside reference parity; its own contract is exact all the same: e4m3 -> fp32 is exact and the scales are powers
-of two, so an fp8-storage solve must return the bits of an fp32 solve of the dequantised matrix evaluated in
-16-element units, which is what the oracle computes with to_fp8_rows() + SUM_CUDA_FP8 (pinned on the CPU in
+of two, so an fp8-storage solve must return the bits of an fp32 solve of the dequantised matrix in the fp32 kernels'
+own order (the kernels reduce 4-element words), which is what the oracle computes with to_fp8_rows() + SUM_CUDA (pinned on the CPU in
 tests/test_oracle_cuda_order.py; the kernels' logic is bit-identical to it on the emulation harness,
 tests/test_kernel_logic_emulated.py).  The quantiser is checked code for code: the device's
 cvt.rn.satfinite.e4m3x2.f32 against the oracle's nearest-code search.
@@ -53,14 +53,14 @@ def test_device_conversion_picks_the_same_codes_and_scales(solver):
     back, codes, scale = oracle.to_fp8_rows(x)
     d_codes, d_scale = solver.to_fp8(solver.upload(x), 300, 256)
     solver.synchronize()
-    assert np.array_equal(d_scale.download(np.float32, 300), scale)
+    assert np.array_equal(d_scale.download(np.float32, 300), scale, equal_nan=True) and np.isnan(scale[7])   # the NaN row
     assert np.array_equal(d_codes.download(np.uint8, 300 * 256).reshape(300, 256), codes)
 
 
 @pytest.mark.parametrize("kind", ["hilbert", "uniform"])
-@pytest.mark.parametrize("dim", [16, 64, 512, 1008, 1024, 4096, 8192, 8208, 16384])
+@pytest.mark.parametrize("dim", [4, 16, 64, 508, 1008, 1024, 4096, 8192, 8196, 16384])
 def test_fp8_storage_solve_is_bit_identical_to_the_oracle(solver, kind, dim):
-    # resident-e kernel (configuration 11: no prefetch slots); 8208 / 16384: rows of two work units
+    # resident-e kernel (configuration 11: no prefetch slots); 8196 / 16384: rows of two work units
     mat, back, codes, scale = _case(kind, dim)
     d8, dsc = solver.upload(codes), solver.upload(scale)
     cap = 12 if dim > 4100 else 1000
@@ -113,11 +113,23 @@ def test_relative_stop_on_fp8_storage(solver):
     _same_bits(info, vec, _want(back, eps=1e-6, stop=oracle.STOP_RELATIVE))
 
 
+def test_a_nan_in_the_matrix_travels_in_its_rows_scale_and_runs_to_the_cap(solver):
+    # the kernels read a code's magnitude bits as a number, so the codes cannot carry a NaN: the row's scale does, and
+    # that row's sum is NaN in every round -- the stop test can never hold (like the fp32 path, tests/test_gpu_parity.py)
+    dim = 64
+    mat = oracle.hilbert(dim).copy()
+    mat[5, 7] = np.nan
+    d8, dsc = solver.to_fp8(solver.upload(mat), dim, dim)
+    info, vec = solver.solve_device(d8, dim, fp8_scale=dsc, max_iter=7)
+    assert info.iter_count == 7 and info.passes == 7
+    assert np.isnan(dsc.download(np.float32, dim)[5]) and np.isnan(vec).any()
+
+
 def test_unsupported_combinations_are_refused(solver):
     _, _, codes, scale = _case("hilbert", 64)
     d, dsc = solver.upload(codes), solver.upload(scale)
     with pytest.raises(Exception):
-        solver.solve_device(d, 56, fp8_scale=dsc)                       # dim % 16 != 0
+        solver.solve_device(d, 62, fp8_scale=dsc)                       # dim % 4 != 0
     with pytest.raises(Exception):
         solver.solve_device(d, 64, fp8_scale=dsc, form=FORM_INPLACE)    # read-only form only
     with pytest.raises(Exception):
