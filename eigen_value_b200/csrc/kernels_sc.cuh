@@ -82,108 +82,20 @@ chunk_dot_prefetched(const float4* __restrict__ a, const float4* es, uint32_t nv
   return (float)warp_sum(acc[0]);
 }
 
-// ---- scalar units through shared memory: a per-warp ring of bulk copies ------------------------------------------
-// For dim % 4 != 0 a row starts on a 4-byte boundary: a warp's 4-byte loads of 128 consecutive bytes touch five 32-byte
-// sectors instead of four, and the L2 -> SM path -- what bounds this kernel at N ~ 8192 -- carries a quarter more
-// (profiles/r2_c23_ncu_ragged8191_details.txt: 25.7 of 32 bytes per sector used, DRAM 59 % busy, top stall the L1TEX
-// scoreboard).  When the matrix itself is 16-byte aligned, the bulk-copy engine can fetch the 16-byte-ALIGNED SUPERSET of
-// a 1024-float batch instead (at most 12 bytes more) into a slot of the warp's ring, and the lanes read their elements
-// from shared memory at any 4-byte offset: same element -> lane / accumulator mapping, same bits, sector-exact traffic,
-// and kScalarRingSlots batches in flight per warp.  The one vector at the very end of this GPU's rows that the matrix
-// does not fill is never bulk-copied: a batch that reaches into it reads those (at most 3) floats with plain loads.
-constexpr uint32_t kRingBatch = 1024u;           // floats per batch: 32 lanes x 32 elements = four accumulator rounds
-constexpr uint32_t kRingSlotFloats = 1024u + 4u; // the aligned superset of a batch: up to 3 floats before it, up to 3 after
-
-struct ScalarRing
-{
-  float* slots;            // kScalarRingSlots x kRingSlotFloats
-  uint64_t* bars;          // one mbarrier per slot
-  const float* bulk_end;   // 16-byte floor of the end of this GPU's rows: nothing at or beyond it is bulk-copied
-  uint32_t issued = 0;     // batches issued / consumed by this warp since the kernel started (warp-uniform)
-  uint32_t consumed = 0;
-};
-
-template<int SLOTS>
-__device__ __forceinline__ void
-ring_issue(ScalarRing& r, const float* first, uint32_t cnt, int lane)
-{
-  if (lane == 0) {
-    const uint32_t slot = r.issued % (uint32_t)SLOTS;
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(first) & ~(uintptr_t)15;
-    uintptr_t hi = (reinterpret_cast<uintptr_t>(first + cnt) + 15u) & ~(uintptr_t)15;
-    hi = min(hi, reinterpret_cast<uintptr_t>(r.bulk_end));
-    const uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) : 0u;
-    fence_proxy_async(); // the slot's last readers (generic proxy, ordered by the __syncwarp) come before the copy
-    mbar_arrive_expect_tx(r.bars + slot, bytes);
-    if (bytes)
-      bulk_load(r.slots + slot * kRingSlotFloats, reinterpret_cast<const float*>(lo), bytes, r.bars + slot);
-  }
-  r.issued++;
-}
-
-// One work unit (`len` floats of one row starting at `seg`, against e) through the ring; `pre` batches of it were
-// issued earlier (across the round barrier).  Order = row_dot_readonly<1>: element j -> lane j % 32, accumulator
-// (j / 32) % 8, ascending j.
-template<int SLOTS, typename ACC>
-__device__ __forceinline__ float
-ring_unit_dot(ScalarRing& r, const float* __restrict__ seg, const float* e, uint32_t len, int lane, uint32_t pre,
-              unsigned long long timeout_ns, bool& ok)
-{
-  const uint32_t nb = (len + kRingBatch - 1u) / kRingBatch;
-  for (uint32_t b = pre; b < min((uint32_t)SLOTS, nb); b++)
-    ring_issue<SLOTS>(r, seg + b * kRingBatch, min(kRingBatch, len - b * kRingBatch), lane);
-  ACC acc[kUnroll];
-#pragma unroll
-  for (int u = 0; u < kUnroll; u++)
-    acc[u] = ACC(0);
-  for (uint32_t b = 0; b < nb; b++) {
-    const float* first = seg + b * kRingBatch;
-    const uint32_t cnt = min(kRingBatch, len - b * kRingBatch);
-    const uint32_t slot = r.consumed % (uint32_t)SLOTS;
-    ok &= mbar_wait(r.bars + slot, (r.consumed / (uint32_t)SLOTS) & 1u, timeout_ns);
-    r.consumed++;
-    const float* src = r.slots + slot * kRingSlotFloats + ((reinterpret_cast<uintptr_t>(first) & 15u) >> 2);
-    const float* es = e + b * kRingBatch;
-    if (first + cnt <= r.bulk_end) {
-#pragma unroll
-      for (int t = 0; t < 32; t++) {
-        const uint32_t j = 32u * (uint32_t)t + (uint32_t)lane;
-        if (j < cnt)
-          acc[t % kUnroll] = dot_acc(src[j], es[j], acc[t % kUnroll]);
-      }
-    } else { // the batch reaches into the last, partial vector of this GPU's rows
-#pragma unroll 4
-      for (int t = 0; t < 32; t++) {
-        const uint32_t j = 32u * (uint32_t)t + (uint32_t)lane;
-        if (j < cnt)
-          acc[t % kUnroll] = dot_acc(first + j < r.bulk_end ? src[j] : ld_stream(first + j), es[j], acc[t % kUnroll]);
-      }
-    }
-    __syncwarp(); // every lane has read the slot before lane 0 hands it back to the copy engine
-    if (b + (uint32_t)SLOTS < nb)
-      ring_issue<SLOTS>(r, seg + (b + (uint32_t)SLOTS) * kRingBatch, min(kRingBatch, len - (b + (uint32_t)SLOTS) * kRingBatch), lane);
-  }
-#pragma unroll
-  for (int s = kUnroll / 2; s >= 1; s >>= 1)
-#pragma unroll
-    for (int u = 0; u < s; u++)
-      acc[u] += acc[u + s];
-  return (float)warp_sum(acc[0]);
-}
-
 // VEC = 1: dim % 4 != 0 (or a matrix that is not 16-byte aligned).  Rows then start on 4-byte boundaries, the unit of
 // the evaluation order is a single float (element j of a chunk -> lane j % 32, accumulator (j / 32) % 8: the order
 // round_loop_kernel<1, ...> and the oracle's SUM_CUDA already use for these dimensions), the matrix is streamed with
-// 32 scalar loads in flight per lane (PF_BATCHES == 0) or through a per-warp ring of PF_BATCHES bulk-copy slots (above;
-// the host picks it when the matrix is 16-byte aligned and the ring fits next to e).  Everything else -- units,
-// scheduling, publication, barrier, vector tail -- is shared.
+// 32 scalar loads in flight per lane and there are no prefetch slots (bulk copies need 16-byte alignment).  Everything
+// else -- units, scheduling, publication, barrier, vector tail -- is shared.  (A per-warp two-slot ring of bulk copies
+// of the 16-byte-aligned superset of each 1024-float batch, read back from shared memory at any 4-byte offset -- same
+// bits, sector-exact traffic -- ran at HALF the rate of the plain 4-byte loads: 89.7 against 43.8 us per round at Hilbert
+// 8191, profiles/r2_c25_ragged_ring_vs_scalar_loads.json; removed, commit 22a4650.)
 template<int MAX_THREADS, int PF_BATCHES, int STOP = kStopAbsolute, typename T = float, typename ACC = float, int VEC = 4>
 __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const RoundParams p)
 {
   constexpr int LD = kUnroll; // independent 128-bit loads in flight per lane (16 measured no better, profiles/r1_sweep_resident_e_variants.txt)
   static_assert(sizeof(ACC) == 4 || sizeof(T) == 4, "fp64 accumulation is built for fp32 storage");
-  static_assert(VEC == 4 || (VEC == 1 && sizeof(T) == 4), "scalar units: fp32 storage");
-  constexpr bool kRing = VEC == 1 && PF_BATCHES > 0; // scalar units through a per-warp ring of PF_BATCHES bulk-copy slots
+  static_assert(VEC == 4 || (VEC == 1 && PF_BATCHES == 0 && sizeof(T) == 4), "scalar units: fp32 storage, no prefetch slots");
   // bf16 storage (p.A points to bf16 data, N % 4 == 0): a work unit is still one 8192-column chunk
   // of one row (16 KB); built without the cross-barrier prefetch
   constexpr bool kBf16 = sizeof(T) == 2;
@@ -193,7 +105,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   static_assert(!kFp8 || (PF_BATCHES == 0 && sizeof(ACC) == 4 && VEC == 4), "fp8 storage: no prefetch slots, fp32 accumulation");
   const uint32_t THREADS = blockDim.x; // run-time CTA size (a multiple of 32, <= MAX_THREADS)
   const uint32_t kWarps = THREADS >> 5;
-  constexpr uint32_t kPfFloats = kRing ? PF_BATCHES * kRingSlotFloats : PF_BATCHES * 1024u; // prefetch slot (or ring) per warp
+  constexpr uint32_t kPfFloats = PF_BATCHES * 1024u; // prefetch slot per warp
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* pf_all = reinterpret_cast<float*>(smem_raw);        // kWarps x kPfFloats
@@ -229,15 +141,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   const uint32_t D = (p.dynamic && U > TW) ? U - TW : 0u; // dynamically scheduled units per round
   constexpr uint32_t kChunkVec = kChunkCols / 4;
   float* my_pf = pf_all + (size_t)warp * kPfFloats;
-  uint64_t* my_bar = mbar_all + (kRing ? warp * (uint32_t)PF_BATCHES : warp);
+  uint64_t* my_bar = mbar_all + warp;
   if (PF_BATCHES > 0 && lane == 0)
-    for (int i = 0; i < (kRing ? PF_BATCHES : 1); i++)
-      mbar_init(my_bar + i, 1u);
-  ScalarRing ring;
-  ring.slots = my_pf;
-  ring.bars = my_bar;
-  ring.bulk_end = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(p.A + (size_t)p.rows * p.N) & ~(uintptr_t)15);
-  uint32_t ring_pre = 0; // batches of this warp's first unit of the coming round that were issued across the barrier
+    mbar_init(my_bar, 1u);
   if (tid == 0)
     s_cta_max = 0u;
   for (uint32_t c = tid; c < N; c += THREADS)
@@ -255,7 +161,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   // the warp's prefetch slot, the "prefetch" is issued once, before the first round, and the
   // unit simply stays in shared memory for the whole solve -- N = 1024 (4 KB rows, 64 CTAs) and
   // N = 2048 (8 KB rows, 128 CTAs) never touch the matrix in L2 again after round 0.
-  const bool resident = !kRing && PF_BATCHES > 0 && U <= TW && min(kChunkVec, nv) <= (kPfFloats >> 2);
+  const bool resident = PF_BATCHES > 0 && U <= TW && min(kChunkVec, nv) <= (kPfFloats >> 2);
   if (resident && gw < U) {
     if (lane == 0) {
       const uint32_t rl = gw / nch;
@@ -322,7 +228,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
           const uint32_t seg_nv = min(kChunkVec, nv - ch * kChunkVec);
           const float4* seg = reinterpret_cast<const float4*>(p.A + (size_t)rl * N) + ch * kChunkVec;
           uint32_t npre = 0;
-          if (!kRing && PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
+          if (PF_BATCHES > 0 && first_unit && pf_consumed < pf_issued) {
             tma_ok = mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
             pf_consumed++;
             npre = min(kPfFloats >> 2, seg_nv);
@@ -330,13 +236,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
             npre = seg_nv; // landed before round 0 and never evicted
           }
           float t;
-          if (kRing) {
-            t = ring_unit_dot<(PF_BATCHES > 0 ? PF_BATCHES : 1), ACC>(ring, p.A + (size_t)rl * N + (size_t)ch * kChunkCols,
-                                                                     e_s + (size_t)ch * kChunkCols,
-                                                                     min((uint32_t)kChunkCols, N - ch * (uint32_t)kChunkCols), lane,
-                                                                     first_unit ? ring_pre : 0u, p.timeout_ns, tma_ok);
-            ring_pre = 0;
-          } else if (VEC == 1) {
+          if (VEC == 1) {
             t = row_dot_readonly<1, false, ACC>(p.A + (size_t)rl * N + (size_t)ch * kChunkCols, e_s + (size_t)ch * kChunkCols,
                                                 min((uint32_t)kChunkCols, N - ch * (uint32_t)kChunkCols), lane);
           } else if (kFp8) {
@@ -387,20 +287,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
         finish_row(pend_row, pend_old);
     }
     // keep the L2->SM pipe busy across the barrier: fetch the head of next round's first unit
-    if (kRing && gw < U && k + 1u < p.max_iter) {
-      // the ring is empty here: the head of next round's first unit goes into it across the barrier
-      const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - gw) : gw;
-      const uint32_t rl = u / nch;
-      const uint32_t ch = u - rl * nch;
-      const uint32_t len = min((uint32_t)kChunkCols, N - ch * (uint32_t)kChunkCols);
-      const float* seg = p.A + (size_t)rl * N + (size_t)ch * kChunkCols;
-      const uint32_t nb = (len + kRingBatch - 1u) / kRingBatch;
-      __syncwarp();
-      for (uint32_t b = 0; b < min((uint32_t)PF_BATCHES, nb); b++)
-        ring_issue<(PF_BATCHES > 0 ? PF_BATCHES : 1)>(ring, seg + b * kRingBatch, min(kRingBatch, len - b * kRingBatch), lane);
-      ring_pre = min((uint32_t)PF_BATCHES, nb);
-    }
-    if (!kRing && PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {
+    if (PF_BATCHES > 0 && !resident && gw < U && k + 1u < p.max_iter) {
       __syncwarp();
       if (lane == 0) {
         const uint32_t u = (p.sweep && ((k + 1u) & 1u)) ? (U - 1u - gw) : gw;
@@ -513,12 +400,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
     }
   }
   // a prefetch issued for a round that did not run must land before the CTA exits
-  if (!kRing && PF_BATCHES > 0 && lane == 0)
+  if (PF_BATCHES > 0 && lane == 0)
     for (; pf_consumed < pf_issued; pf_consumed++)
       mbar_wait(my_bar, pf_consumed & 1u, p.timeout_ns);
-  if (kRing)
-    for (; ring.consumed < ring.issued; ring.consumed++)
-      mbar_wait(ring.bars + ring.consumed % (uint32_t)PF_BATCHES, (ring.consumed / (uint32_t)PF_BATCHES) & 1u, p.timeout_ns);
 }
 
 } // namespace st

@@ -62,21 +62,15 @@ is_known_kernel_id(int id)
 }
 
 // dynamic shared memory of the resident-e kernel: prefetch slots | e | mbarriers
-// (ring_slots > 0: the scalar-unit build's per-warp ring of bulk-copy slots -- 1028 floats and one mbarrier each --
-// instead of the prefetch slot)
-constexpr int kScalarRingSlots = 2;
 inline size_t
-sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t* mbar_offset, int ring_slots = 0)
+sc_smem_bytes(int threads, int pf_batches, uint32_t cols, uint32_t* mbar_offset)
 {
-  size_t off = ring_slots ? (size_t)(threads / 32) * ring_slots * 1028 * sizeof(float)
-                          : (size_t)(threads / 32) * pf_batches * 1024 * sizeof(float);
+  size_t off = (size_t)(threads / 32) * pf_batches * 1024 * sizeof(float);
   off += (size_t)cols * sizeof(float);
   off = (off + 15) & ~(size_t)15;
   *mbar_offset = (uint32_t)off;
-  return off + (size_t)(threads / 32) * (ring_slots ? ring_slots : 1) * sizeof(uint64_t);
+  return off + (size_t)(threads / 32) * sizeof(uint64_t);
 }
-// the ring is worth its shared memory only while the whole CTA stays under the 195 KB carve-out step (below)
-constexpr size_t kScalarRingSmemLimit = 194 * 1024;
 // The shared-memory carve-out of an SM comes in steps (..., 164, 196, 228 KB; a CTA can use the step minus 1 KB) and
 // what is left of the 256 KB is L1, which the streaming loads pass through.  Measured in round 2
 // (profiles/r2_c5_endgame_v2_n1.json, r2_c6_endgame_v3_n1.json): Hilbert 32768 -- 64 KB of slots + 128 KB of e --

@@ -639,7 +639,6 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
   uint32_t rows_cap = 0;
   size_t smem = 0;
   const ScConfig* sc = nullptr;
-  bool sc_ring = false;
   const bool readonly4 = vec4 && form == kFormReadOnly;
   int cluster_ctas = 0;
   if (opt.kernel == kClusterKernelId || (opt.kernel == 0 && readonly4 && !shard && !narrow && !acc64 && dim <= (uint32_t)kClusterCols)) {
@@ -681,19 +680,7 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       int g, t;
       uint32_t cap, moff = 0;
       shape(c.max_threads, false, &g, &t, &cap);
-      size_t need = sc_smem_bytes(t, c.pf_batches, dim, &moff);
-      // scalar units: through the per-warp ring of bulk copies when the matrix is 16-byte aligned and the ring fits
-      // next to e under the carve-out step (N <= ~15800 at 512 threads); st_options.sweep bit 4 keeps the 4-byte loads
-      sc_ring = false;
-      if (readonly1 && aligned16(d_rows) && !(opt.sweep & 16)) {
-        uint32_t rmoff = 0;
-        const size_t rneed = sc_smem_bytes(t, 0, dim, &rmoff, kScalarRingSlots);
-        if (rneed <= kScalarRingSmemLimit) {
-          sc_ring = true;
-          need = rneed;
-          moff = rmoff;
-        }
-      }
+      const size_t need = sc_smem_bytes(t, c.pf_batches, dim, &moff);
       if (need <= kSmemLimit) {
         sc = &c;
         grid = g;
@@ -801,11 +788,6 @@ Context::solve(const float* d_rows, uint32_t dim, const st_options& opt, Shard* 
       launch_cluster<kStopRelative>(p, cluster_ctas, smem, stream_);
     else
       launch_cluster<kStopAbsolute>(p, cluster_ctas, smem, stream_);
-  } else if (sc && readonly1 && sc_ring) {
-    if (stop == kStopRelative)
-      launch_cooperative(round_loop_sc_kernel<512, kScalarRingSlots, kStopRelative, float, float, 1>, p, grid, threads, smem, stream_);
-    else
-      launch_cooperative(round_loop_sc_kernel<512, kScalarRingSlots, kStopAbsolute, float, float, 1>, p, grid, threads, smem, stream_);
   } else if (sc && readonly1) {
     if (stop == kStopRelative)
       launch_cooperative(round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>, p, grid, threads, smem, stream_);

@@ -219,17 +219,6 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
         uint32_t moff = 0;
         (void)cap;
         r.smem = sc_smem_bytes((int)r.threads, pf, dim, &moff);
-        // scalar units go through the ring of bulk copies like Context::solve decides: aligned rows, ring fits, sweep bit 4 clear
-        bool ring = false;
-        if (scalar_units && (reinterpret_cast<uintptr_t>(p.A) & 15u) == 0 && !(o->sweep & 16)) {
-          uint32_t rmoff = 0;
-          const size_t rneed = sc_smem_bytes((int)r.threads, 0, dim, &rmoff, kScalarRingSlots);
-          if (rneed <= kScalarRingSmemLimit) {
-            ring = true;
-            r.smem = rneed;
-            moff = rmoff;
-          }
-        }
         if (r.smem > kSmemLimit)
           throw std::string("resident-e configuration does not fit shared memory");
         p.mbar_offset = moff;
@@ -242,10 +231,7 @@ emu_solve(const void* mat, uint32_t dim, const emu_opts* o, float* eigen_val, fl
           p.row_done = r.row_done.data();
         }
         kernel = o->stop ? sc_kernel<kStopRelative>(pf, bf16, acc64, fp8) : sc_kernel<kStopAbsolute>(pf, bf16, acc64, fp8);
-        if (scalar_units && ring)
-          kernel = o->stop ? round_loop_sc_kernel<512, kScalarRingSlots, kStopRelative, float, float, 1>
-                           : round_loop_sc_kernel<512, kScalarRingSlots, kStopAbsolute, float, float, 1>;
-        else if (scalar_units)
+        if (scalar_units)
           kernel = o->stop ? round_loop_sc_kernel<512, 0, kStopRelative, float, float, 1>
                            : round_loop_sc_kernel<512, 0, kStopAbsolute, float, float, 1>;
       } else if (kid == 2) {

@@ -156,12 +156,8 @@ emu_bump(uint64_t* bar)
   *bar += 1;
 }
 inline void
-mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+mbar_arrive_expect_tx(uint64_t*, uint32_t)
 {
-  if (bytes == 0u) { // nothing to wait for: the arrival itself completes the phase (count 1, no pending bytes)
-    EMU_RELEASE(bar);
-    emu_bump(bar);
-  }
 }
 EMU_NO_TSAN inline bool
 mbar_try_wait(uint64_t* bar, uint32_t parity)

@@ -109,19 +109,17 @@ def test_rows_of_several_work_units(kernel, dynamic):
 def test_resident_e_kernel_on_scalar_units(dim, threads, ctas, dynamic):
     mat = A3 if dim == 3 else U(dim)
     want = expect(mat)
-    same_bits(emu.solve(mat, dim, kernel=11, threads=threads, ctas=ctas, dynamic=dynamic), want)             # ring of bulk copies
-    same_bits(emu.solve(mat, dim, kernel=11, threads=threads, ctas=ctas, dynamic=dynamic, sweep=17), want)   # 4-byte loads
+    same_bits(emu.solve(mat, dim, kernel=11, threads=threads, ctas=ctas, dynamic=dynamic), want)
     same_bits(emu.solve(mat, dim, kernel=1, threads=threads, ctas=ctas), want)       # the general loop's order, bit for bit
 
 
 def test_resident_e_kernel_on_scalar_units_extras():
     mat = U(8195)                                                            # two units per row: 8192 + 3 columns
     same_bits(emu.solve(mat, 8195, kernel=11, threads=128, ctas=6, dynamic=1, max_iter=3), expect(mat, max_iter=3))
-    same_bits(emu.solve(mat, 8195, kernel=11, threads=128, ctas=6, dynamic=1, max_iter=3, sweep=17), expect(mat, max_iter=3))
     same_bits(emu.solve(mat, 8195, kernel=11, threads=128, ctas=3, world=2, max_iter=3), expect(mat, max_iter=3))
-    mat = U(2051)                                                            # three batches per unit, the last of 3 floats
+    mat = U(2051)                                                            # 2048 + 3 columns
     same_bits(emu.solve(mat, 2051, kernel=11, threads=64, ctas=5, dynamic=1, max_iter=5), expect(mat, max_iter=5))
-    mat = U(1025)                                                            # 1025^2 % 4 == 1: the matrix's last float cannot be bulk-copied
+    mat = U(1025)
     same_bits(emu.solve(mat, 1025, kernel=11, threads=64, ctas=5, max_iter=5), expect(mat, max_iter=5))
     mat = U(1001)                                                            # sharded, ranks of 333 / 334 / 334 rows
     same_bits(emu.solve(mat, 1001, kernel=11, threads=64, ctas=3, world=3), expect(mat))

@@ -2,6 +2,7 @@
 # Round 2, call 25 (1 GPU): narrow storage on 4-element units (fp8: 32-bit loads, bf16: 64-bit loads -- conflict-free reads of
 # the eigenvector from shared memory), and the scalar-unit ring of bulk copies for dim % 4 != 0 against the 4-byte loads
 # (--sweep 17).  Parity tests first (the multi-GiB cases are left to the full suite at the end of the round).
+# (Ran at commit 22a4650: the ring and its --sweep 17 switch were removed after this measurement.)
 set -u
 O=gpurun_out/r2c25; mkdir -p $O
 timeout 600 python -m pytest tests/test_zzz_gpu_fp8_storage.py tests/test_zzz_gpu_bf16_storage.py tests/test_zz_gpu_bitexact.py -m gpu -q -x -k "not beyond" > $O/pytest.txt 2>&1; tail -4 $O/pytest.txt
