@@ -373,7 +373,10 @@ dot_acc_fp8(uint32_t w, float4 e, float acc)
 }
 
 // One row segment of fp8 storage, one warp: `nw` words of four elements starting at `a`; the matching eigenvector
-// entries are es[j] (float4, shared memory, pre-scaled).  Same loop shape as row_dot_readonly<1>: LDN 4-byte loads in flight.
+// entries are es[j] (float4, shared memory, pre-scaled).  Same loop shape as row_dot_readonly<1>: LDN 4-byte loads in
+// flight per lane, all issued before the first is decoded.  (Software-pipelining the loop over half-batches -- the next
+// 16 words in flight while 16 are decoded -- measured SLOWER: 401 against 309 us per round at Hilbert 32768,
+// profiles/r2_c26_storage_and_ragged.json against r2_c25_storage_fp8_bf16_word_units.json; reverted.)
 template<int LDN>
 __device__ __forceinline__ float
 row_dot_fp8(const uint32_t* __restrict__ a, const float4* es, uint32_t nw, int lane)

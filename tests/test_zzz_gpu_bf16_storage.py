@@ -6,10 +6,8 @@ contract is exact all the same: bf16 -> fp32 is exact, so a bf16-storage solve m
 an fp32 solve of the bf16-rounded matrix in the fp32 kernels' own order (the kernels reduce 4-element words), which
 is what the oracle computes with to_bf16() + SUM_CUDA (pinned on the CPU in tests/test_oracle_cuda_order.py).
 
-STATUS: this code path was written after round 1's GPU budget was spent.  Its logic has been executed
-on the CPU emulation harness (tests/test_kernel_logic_emulated.py: both kernels, several work units
-per row, sharded, relative stop, the conversion kernel) and is bit-identical to the oracle there; this
-file is its first run on hardware, and it sorts last so that it cannot disturb the tests before it.
+Its logic also runs on the CPU emulation harness (tests/test_kernel_logic_emulated.py: both kernels, several work
+units per row, sharded, relative stop, the conversion kernel), bit-identical to the oracle there.
 """
 import numpy as np
 import pytest
