@@ -138,6 +138,80 @@ def test_in_process_sharded_solve_with_local_link(world):
         s.close()
 
 
+@pytest.mark.parametrize("case", ["ragged-1001", "bf16-1000", "fp8-1000", "fp8-8196"])
+def test_in_process_sharded_storage_formats_and_ragged_dims(case):
+    """The sharded builds added after the first multi-GPU runs, two GPUs in one process: dim % 4 != 0 on the resident-e
+    kernel's scalar units (ranks of 500 and 501 rows), bf16 storage, fp8 storage with each rank's own row scales
+    (st_shard_solve_fp8; 8196: two work units per row).  Every rank returns the oracle's bits."""
+    world = 2
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs in one process")
+    import ctypes
+    import threading
+    from eigen_value_b200 import Solver
+    from eigen_value_b200._lib import StResult, check
+    from eigen_value_b200.similarity_transform import make_options
+
+    kind, dim = case.split("-")
+    dim, seed = int(dim), 0x5EED0002
+    cap = 4 if dim > 4100 else 1000
+    solvers = [Solver(g) for g in range(world)]
+    lib = solvers[0].lib
+    shards = []
+    for g in range(world):
+        sh = ctypes.c_void_p()
+        check(lib.st_shard_create(solvers[g].ctx, dim, g, world, ctypes.byref(sh)), "st_shard_create")
+        shards.append(sh)
+    check(lib.st_shard_link_local((ctypes.c_void_p * world)(*[s.value for s in shards]), world), "st_shard_link_local")
+    mat = (oracle.uniform(dim, seed) + np.float32(0.25)).astype(np.float32)
+    rows, scales, vecs = [], [], []
+    for g in range(world):
+        r0, n = ctypes.c_uint32(), ctypes.c_uint32()
+        check(lib.st_shard_rows(shards[g], ctypes.byref(r0), ctypes.byref(n)), "st_shard_rows")
+        d32 = solvers[g].upload(mat[r0.value:r0.value + n.value])
+        if kind == "bf16":
+            rows.append(solvers[g].to_bf16(d32, n.value * dim))
+            scales.append(None)
+        elif kind == "fp8":
+            codes, sc = solvers[g].to_fp8(d32, n.value, dim)          # every rank quantises its own rows
+            rows.append(codes)
+            scales.append(sc)
+        else:
+            rows.append(d32)
+            scales.append(None)
+        solvers[g].synchronize()
+        vecs.append(solvers[g].alloc(4 * dim))
+    out = [None] * world
+
+    def work(g):
+        o = make_options(lib, max_iter=cap)
+        res = StResult()
+        if kind == "fp8":
+            rc = lib.st_shard_solve_fp8(shards[g], rows[g].ptr, scales[g].ptr, ctypes.byref(o), vecs[g].ptr, ctypes.byref(res))
+        elif kind == "bf16":
+            rc = lib.st_shard_solve_bf16(shards[g], rows[g].ptr, ctypes.byref(o), vecs[g].ptr, ctypes.byref(res))
+        else:
+            rc = lib.st_shard_solve(shards[g], rows[g].ptr, ctypes.byref(o), vecs[g].ptr, ctypes.byref(res))
+        out[g] = (rc, res.eigen_val, res.iter_count, res.kernel_id, vecs[g].download(np.float32, dim) if rc == 0 else None)
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert all(o is not None and o[0] == 0 for o in out), out
+    stored = oracle.to_bf16(mat)[0] if kind == "bf16" else oracle.to_fp8_rows(mat)[0] if kind == "fp8" else mat
+    o_val, o_vec, _, o_it = oracle.similarity_transform(stored, form=oracle.FORM_READONLY, sum_mode=oracle.SUM_CUDA, max_itr=cap)
+    for rc, val, it, kid, vec in out:
+        assert kid == 11 and it == o_it and np.float32(val) == o_val and np.array_equal(vec, o_vec)
+    for v in vecs:
+        v.free()
+    for sh in shards:
+        lib.st_shard_destroy(sh)
+    for s in solvers:
+        s.close()
+
+
 def test_missing_peer_turns_into_a_timeout_error_not_a_hang():
     """Two linked shards, only rank 0 calls the collective solve: its round barrier waits for rank 1's flag, gives up
     after the device-side timeout (10 s) and the call returns ST_ERR_TIMEOUT -- no hang, no crash.  The shard group is
