@@ -13,10 +13,11 @@
 // cross-GPU exchange, the canonical row reduction) and the GENERAL loop: any N, both forms,
 // column-chunked scale vector.  The specialised loops build on it:
 //   kernels_cluster.cuh  N <= 512    matrix resident in the shared memory of one cluster
-//   kernels_sc.cuh       N <= 32768  eigenvector resident in shared memory (the default)
+//   kernels_sc.cuh       N <= 32768  eigenvector resident in shared memory (the default; dim % 4 != 0 on scalar units)
+//   kernels_wide.cuh     N >  32768  the same work-unit scheduling, eigenvector staged one 32768-column window at a time
 //
 // Opt-in variants are template parameters, so the default instantiations stay exactly the measured
-// code: STOP (the reference's absolute stop test | relative), T (fp32 | bf16 STORAGE of the matrix),
+// code: STOP (the reference's absolute stop test | relative), T (fp32 | bf16 | fp8 STORAGE of the matrix),
 // ACC (fp32 | fp64 accumulators).  None of them changes the evaluation order.
 //
 // The small standalone kernels at the bottom are the per-kernel entry points mirroring the

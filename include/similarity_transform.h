@@ -110,12 +110,13 @@ typedef struct st_options
                         no in-kernel time stamps                                                 */
   int32_t threads;   /* CTA size of the round kernel, 0 = default                   */
   int32_t ctas;      /* grid size of the round kernel, 0 = one per SM               */
-  int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, one GPU), resident-e
-                        kernel (N <= 32768), general chunked loop otherwise; 1 = general loop,
-                        10-13 = resident-e configurations (prefetch slot of 2 / 0 / 3 / 1 x 4 KB per
-                        warp), 20 = on-chip cluster kernel; any other value is refused (the TMA-ring,
-                        256- / 1024-thread and L2-prefetch variants of round 1 lost on hardware and
-                        were removed)                                                              */
+  int32_t kernel;    /* 0 = automatic: on-chip cluster kernel (N <= 512, dim % 4 == 0, one GPU),
+                        resident-e kernel (N <= 32768; dim % 4 != 0, bf16 and fp8 storage on
+                        configuration 11), wide kernel above (general chunked loop for what the wide
+                        kernel is not built for); 1 = general loop, 2 = wide kernel, 10-13 = resident-e
+                        configurations (prefetch slot of 2 / 0 / 3 / 1 x 4 KB per warp), 20 = on-chip
+                        cluster kernel; any other value is refused (the TMA-ring, 256- / 1024-thread
+                        and L2-prefetch variants of round 1 lost on hardware and were removed)         */
   int32_t l2_keep_pct; /* 0..100: share of each CTA's rows loaded with an L2 evict_last policy
                           (the rest evict_first) so that part of A stays L2-resident across
                           rounds; 0 = no cache hints                                       */
