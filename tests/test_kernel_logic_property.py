@@ -16,18 +16,19 @@ import emu  # noqa: E402
 
 @st.composite
 def cases(draw):
-    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 20, 2, 2]))
+    kernel = draw(st.sampled_from([1, 1, 13, 10, 12, 11, 11, 20, 2, 2]))
     dim = draw(st.integers(1, 1100))
-    if kernel != 1:
-        dim = max(4, dim - dim % 4)                       # vector kernels: dim % 4 == 0
+    if kernel not in (1, 11):
+        dim = max(4, dim - dim % 4)                       # vector kernels: dim % 4 == 0 (11 also runs on scalar units)
     if kernel == 20:
         dim = min(dim, 512)
     world = 1 if kernel == 20 else draw(st.integers(1, min(8, dim)))
-    bf16 = kernel in (1, 11) and dim % 8 == 0 and draw(st.booleans())
-    acc64 = (not bf16) and kernel in (1, 13, 10, 12) and draw(st.booleans())
-    form = draw(st.integers(0, 1)) if (kernel == 1 and not bf16 and not acc64) else 0
+    storage = draw(st.sampled_from(["f32", "f32", "bf16", "fp8"])) if (kernel in (1, 11) and dim % 4 == 0) else "f32"
+    bf16, fp8 = storage == "bf16", storage == "fp8"
+    acc64 = storage == "f32" and kernel in (1, 13, 10, 12) and draw(st.booleans())
+    form = draw(st.integers(0, 1)) if (kernel == 1 and storage == "f32" and not acc64) else 0
     stop = draw(st.integers(0, 1))
-    return dict(kernel=kernel, dim=dim, world=world, bf16=bf16, acc64=acc64, form=form, stop=stop,
+    return dict(kernel=kernel, dim=dim, world=world, bf16=bf16, fp8=fp8, acc64=acc64, form=form, stop=stop,
                 threads=draw(st.sampled_from([32, 64, 96, 128, 256, 512])), ctas=draw(st.integers(1, 9)),
                 dynamic=draw(st.integers(0, 1)), sweep=draw(st.integers(0, 1)),
                 eps=draw(st.sampled_from([1e-3, 1e-5])), max_iter=draw(st.sampled_from([1, 2, 7, 40])),
@@ -39,15 +40,16 @@ def cases(draw):
 def test_any_shape_any_option_matches_the_oracle(c):
     dim = c["dim"]
     mat = oracle.hilbert(dim) if c["hilbert"] else (oracle.uniform(dim, c["seed"]) + np.float32(0.25)).astype(np.float32)
-    sum_mode, data = oracle.SUM_CUDA, mat
+    sum_mode, data, scale = oracle.SUM_CUDA, mat, None
     if c["bf16"]:
-        mat, data = oracle.to_bf16(mat)
-        sum_mode = oracle.SUM_CUDA_BF16
+        mat, data = oracle.to_bf16(mat)                   # 4-element words in the fp32 kernels' order: SUM_CUDA
+    elif c["fp8"]:
+        mat, data, scale = oracle.to_fp8_rows(mat)        # the same, on the dequantised matrix
     elif c["acc64"]:
         sum_mode = oracle.SUM_CUDA_F64
     got = emu.solve(data, dim, kernel=c["kernel"], threads=c["threads"], ctas=c["ctas"], world=c["world"], form=c["form"],
                     stop=c["stop"], dynamic=c["dynamic"], sweep=c["sweep"], eps=c["eps"], max_iter=c["max_iter"],
-                    bf16=c["bf16"], acc64=c["acc64"])
+                    bf16=c["bf16"], acc64=c["acc64"], fp8_scale=scale)
     want = oracle.similarity_transform(mat, form=oracle.FORM_INPLACE if c["form"] else oracle.FORM_READONLY, sum_mode=sum_mode,
                                        eps=c["eps"], max_itr=c["max_iter"], stop=c["stop"], ranks=c["world"])
     val, vec, it, passes, agree = got
