@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_kernel(const RoundP
 
   float m_prev = 1.f;
   for (uint32_t k = 0;; ++k) {
-    const uint32_t par = (k + p.flip) & 1u; // buffer / flag set of this round (sharded: see RoundParams::flip)
+    const uint32_t par = (k + p.flip) & 1u; // buffer set of this round (sharded: see RoundParams::flip)
     const float* Sprev = p.S[par ^ 1u];
     const float* Eprev = p.E[par ^ 1u];
     float* Scur = p.S[par];

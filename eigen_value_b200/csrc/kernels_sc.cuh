@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) round_loop_sc_kernel(const Rou
   }
 
   for (uint32_t k = 0;; ++k) {
-    const uint32_t par = (k + p.flip) & 1u; // buffer / flag set of this round
+    const uint32_t par = (k + p.flip) & 1u; // buffer set of this round
     float* Scur = p.S[par];
     float wmax = 0.f; // lane 0: largest row sum this warp published this round; the reference zero-fills the max cell (:169)
     const bool backward = !resident && p.sweep && (k & 1); // resident units never change owner

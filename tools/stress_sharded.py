@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Soak test of the fused cross-GPU exchange (round barrier with flags by round parity, solves starting on the parity
-the previous one did not end on, flags never reset): thousands of sharded solves back to back on one shard group,
+"""Soak test of the fused cross-GPU exchange (flat round barrier whose counters and max slots are never reset, solves
+starting on the buffer parity the previous one did not end on): thousands of sharded solves back to back on one shard group,
 round caps chosen so that consecutive solves end on either parity, every result compared bit for bit with the first
 solve of the same (size, cap) and across ranks.  One JSON line from rank 0.
 
